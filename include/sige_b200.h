@@ -1,0 +1,198 @@
+/*
+ * sige_b200.h — C-ABI of the B200-native SIGE tile-sparse hot path.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and a cudaStream_t; no torch
+ * types.  It replaces the reference's pybind surface `sige.cuda`
+ * (reference sige/cuda/pybind_cuda.cpp:5-12) and the libtorch host wrappers
+ * behind it.  INTEGRATION.md shows the binding a maintainer of the reference
+ * would add (ctypes / pybind stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     available from sige_last_error() (thread-local).  N == 0 is a no-op.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - the caller owns every buffer, including outputs (allocation stays with the
+ *     caller's allocator); inputs are never modified.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises the host, so every call is CUDA-graph capturable.
+ *   - activations are 4-D, logical (B, C, H, W).  `layout` says how they sit in
+ *     memory: SIGE_NCHW (the reference's layout) or SIGE_NHWC (channels-last, the
+ *     layout the tensor-core path wants).  Tile stacks are logical
+ *     (B*N, C, R, S), tile row b*N + i (reference sige/cuda/gather_kernel.cu:30),
+ *     stored in the same layout family as the activations.
+ *   - active index lists are int32 [N,2] = (h, w) tile origins in the frame of
+ *     the gather input; may be negative (reference sige/utils.py:31-37).
+ */
+#ifndef SIGE_B200_H_
+#define SIGE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIGE_B200_ABI_VERSION 1
+
+typedef enum { SIGE_F32 = 0, SIGE_F16 = 1, SIGE_BF16 = 2 } sige_dtype_t;
+typedef enum { SIGE_NCHW = 0, SIGE_NHWC = 1 } sige_layout_t;
+/* reference sige/common.cpp:11-23 (ActivationType, getActivationType) */
+typedef enum { SIGE_ACT_IDENTITY = 0, SIGE_ACT_SWISH = 1 } sige_act_t;
+
+typedef void *sige_stream_t; /* cudaStream_t */
+
+/*
+ * Broadcast operand (scale / shift / residual): a 4-D tensor whose every dim is
+ * either 1 or the full extent (reference sige/common.cpp:25-34 `broadcastable`,
+ * sige/cuda/common_cuda.cu:15-30 `binary_op_array_cuda`).  Element strides are
+ * explicit so that any memory layout can be passed; a size-1 dim is never
+ * multiplied by its stride.  ptr == NULL means "operand absent".
+ */
+typedef struct {
+    const void *ptr;
+    int dims[4];       /* B, C, H, W — each 1 or full */
+    int64_t stride[4]; /* element strides of B, C, H, W */
+    int dtype;         /* sige_dtype_t */
+} sige_bcast_t;
+
+/* ------------------------------------------------------------------------- */
+/* library                                                                    */
+/* ------------------------------------------------------------------------- */
+const char *sige_last_error(void);
+int sige_abi_version(void);
+/* "sm_100a" etc. — the architecture the kernels in this library were built for. */
+const char *sige_built_arch(void);
+/* reference sige/common.cpp:17-23: "identity" / "swish" -> sige_act_t, -1 if unknown
+ * (the reference has undefined behaviour for unknown names). */
+int sige_activation_from_name(const char *name);
+
+/* ------------------------------------------------------------------------- */
+/* a1: mask -> active tile origins      (reference sige/utils.py:8-37)        */
+/* ------------------------------------------------------------------------- */
+/*
+ * mask: uint8 [H, W] (non-zero = edited).  Writes up to `capacity` (h, w) pairs
+ * into idx_out in row-major order of the pooled grid and the total count into
+ * *count_out (device int32).  Bit-exact with the reference's pad -> max_pool2d ->
+ * nonzero chain.  The pooled grid has floor((H+padH)/strideH)+1 rows.
+ */
+int sige_reduce_mask(const uint8_t *mask, int H, int W, int R, int S, int strideH, int strideW,
+                     int padH, int padW, int32_t *idx_out, int capacity, int32_t *count_out,
+                     sige_stream_t stream);
+/* host helper: number of candidate tiles (upper bound for `capacity`) */
+int sige_reduce_mask_capacity(int H, int W, int R, int S, int strideH, int strideW, int padH,
+                              int padW);
+
+/* ------------------------------------------------------------------------- */
+/* a2: gather                 (reference sige/cuda/gather_kernel.cu:7-124)    */
+/* ------------------------------------------------------------------------- */
+/* out: tile stack (B*N, C, R, S).  Zero outside the image, applied AFTER the
+ * affine/activation (gather_kernel.cu:33-42). */
+int sige_gather(const void *x, int dtype, int layout, int B, int C, int H, int W, int R, int S,
+                const int32_t *idx, int N, const sige_bcast_t *scale, const sige_bcast_t *shift,
+                int act, int act_first, void *out, sige_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* a6: scatter                (reference sige/cuda/scatter_kernel.cu:8-44,76-117) */
+/* ------------------------------------------------------------------------- */
+/*
+ * x: stack (B*N, C, Ro, So).  y: cached full tensor (B, C, H, W) or NULL.
+ * out: (B, C, H, W).  If y != NULL and y != out the function first copies y into
+ * out (the reference's `y.clone()`, scatter_kernel.cu:89); with y == NULL (or
+ * y == out) the tiles are pasted in place into `out`.
+ * out[b,c,oy+r,ox+s] = x[...] (+ residual[b,c,oy+r,ox+s]), oy = (offH + iy)/strideH.
+ */
+int sige_scatter(const void *x, const void *y, void *out, int dtype, int layout, int B, int C,
+                 int H, int W, int Ro, int So, int offH, int offW, int strideH, int strideW,
+                 const int32_t *idx, int N, const sige_bcast_t *residual, sige_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* a7: scatter_with_block_residual (reference scatter_kernel.cu:46-74,119-146) */
+/* ------------------------------------------------------------------------- */
+/* out = scatter(x0 -> y0, residual = y1); then out += x1 - y1 on the shortcut tiles
+ * idx1 (raw origins, no offset/stride).  Same in-place convention as sige_scatter. */
+int sige_scatter_with_block_residual(const void *x0, const void *y0, const void *x1,
+                                     const void *y1, void *out, int dtype, int layout, int B,
+                                     int C, int H, int W, int R0, int S0, int R1, int S1, int offH,
+                                     int offW, int strideH, int strideW, const int32_t *idx0,
+                                     int N0, const int32_t *idx1, int N1, sige_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* a5: get_scatter_map   (reference sige/cuda/scatter_gather_kernel.cu:69-98,164-188) */
+/* ------------------------------------------------------------------------- */
+/* map_out: int32 [H, W, 3] = (tile id, r, s) or -1. Fills -1 itself. */
+int sige_get_scatter_map(int H, int W, int R, int S, int kH, int kW, int offH, int offW,
+                         int strideH, int strideW, const int32_t *idx, int N, int32_t *map_out,
+                         sige_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* a4: scatter_gather    (reference sige/cuda/scatter_gather_kernel.cu:8-67,100-162) */
+/* ------------------------------------------------------------------------- */
+/* x: previous conv's output stack (B*N, C, Rx, Sx); y: cached (B, C, H, W);
+ * out: stack (B*N, C, R, S) for the next conv. */
+int sige_scatter_gather(const void *x, const void *y, int dtype, int layout, int B, int C, int H,
+                        int W, int Rx, int Sx, int R, int S, const int32_t *idx, int N,
+                        const int32_t *scatter_map, const sige_bcast_t *scale,
+                        const sige_bcast_t *shift, int act, int act_first, void *out,
+                        sige_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* a3 + fused forms: tile convolution                                         */
+/*   (reference sige/nn/base.py:85-92 -> F.conv2d on the stack; the fused forms */
+/*    replace the gather -> conv -> scatter call triple of                     */
+/*    diffusion/models/ddpm_arch/sige_fused_unet.py:111-128)                   */
+/* ------------------------------------------------------------------------- */
+
+/* Weight repack for the tensor-core path: OIHW (any dtype) -> [kH*kW][Cout][Cin]
+ * in `dst_dtype` (f16/bf16).  Run once per weight. */
+int sige_pack_conv_weight(const void *w_oihw, int src_dtype, int Cout, int Cin, int kH, int kW,
+                          void *w_packed, int dst_dtype, sige_stream_t stream);
+
+/* One source segment of the (virtually concatenated) conv input: NHWC. */
+typedef struct {
+    const void *ptr; /* [B, H>>up, W>>up, C] */
+    int C;           /* channels in this segment (multiple of 64 on the tensor-core path) */
+    int up;          /* 0, or 1 = nearest-neighbour x2 upsample applied on read */
+} sige_conv_src_t;
+
+typedef struct {
+    int dtype; /* SIGE_F16 / SIGE_BF16 (tensor cores) */
+    /* ---- source: where halo tiles are gathered from ---- */
+    int n_src;              /* 1 or 2 (channel concat of two tensors, torch.cat dim=1) */
+    sige_conv_src_t src[2];
+    int B, H, W;            /* logical input extent (after optional upsample) */
+    int src_is_stack;       /* 1: src[0] is a tile stack (B*N, R, S, C); origins are (0,0) */
+    const int32_t *idx;     /* [N,2] tile origins (input frame); unused for a stack source */
+    int N;                  /* active tiles per batch element */
+    int R, S;               /* halo tile extent */
+    /* ---- fused pre-op: act(x*scale+shift), zero outside the image ---- */
+    const float *scale;     /* fp32 [B or 1, Cin] or NULL */
+    const float *shift;     /* fp32 [B or 1, Cin] or NULL */
+    int affine_bstride;     /* 0 (shared) or Cin (per batch element) */
+    int act;                /* sige_act_t */
+    /* ---- conv ---- */
+    const void *w_packed;   /* [kH*kW][Cout][Cin], from sige_pack_conv_weight */
+    const float *bias;      /* fp32 [Cout] or NULL */
+    int Cin, Cout, kH, kW, stride;
+    /* ---- destination ---- */
+    void *dst;              /* NHWC [B, dH, dW, dC] or stack (B*N, Ro, So, dC) */
+    int dst_is_stack;
+    int dH, dW, dC, dst_c0; /* writes channels [dst_c0, dst_c0 + Cout) of dC */
+    int offH, offW;         /* output origin = (off + idx) / stride  (scatter_kernel.cu:29,33) */
+    const void *residual;   /* NHWC, same geometry as dst (rC channels), added in the epilogue; or NULL */
+    int rC, res_c0;
+} sige_tile_conv_t;
+
+/* Fused gather -> (affine+SiLU) -> conv (+bias) -> (+residual) -> scatter, one launch. */
+int sige_tile_conv(const sige_tile_conv_t *p, sige_stream_t stream);
+
+/* Generic (any dtype incl. fp32, any channel count, groups, dilation) tile convolution on a
+ * stack: x (M, Cin, R, S) -> out (M, Cout, Ro, So); w OIHW in `dtype`; fp32 accumulate. */
+int sige_tile_conv_generic(const void *x, const void *w, const void *bias, void *out, int dtype,
+                           int layout, int M, int Cin, int R, int S, int Cout, int kH, int kW,
+                           int strideH, int strideW, int dilH, int dilW, int groups,
+                           sige_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGE_B200_H_ */

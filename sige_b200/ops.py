@@ -1,0 +1,392 @@
+"""torch-facing wrappers of the C-ABI ops: same names, argument order and return convention as
+the reference's pybind module ``sige.cuda`` (reference sige/cuda/pybind_cuda.cpp:5-12), so the
+operator modules in ``sige_b200.nn`` call them exactly as the reference's modules call theirs.
+
+PyTorch is plumbing here: it owns device memory (outputs are allocated with ``torch.empty``) and
+the current stream; every byte of work is done by libsige_b200.so.  CUDA tensors only — a CPU or
+MPS tensor raises (north-star: no multi-backend dispatch, no CPU fallback).
+
+Extensions over the reference:
+  * dtypes fp32 / fp16 / bf16 (the reference is fp32-only, sige/nn/base.py:15);
+  * memory layout: NCHW-contiguous (the reference's) or channels-last; the stack a call returns
+    follows the layout of its input;
+  * ``out=`` / in-place forms used by the step engine (no per-call clone).
+"""
+from __future__ import annotations
+
+from ctypes import byref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import BF16, F16, F32, NCHW, NHWC, Bcast, ConvSrc, TileConv
+
+_DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+_ACTS = {"identity": _cabi.ACT_IDENTITY, "swish": _cabi.ACT_SWISH}
+
+# launch counter: bench.py reports it as `gpu_launches` (kernels of OUR library only)
+launch_count = 0
+
+
+def _act(name: str) -> int:
+    try:
+        return _ACTS[name]
+    except KeyError:
+        # the reference hits __builtin_unreachable() here (sige/common.cpp:22)
+        raise ValueError("Unknown activation: [%s]!!!" % name) from None
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise NotImplementedError("sige_b200 does not support dtype [%s]" % t.dtype) from None
+
+
+def _require_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "sige_b200 runs on CUDA (sm_100a) only; got a tensor on '%s'. "
+                "There is no CPU/MPS backend and no fallback." % t.device
+            )
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def layout_of(t: torch.Tensor) -> int:
+    """NHWC if the 4-D tensor is densely channels-last (and not also NCHW-dense)."""
+    if t.is_contiguous():
+        return NCHW
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return NHWC
+    return -1
+
+
+def _dense(t: torch.Tensor, layout: Optional[int] = None) -> Tuple[torch.Tensor, int]:
+    """Return (tensor, layout) with the tensor dense in `layout` (or in its own dense layout)."""
+    lo = layout_of(t)
+    if layout is None:
+        if lo >= 0:
+            return t, lo
+        return t.contiguous(), NCHW
+    if lo == layout:
+        return t, layout
+    if layout == NCHW:
+        return t.contiguous(), NCHW
+    # NHWC requested.  A tensor that is NCHW-dense with C == 1 or H == W == 1 is also NHWC-dense
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return t, NHWC
+    return t.contiguous(memory_format=torch.channels_last), NHWC
+
+
+def _empty_like_layout(shape, ref: torch.Tensor, layout: int) -> torch.Tensor:
+    fmt = torch.channels_last if layout == NHWC else torch.contiguous_format
+    return torch.empty(shape, dtype=ref.dtype, device=ref.device, memory_format=fmt)
+
+
+def _bcast(t: Optional[torch.Tensor]) -> Optional[Bcast]:
+    if t is None:
+        return None
+    if t.dim() != 4:
+        raise NotImplementedError("broadcast operand must be 4-D, got %d-D" % t.dim())
+    b = Bcast()
+    b.ptr = t.data_ptr()
+    for d in range(4):
+        b.dims[d] = t.shape[d]
+        b.stride[d] = t.stride(d)
+    b.dtype = _dt(t)
+    return b
+
+
+def _bref(b: Optional[Bcast]):
+    return None if b is None else byref(b)
+
+
+def _idx(active_indices: torch.Tensor) -> torch.Tensor:
+    if active_indices.dtype != torch.int32:
+        raise TypeError("active_indices must be int32 [N,2]")
+    return active_indices if active_indices.is_contiguous() else active_indices.contiguous()
+
+
+def _bump(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+# --------------------------------------------------------------------------------------
+# a1: reduce_mask on device          (reference sige/utils.py:8-37)
+# --------------------------------------------------------------------------------------
+def reduce_mask_cuda(mask: torch.Tensor, block_size, stride, padding) -> torch.Tensor:
+    """bool/uint8 [H,W] CUDA mask -> int32 [N,2] active tile origins, row-major, bit-exact."""
+    _require_cuda(mask)
+    H, W = mask.shape
+    m8 = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
+    m8 = m8.contiguous()
+    cap = _cabi.lib().sige_reduce_mask_capacity(H, W, block_size[0], block_size[1], stride[0], stride[1], padding[0], padding[1])
+    out = torch.empty((cap, 2), dtype=torch.int32, device=mask.device)
+    count = torch.empty((1,), dtype=torch.int32, device=mask.device)
+    with torch.cuda.device(mask.device):
+        _cabi.check(
+            _cabi.lib().sige_reduce_mask(m8.data_ptr(), H, W, block_size[0], block_size[1], stride[0], stride[1],
+                                         padding[0], padding[1], out.data_ptr(), cap, count.data_ptr(), _stream(mask)),
+            "sige_reduce_mask",
+        )
+    _bump()
+    n = int(count.item())  # the one host sync of set_masks (the reference's torch.nonzero syncs too)
+    return out[:n].contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# a2: gather                          (reference sige/cuda/gather_kernel.cu:69-124)
+# --------------------------------------------------------------------------------------
+def gather(x, bsize_h: int, bsize_w: int, active_indices, scale=None, shift=None, activation_name: str = "identity",
+           activation_first: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, active_indices, scale, shift)
+    x, layout = _dense(x)
+    idx = _idx(active_indices)
+    B, C, H, W = x.shape
+    N = idx.shape[0]
+    if out is None:
+        out = _empty_like_layout((B * N, C, bsize_h, bsize_w), x, layout)
+    if N == 0:
+        return out
+    sc, sh = _bcast(scale), _bcast(shift)
+    with torch.cuda.device(x.device):
+        _cabi.check(
+            _cabi.lib().sige_gather(x.data_ptr(), _dt(x), layout, B, C, H, W, bsize_h, bsize_w, idx.data_ptr(), N, _bref(sc),
+                                    _bref(sh), _act(activation_name), int(activation_first), out.data_ptr(), _stream(x)),
+            "sige_gather",
+        )
+    _bump()
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a6: scatter                         (reference sige/cuda/scatter_kernel.cu:76-117)
+# --------------------------------------------------------------------------------------
+def scatter(x, y, offset_h: int, offset_w: int, stride_h: int, stride_w: int, active_indices, residual=None,
+            out: Optional[torch.Tensor] = None, inplace: bool = False) -> torch.Tensor:
+    """out = copy(y) with the tiles of x pasted (+ residual).  ``inplace=True`` pastes into y itself
+    (the step engine's no-clone form; equals the reference's sparse_update, sige/nn/scatter.py:59-60)."""
+    _require_cuda(x, y, active_indices, residual)
+    y, layout = _dense(y)
+    x, _ = _dense(x, layout)
+    idx = _idx(active_indices)
+    B, C, H, W = y.shape
+    _, Cx, Ro, So = x.shape
+    if Cx != C:
+        raise ValueError("scatter: channel mismatch %d vs %d" % (Cx, C))
+    N = idx.shape[0]
+    if inplace:
+        out, y_ptr = y, None
+    else:
+        if out is None:
+            out = _empty_like_layout(y.shape, y, layout)
+        y_ptr = y.data_ptr()
+    res = _bcast(residual)
+    with torch.cuda.device(y.device):
+        _cabi.check(
+            _cabi.lib().sige_scatter(x.data_ptr() if N else None, y_ptr, out.data_ptr(), _dt(y), layout, B, C, H, W, Ro, So,
+                                     offset_h, offset_w, stride_h, stride_w, idx.data_ptr() if N else None, N, _bref(res),
+                                     _stream(y)),
+            "sige_scatter",
+        )
+    _bump(1 if inplace else 2)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a7: scatter_with_block_residual     (reference sige/cuda/scatter_kernel.cu:119-146)
+# --------------------------------------------------------------------------------------
+def scatter_with_block_residual(x0, y0, x1, y1, offset_h: int, offset_w: int, stride_h: int, stride_w: int,
+                                active_indices0, active_indices1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x0, y0, x1, y1, active_indices0, active_indices1)
+    y0, layout = _dense(y0)
+    x0, _ = _dense(x0, layout)
+    x1, _ = _dense(x1, layout)
+    y1, _ = _dense(y1, layout)
+    idx0, idx1 = _idx(active_indices0), _idx(active_indices1)
+    B, C, H, W = y0.shape
+    if out is None:
+        out = _empty_like_layout(y0.shape, y0, layout)
+    N0, N1 = idx0.shape[0], idx1.shape[0]
+    with torch.cuda.device(y0.device):
+        _cabi.check(
+            _cabi.lib().sige_scatter_with_block_residual(
+                x0.data_ptr() if N0 else None, y0.data_ptr(), x1.data_ptr() if N1 else None, y1.data_ptr(), out.data_ptr(),
+                _dt(y0), layout, B, C, H, W, x0.shape[2], x0.shape[3], x1.shape[2], x1.shape[3], offset_h, offset_w,
+                stride_h, stride_w, idx0.data_ptr() if N0 else None, N0, idx1.data_ptr() if N1 else None, N1, _stream(y0)),
+            "sige_scatter_with_block_residual",
+        )
+    _bump(3)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a5: get_scatter_map                 (reference sige/cuda/scatter_gather_kernel.cu:164-188)
+# --------------------------------------------------------------------------------------
+def get_scatter_map(H: int, W: int, bsize_h: int, bsize_w: int, ksize_h: int, ksize_w: int, offset_h: int, offset_w: int,
+                    stride_h: int, stride_w: int, active_indices) -> torch.Tensor:
+    _require_cuda(active_indices)
+    idx = _idx(active_indices)
+    out = torch.empty((H, W, 3), dtype=torch.int32, device=idx.device)
+    N = idx.shape[0]
+    with torch.cuda.device(idx.device):
+        _cabi.check(
+            _cabi.lib().sige_get_scatter_map(H, W, bsize_h, bsize_w, ksize_h, ksize_w, offset_h, offset_w, stride_h, stride_w,
+                                             idx.data_ptr() if N else None, N, out.data_ptr(), _stream(idx)),
+            "sige_get_scatter_map",
+        )
+    _bump(2)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a4: scatter_gather                  (reference sige/cuda/scatter_gather_kernel.cu:100-162)
+# --------------------------------------------------------------------------------------
+def scatter_gather(x, y, bsize_h: int, bsize_w: int, active_indices, scatter_map, scale=None, shift=None,
+                   activation_name: str = "identity", activation_first: bool = False,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, y, active_indices, scatter_map, scale, shift)
+    y, layout = _dense(y)
+    x, _ = _dense(x, layout)
+    idx = _idx(active_indices)
+    B, C, H, W = y.shape
+    N = idx.shape[0]
+    if out is None:
+        out = _empty_like_layout((B * N, C, bsize_h, bsize_w), y, layout)
+    if N == 0:
+        return out
+    if x.shape[1] != C:
+        raise ValueError("scatter_gather: channel mismatch %d vs %d" % (x.shape[1], C))
+    smap = scatter_map if scatter_map.is_contiguous() else scatter_map.contiguous()
+    sc, sh = _bcast(scale), _bcast(shift)
+    with torch.cuda.device(y.device):
+        _cabi.check(
+            _cabi.lib().sige_scatter_gather(x.data_ptr(), y.data_ptr(), _dt(y), layout, B, C, H, W, x.shape[2], x.shape[3],
+                                            bsize_h, bsize_w, idx.data_ptr(), N, smap.data_ptr(), _bref(sc), _bref(sh),
+                                            _act(activation_name), int(activation_first), out.data_ptr(), _stream(y)),
+            "sige_scatter_gather",
+        )
+    _bump()
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a3: tile convolution
+# --------------------------------------------------------------------------------------
+def pack_conv_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """OIHW -> [kH*kW, Cout, Cin] in `dtype` (f16/bf16) for the tensor-core kernel."""
+    _require_cuda(weight)
+    w = weight.detach().contiguous()
+    Cout, Cin, kH, kW = w.shape
+    out = torch.empty((kH * kW, Cout, Cin), dtype=dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        _cabi.check(
+            _cabi.lib().sige_pack_conv_weight(w.data_ptr(), _dt(w), Cout, Cin, kH, kW, out.data_ptr(), _DTYPES[dtype], _stream(w)),
+            "sige_pack_conv_weight",
+        )
+    _bump()
+    return out
+
+
+def tile_conv_tc_supported(x: torch.Tensor, weight: torch.Tensor, stride, dilation, groups) -> bool:
+    """Can the tensor-core kernel take this stack convolution?  (north-star: tensor cores where
+    channels >= 64, CUDA-core kernel otherwise.)"""
+    return (
+        x.dtype in (torch.float16, torch.bfloat16)
+        and groups == 1
+        and tuple(dilation) == (1, 1)
+        and stride[0] == stride[1]
+        and weight.shape[1] % 64 == 0
+        and weight.shape[0] % 8 == 0
+        and x.shape[2] >= weight.shape[2] and x.shape[3] >= weight.shape[3]
+        and ((x.shape[2] - weight.shape[2]) // stride[0] + 1) * ((x.shape[3] - weight.shape[3]) // stride[1] + 1) <= 128
+        and x.shape[2] * x.shape[3] <= 288
+    )
+
+
+def tile_conv_descriptor() -> TileConv:
+    return TileConv()
+
+
+def launch_tile_conv(desc: TileConv, stream: int) -> None:
+    _cabi.check(_cabi.lib().sige_tile_conv(byref(desc), stream), "sige_tile_conv")
+    _bump()
+
+
+def tile_conv_stack(x: torch.Tensor, w_packed: torch.Tensor, bias_f32: Optional[torch.Tensor], ksize: Tuple[int, int],
+                    stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Tensor-core conv on a stack: x (M, Cin, R, S) channels-last -> (M, Cout, Ro, So) channels-last.
+    Equivalent of F.conv2d(x, w, b, stride, padding=0) (reference sige/nn/base.py:88-89)."""
+    _require_cuda(x, w_packed, bias_f32)
+    x, _ = _dense(x, NHWC)
+    M, Cin, R, S = x.shape
+    taps, Cout, Cin_w = w_packed.shape
+    kH, kW = ksize
+    if Cin_w != Cin or taps != kH * kW:
+        raise ValueError("tile_conv_stack: weight does not match input")
+    Ro, So = (R - kH) // stride + 1, (S - kW) // stride + 1
+    if out is None:
+        out = _empty_like_layout((M, Cout, Ro, So), x, NHWC)
+    if M == 0:
+        return out
+    d = TileConv()
+    d.dtype = _dt(x)
+    d.n_src = 1
+    d.src[0].ptr = x.data_ptr(); d.src[0].C = Cin; d.src[0].up = 0
+    d.B, d.H, d.W = 1, R, S
+    d.src_is_stack = 1
+    d.idx = None
+    d.N = M
+    d.R, d.S = R, S
+    d.scale = None; d.shift = None; d.affine_bstride = 0; d.act = 0
+    d.w_packed = w_packed.data_ptr()
+    d.bias = None if bias_f32 is None else bias_f32.data_ptr()
+    d.Cin, d.Cout, d.kH, d.kW, d.stride = Cin, Cout, kH, kW, stride
+    d.dst = out.data_ptr()
+    d.dst_is_stack = 1
+    d.dH, d.dW, d.dC, d.dst_c0 = Ro, So, Cout, 0
+    d.offH = d.offW = 0
+    d.residual = None; d.rC = 0; d.res_c0 = 0
+    with torch.cuda.device(x.device):
+        launch_tile_conv(d, _stream(x))
+    return out
+
+
+def tile_conv_generic(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride, dilation, groups: int,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CUDA-core conv on a stack, any dtype/shape; fp32 accumulate (F.conv2d(..., padding=0))."""
+    _require_cuda(x, weight, bias)
+    x, layout = _dense(x)
+    w = weight.detach()
+    if w.dtype != x.dtype:
+        w = w.to(x.dtype)
+    w = w.contiguous()
+    b = None
+    if bias is not None:
+        b = bias.detach()
+        if b.dtype != x.dtype:
+            b = b.to(x.dtype)
+        b = b.contiguous()
+    M, Cin, R, S = x.shape
+    Cout, _, kH, kW = w.shape
+    Ro = (R - dilation[0] * (kH - 1) - 1) // stride[0] + 1
+    So = (S - dilation[1] * (kW - 1) - 1) // stride[1] + 1
+    if out is None:
+        out = _empty_like_layout((M, Cout, Ro, So), x, layout)
+    if M == 0:
+        return out
+    with torch.cuda.device(x.device):
+        _cabi.check(
+            _cabi.lib().sige_tile_conv_generic(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(),
+                                               _dt(x), layout, M, Cin, R, S, Cout, kH, kW, stride[0], stride[1], dilation[0],
+                                               dilation[1], groups, _stream(x)),
+            "sige_tile_conv_generic",
+        )
+    _bump()
+    return out
