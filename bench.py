@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — DDPM 256x256 denoising steps/sec @ 1.2 % edit (BASELINE.json metric), B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--ratio 0.012]
+                    [--path engine|modules] [--no-flush]
+
+One "step" = one SPARSE forward of the DDPM U-Net on the edited latent with pre-filled caches —
+what the reference's Runner.profile times (reference diffusion/runner.py:214-245).  Workload =
+BASELINE.json configs[1]: DDPM 256x256, 1.2 % centred-square edit, random-init (deterministic)
+weights, synthetic inputs, fp16.
+
+Multi-GPU (⑤): independent edits, one per GPU (weak scaling).  Rank 0 runs the dense pass on the
+original image; its caches are sent ONCE with NCCL broadcast before the step loop; there is no
+collective on the per-step path.  value = edits-steps/s summed over ranks, time = max over ranks.
+
+Timing: W untimed steps, then K timed steps, each bracketed by CUDA events on the launching
+stream, with an L2 flush (256 MiB write) between steps outside the event brackets; the whole
+region sits between barrier + synchronize.  e2e = the same step through the public API with
+host buffers: pinned H2D copy of x_t and D2H copy of eps inside every timed step.
+
+--impl reference: the reference's CPU flow (its sige/cpu kernels via oracle/_ref + oneDNN conv,
+the same model graph) on this box's host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ratio", type=float, default=0.012)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--path", default="auto", choices=["auto", "engine", "modules"],
+                    help="engine = fused CUDA-graph step engine; modules = sige.nn operator modules (graph-captured)")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (NVML) during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle/ is imported ONLY here)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_steps(ratio: float, steps: int, warmup: int):
+    import torch
+
+    from oracle.cpu_runtime import ddpm_cpu_sparse_step
+    from sige_b200.workloads.ddpm import DDPMConfig
+
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        pass
+    step, kind = ddpm_cpu_sparse_step(DDPMConfig(), ratio, threads=cores)
+    try:
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+    finally:
+        step.close()
+    return {"value": steps / dt, "unit": "steps/s", "cores": cores, "kind": kind,
+            "sample": "%d sparse DDPM-256 steps @%.1f%% edit after %d warm-up, %d torch threads, fp32, oneDNN conv + %s tile kernels"
+                      % (steps, 100 * ratio, warmup, torch.get_num_threads(), "reference sige/cpu (oracle/_ref)" if kind == "reference" else "oracle C port"),
+            "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 60))
+    r = cpu_reference_steps(args.ratio, steps, max(1, min(args.warmup, 5)))
+    line = {
+        "impl": "reference", "metric": "DDPM 256x256 denoising steps/sec @1.2% edit", "value": r["value"], "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 5)), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DDPM U-Net 256x256, %.1f%% centred-square edit, sparse step, random-init weights" % (100 * args.ratio),
+                   "device": "cpu"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from sige_b200 import ops
+    from sige_b200.masks import downsample_mask
+    from sige_b200.workloads.ddpm import DDPMConfig, SIGEDDPMUNet, init_deterministic, synthetic_inputs
+
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    cfg = DDPMConfig()
+    torch.backends.cudnn.benchmark = True
+
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = init_deterministic(SIGEDDPMUNet(cfg), seed=0).eval().to(dev).to(dtype).to(memory_format=torch.channels_last)
+    # every rank edits the SAME original image with its OWN edit (seed + rank)
+    x0, x1, mask, t = synthetic_inputs(cfg, args.ratio, seed=0, edit_seed=rank)
+    fmt = torch.channels_last
+    x0d = x0.to(dev).to(dtype).contiguous(memory_format=fmt)
+    td = t.to(dev)
+
+    path = args.path
+    if path == "auto":
+        try:
+            from sige_b200 import engine as _engine  # noqa: F401
+
+            path = "engine" if getattr(_engine, "AVAILABLE", False) else "modules"
+        except Exception:  # noqa: BLE001
+            path = "modules"
+
+    with torch.no_grad():
+        model.set_mode("full")
+        model(x0d, td)                       # every rank records shapes; rank 0's caches are authoritative
+        if distributed:
+            from sige_b200.parallel import broadcast_caches
+
+            nbytes = broadcast_caches(model, src=0)
+        else:
+            nbytes = 0
+        model.set_masks(downsample_mask(mask.to(dev), min_res=8))
+        model.set_mode("sparse")
+
+    x_host = x1.to(dtype).contiguous(memory_format=fmt).pin_memory()
+    x_dev = torch.empty_like(x_host, device=dev)
+    x_dev.copy_(x_host)
+    out_host = torch.empty((1, cfg.out_ch, cfg.image_size, cfg.image_size), dtype=dtype).pin_memory()
+
+    if path == "engine":
+        from sige_b200.engine import DDPMStepEngine
+
+        runner = DDPMStepEngine(model, x_dev)
+    else:
+        from sige_b200.graphs import GraphedStep
+
+        runner = GraphedStep(model, x_dev, td)
+    launches_per_step = runner.launches_per_step
+    out_dev = runner.output
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def timed_steps(k, e2e):
+        total = 0.0
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        for i in range(k):
+            if flush is not None:
+                flush.fill_(i & 0xFF)
+            evs[i][0].record(stream)
+            if e2e:
+                x_dev.copy_(x_host, non_blocking=True)
+            runner.replay()
+            if e2e:
+                out_host.copy_(out_dev, non_blocking=True)
+            evs[i][1].record(stream)
+            if e2e:
+                evs[i][1].synchronize()      # the caller consumes eps before issuing the next step
+        torch.cuda.synchronize()
+        for a, b in evs:
+            total += a.elapsed_time(b)
+        return total                         # milliseconds of device time over k steps
+
+    def region(k, e2e):
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = timed_steps(k, e2e)
+        torch.cuda.synchronize()
+        if distributed:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+            dist.barrier()
+        return ms
+
+    region(max(3, args.warmup), False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = region(args.steps, False)
+    ms_e2e = region(args.steps, True)
+    clocks = sampler.stop()
+
+    value = world * args.steps / (ms / 1e3)
+    e2e_value = world * args.steps / (ms_e2e / 1e3)
+
+    roof = None
+    cpu = None
+    if rank == 0:
+        try:
+            from sige_b200.roofline import measure_dominant_kernel
+
+            roof = measure_dominant_kernel(model, dtype, flush)
+        except Exception as e:  # noqa: BLE001
+            roof = {"error": repr(e)}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_reference_steps(args.ratio, args.cpu_steps, 3)
+                cpu.pop("ms_per_step", None)
+            except Exception as e:  # noqa: BLE001
+                cpu = {"error": repr(e)}
+        line = {
+            "metric": "DDPM 256x256 denoising steps/sec @1.2% edit", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
+            "config": {
+                "workload": "DDPM U-Net 256x256 (ch128, mult 1-1-2-2-4-4), %.1f%% centred-square edit (28 px), sparse step, random-init weights"
+                            % (100 * args.ratio),
+                "path": path, "edits_per_gpu": 1, "parallelism": "edits sharded 1/GPU, caches broadcast once (%d bytes), no per-step collective" % nbytes,
+                "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
+                "timing": "per-step CUDA events on the launching stream, max over ranks",
+            },
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
+                    "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""Live roofline measurement of the dominant kernel (the fused tile convolution), for bench.py.
+
+achieved = ALGORITHMIC bytes per launch / average launch duration, with the duration taken from
+CUDA events on the launching stream around each launch (L2 flushed before every launch).
+Algorithmic bytes of one tile-conv launch:
+    e * [ M*Cin*R*S (tile read) + kH*kW*Cout*Cin (weights) + M*Cout*Ro*So (write) ],  e = 2 (fp16/bf16)
+and its FLOPs 2*M*Ro*So*Cout*Cin*kH*kW.  Peaks come from MEASURED_PEAKS.json (driver-written),
+else the fallback of /opt/skills/guides/B200_PROFILING.md (6650 GB/s, 1590 TFLOP/s).
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+
+from . import ops
+from .nn import SIGEConv2d
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def peaks():
+    p = os.path.join(_REPO, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def conv_layers_of_step(model, x, t):
+    """One sparse forward with hooks: [(module, input stack shape)] for every tensor-core tile conv."""
+    seen = []
+    hooks = []
+
+    def hook(mod, inp, out):
+        xin = inp[0]
+        if xin.is_cuda and mod.mode == "sparse" and ops.tile_conv_tc_supported(xin, mod.weight, mod.stride, mod.dilation, mod.groups):
+            seen.append((mod, tuple(xin.shape)))
+
+    for m in model.modules():
+        if isinstance(m, SIGEConv2d):
+            hooks.append(m.register_forward_hook(hook))
+    try:
+        with torch.no_grad():
+            model(x, t)
+    finally:
+        for h in hooks:
+            h.remove()
+    return seen
+
+
+def measure_layers(layers, dtype, flush, reps: int = 10):
+    """layers: [(module, (M, Cin, R, S))].  Returns the roofline dict."""
+    if not layers:
+        return None
+    dev = layers[0][0].weight.device
+    stream = torch.cuda.current_stream(dev)
+    tot_bytes = tot_flops = tot_ms = 0.0
+    n_launch = 0
+    cache = {}
+    for mod, shape in layers:
+        M, Cin, R, S = shape
+        kH, kW = mod.kernel_size
+        st = mod.stride[0]
+        Cout = mod.out_channels
+        Ro, So = (R - kH) // st + 1, (S - kW) // st + 1
+        key = (shape, Cout, kH, st)
+        if key not in cache:
+            x = torch.randn(shape, device=dev, dtype=dtype).contiguous(memory_format=torch.channels_last)
+            wp, b32 = mod._packed_weight(dtype)
+            out = ops.tile_conv_stack(x, wp, b32, (kH, kW), st)
+            ms = 0.0
+            for i in range(reps):
+                if flush is not None:
+                    flush.fill_(i)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                ops.tile_conv_stack(x, wp, b32, (kH, kW), st, out=out)
+                b.record(stream)
+                b.synchronize()
+                ms += a.elapsed_time(b)
+            cache[key] = ms / reps
+        tot_ms += cache[key]
+        tot_bytes += 2.0 * (M * Cin * R * S + kH * kW * Cout * Cin + M * Cout * Ro * So)
+        tot_flops += 2.0 * M * Ro * So * Cout * Cin * kH * kW
+        n_launch += 1
+    pk = peaks()
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+    return {
+        "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+        "kernel": "sige::tile_conv_mma_kernel (all %d tensor-core tile convs of one step)" % n_launch,
+        "avg_launch_us": 1e3 * tot_ms / n_launch, "algorithmic_bytes_per_step": tot_bytes, "peak_source": pk["source"],
+        "tensor": {"achieved_tflops": tot_flops / (tot_ms * 1e-3) / 1e12, "peak_tflops": pk["bf16_tflops"],
+                   "frac": tot_flops / (tot_ms * 1e-3) / 1e12 / pk["bf16_tflops"]},
+        "note": "cold L2 (flushed before every launch); launch latency included in the event bracket",
+    }
+
+
+def measure_dominant_kernel(model, dtype, flush):
+    from .workloads.ddpm import synthetic_inputs
+
+    dev = next(model.parameters()).device
+    _, x1, _, t = synthetic_inputs(model.cfg, 0.012, seed=0)
+    x = x1.to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    layers = conv_layers_of_step(model, x, t.to(dev))
+    return measure_layers(layers, dtype, flush)

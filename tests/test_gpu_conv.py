@@ -1,0 +1,215 @@
+"""GPU parity of the tile convolution: tensor-core fused kernel (fp16/bf16) and CUDA-core generic
+kernel (fp32 exact) vs the CPU oracle.  Tolerances are the north-star's: conv outputs within
+1e-3 rel (fp16) / 1e-5 rel (fp32) of the fp32 reference, max-normalised; bf16 (8-bit mantissa)
+is given 8e-3."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a, dtype=torch.float32, cl=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    if t.is_floating_point():
+        t = t.to(dtype)
+    if cl and t.dim() == 4:
+        t = t.contiguous(memory_format=torch.channels_last)
+    return t
+
+
+def _round(a, dtype):
+    return a if dtype == torch.float32 else torch.from_numpy(a).to(dtype).float().numpy()
+
+
+def rel_err(got, want):
+    g = got.float().cpu().numpy()
+    assert g.shape == want.shape, (g.shape, want.shape)
+    return float(np.abs(g - want).max() / max(np.abs(want).max(), 1e-12))
+
+
+TOL = {torch.float32: 1e-5, torch.float16: 1e-3, torch.bfloat16: 8e-3}
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_generic_conv_fp32_exact(oracle, cl):
+    from sige_b200 import ops
+
+    rng = np.random.default_rng(1)
+    for (M, Ci, Co, R, k, s, d, g) in [(5, 8, 12, 6, 3, 1, 1, 1), (3, 16, 16, 5, 3, 2, 1, 1), (4, 12, 12, 6, 3, 1, 1, 12), (7, 36, 70, 6, 3, 1, 1, 1),
+                                       (2, 36, 20, 4, 1, 1, 1, 1), (3, 8, 8, 7, 3, 1, 2, 2), (64, 64, 64, 6, 3, 1, 1, 1), (2, 3, 5, 10, 3, 1, 1, 1)]:
+        x = rng.standard_normal((M, Ci, R, R)).astype(np.float32)
+        w = rng.standard_normal((Co, Ci // g, k, k)).astype(np.float32) / np.sqrt(Ci // g * k * k)
+        b = rng.standard_normal((Co,)).astype(np.float32)
+        want = oracle.conv2d_tiles(x, w, b, (s, s), (d, d), g)
+        got = ops.tile_conv_generic(T(x, cl=cl), T(w), T(b), (s, s), (d, d), g)
+        assert rel_err(got, want) <= 1e-5
+        got = ops.tile_conv_generic(T(x, cl=cl), T(w), None, (s, s), (d, d), g)
+        assert rel_err(got, oracle.conv2d_tiles(x, w, None, (s, s), (d, d), g)) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_generic_conv_half(oracle, dtype):
+    from sige_b200 import ops
+
+    rng = np.random.default_rng(2)
+    x = _round(rng.standard_normal((6, 36, 6, 6)).astype(np.float32), dtype)
+    w = _round(rng.standard_normal((48, 36, 3, 3)).astype(np.float32) / 18, dtype)
+    b = _round(rng.standard_normal((48,)).astype(np.float32), dtype)
+    want = oracle.conv2d_tiles(x, w, b)
+    assert rel_err(ops.tile_conv_generic(T(x, dtype), T(w, dtype), T(b, dtype), (1, 1), (1, 1), 1), want) <= TOL[dtype]
+
+
+STACK_CASES = [  # M, Cin, Cout, R, k, stride  — DDPM shape classes + edge sizes
+    (64, 128, 128, 6, 3, 1), (64, 256, 128, 6, 3, 1), (32, 384, 128, 6, 3, 1), (16, 512, 256, 6, 3, 1), (4, 512, 512, 6, 3, 1),
+    (64, 256, 128, 4, 1, 1), (12, 384, 256, 4, 1, 1), (64, 128, 128, 5, 3, 2), (13, 256, 256, 5, 3, 2),
+    (1, 64, 8, 6, 3, 1), (3, 64, 72, 6, 3, 1), (700, 128, 128, 6, 3, 1), (1300, 64, 64, 6, 3, 1), (33, 128, 136, 4, 1, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_tensor_core_conv_on_stacks(oracle, dtype):
+    from sige_b200 import ops
+
+    rng = np.random.default_rng(3)
+    for (M, Ci, Co, R, k, s) in STACK_CASES:
+        x = _round(rng.standard_normal((M, Ci, R, R)).astype(np.float32), dtype)
+        w = _round(rng.standard_normal((Co, Ci, k, k)).astype(np.float32) / np.sqrt(Ci * k * k), dtype)
+        b = rng.standard_normal((Co,)).astype(np.float32)
+        want = oracle.conv2d_tiles(x, w, b, (s, s))
+        wp = ops.pack_conv_weight(T(w, dtype), dtype)
+        assert tuple(wp.shape) == (k * k, Co, Ci)
+        got = ops.tile_conv_stack(T(x, dtype, cl=True), wp, T(b), (k, k), s)
+        assert got.is_contiguous(memory_format=torch.channels_last) or got.is_contiguous()
+        e = rel_err(got, want)
+        assert e <= TOL[dtype], "case %s: rel err %g" % ((M, Ci, Co, R, k, s), e)
+
+
+def _fused_desc(ops, x, wp, bias, idx, out, *, R, k, stride, off, scale=None, shift=None, act=0, residual=None, x2=None, up=0):
+    d = ops.tile_conv_descriptor()
+    B, C, H, W = x.shape
+    d.dtype = ops._dt(x)
+    d.n_src = 1 if x2 is None else 2
+    d.src[0].ptr, d.src[0].C, d.src[0].up = x.data_ptr(), C, up
+    cin = C
+    if x2 is not None:
+        d.src[1].ptr, d.src[1].C, d.src[1].up = x2.data_ptr(), x2.shape[1], 0
+        cin += x2.shape[1]
+    d.B, d.H, d.W = B, H << up, W << up
+    d.src_is_stack = 0
+    d.idx, d.N = idx.data_ptr(), idx.shape[0]
+    d.R = d.S = R
+    d.scale = None if scale is None else scale.data_ptr()
+    d.shift = None if shift is None else shift.data_ptr()
+    d.affine_bstride = 0 if (scale is None or scale.shape[0] == 1) else cin
+    d.act = act
+    d.w_packed, d.bias = wp.data_ptr(), (None if bias is None else bias.data_ptr())
+    d.Cin, d.Cout, d.kH, d.kW, d.stride = cin, wp.shape[1], k, k, stride
+    d.dst, d.dst_is_stack = out.data_ptr(), 0
+    d.dH, d.dW, d.dC, d.dst_c0 = out.shape[2], out.shape[3], out.shape[1], 0
+    d.offH = d.offW = off
+    d.residual = None if residual is None else residual.data_ptr()
+    d.rC, d.res_c0 = (0 if residual is None else residual.shape[1]), 0
+    return d
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_fused_gather_conv_scatter_vs_oracle(oracle, dtype):
+    """One launch == oracle gather(affine+swish) -> conv -> scatter(+residual) composite."""
+    from sige_b200 import ops
+
+    rng = np.random.default_rng(4)
+    for (B, C, Co, H, W, bs, ts, k, s, off, p) in [(1, 128, 128, 64, 64, 6, 4, 3, 1, 1, 0.02), (2, 64, 192, 24, 40, 6, 4, 3, 1, 1, 0.1),
+                                                   (1, 256, 128, 32, 32, 4, 4, 1, 1, 0, 0.05), (1, 128, 128, 33, 33, 5, 4, 3, 2, 0, 0.05),
+                                                   (1, 64, 64, 16, 16, 6, 4, 3, 1, 1, 1.0)]:
+        mask = rng.random((H, W)) < p
+        mask[0, 0] = mask[H - 1, W - 1] = True
+        idx = oracle.reduce_mask(mask, bs, ts, off)
+        x = _round(rng.standard_normal((B, C, H, W)).astype(np.float32), dtype)
+        w = _round(rng.standard_normal((Co, C, k, k)).astype(np.float32) / np.sqrt(C * k * k), dtype)
+        b = rng.standard_normal((Co,)).astype(np.float32)
+        sc = (1 + 0.2 * rng.standard_normal((B, C, 1, 1))).astype(np.float32)
+        sh = (0.2 * rng.standard_normal((B, C, 1, 1))).astype(np.float32)
+        Ho = H if s == 1 else (H + 1 - k) // 2 + 1
+        Wo = W if s == 1 else (W + 1 - k) // 2 + 1
+        y = _round(rng.standard_normal((B, Co, Ho, Wo)).astype(np.float32), dtype)
+        res = _round(rng.standard_normal((B, Co, Ho, Wo)).astype(np.float32), dtype)
+        g = oracle.gather(x, bs, bs, idx, sc, sh, "swish", False)
+        g = _round(g, dtype)                     # the kernel stages the pre-op result in fp16/bf16
+        c = oracle.conv2d_tiles(g, w, b, (s, s))
+        want = oracle.scatter(c, y, off, off, s, s, idx, res)
+        out = T(y, dtype, cl=True).clone(memory_format=torch.channels_last)
+        tx, tres = T(x, dtype, cl=True), T(res, dtype, cl=True)
+        d = _fused_desc(ops, tx, ops.pack_conv_weight(T(w, dtype), dtype), T(b), T(idx), out, R=bs, k=k, stride=s, off=off,
+                        scale=T(sc).reshape(B, C).contiguous(), shift=T(sh).reshape(B, C).contiguous(), act=1, residual=tres)
+        ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        e = rel_err(out, want)
+        assert e <= 2 * TOL[dtype], "fused case %s: rel err %g" % ((B, C, Co, H, W, bs, k, s), e)
+
+
+def test_fused_concat_and_upsample_sources(oracle):
+    """Two channel-concatenated sources (torch.cat dim=1) and a nearest-x2-upsampled source are read
+    in place by the gather stage: results equal the oracle on the materialised tensors."""
+    from sige_b200 import ops
+
+    dtype = torch.float16
+    rng = np.random.default_rng(6)
+    B, C1, C2, Co, H, W = 1, 128, 64, 128, 32, 32
+    mask = rng.random((H, W)) < 0.05
+    mask[0, 0] = True
+    idx = oracle.reduce_mask(mask, 6, 4, 1)
+    x1 = _round(rng.standard_normal((B, C1, H, W)).astype(np.float32), dtype)
+    x2 = _round(rng.standard_normal((B, C2, H, W)).astype(np.float32), dtype)
+    w = _round(rng.standard_normal((Co, C1 + C2, 3, 3)).astype(np.float32) / np.sqrt((C1 + C2) * 9), dtype)
+    y = _round(rng.standard_normal((B, Co, H, W)).astype(np.float32), dtype)
+    want = oracle.gather_conv_scatter(np.concatenate([x1, x2], 1), w, None, y, idx, (6, 6), (1, 1), (1, 1))
+    out = T(y, dtype, cl=True).clone(memory_format=torch.channels_last)
+    d = _fused_desc(ops, T(x1, dtype, cl=True), ops.pack_conv_weight(T(w, dtype), dtype), None, T(idx), out, R=6, k=3, stride=1, off=1,
+                    x2=T(x2, dtype, cl=True))
+    a, b2 = T(x1, dtype, cl=True), T(x2, dtype, cl=True)
+    d.src[0].ptr, d.src[1].ptr = a.data_ptr(), b2.data_ptr()
+    ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_err(out, want) <= 1e-3
+    # upsample: source at half resolution, logical extent HxW
+    xs = _round(rng.standard_normal((B, C1, H // 2, W // 2)).astype(np.float32), dtype)
+    xu = xs.repeat(2, axis=2).repeat(2, axis=3)
+    w = _round(rng.standard_normal((Co, C1, 3, 3)).astype(np.float32) / np.sqrt(C1 * 9), dtype)
+    want = oracle.gather_conv_scatter(xu, w, None, y, idx, (6, 6), (1, 1), (1, 1))
+    out = T(y, dtype, cl=True).clone(memory_format=torch.channels_last)
+    txs = T(xs, dtype, cl=True)
+    d = _fused_desc(ops, txs, ops.pack_conv_weight(T(w, dtype), dtype), None, T(idx), out, R=6, k=3, stride=1, off=1, up=1)
+    ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_err(out, want) <= 1e-3
+
+
+def test_linearity_and_dense_equals_sparse_at_full_size(oracle):
+    """Size-independent properties at the benchmark's layer size (no oracle run needed):
+    (1) with every tile active the fused sparse layer equals the dense convolution (example.py:95's
+    identity), (2) conv is linear: f(a x1 + x2) = a f(x1) + f(x2) (bias-free)."""
+    from sige_b200 import ops
+
+    dtype = torch.float16
+    torch.manual_seed(0)
+    B, C, H, W = 1, 128, 256, 256
+    x = torch.randn(B, C, H, W, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(C, C, 3, 3, device=DEV) / (C * 9) ** 0.5).to(dtype)
+    bias = torch.randn(C, device=DEV)
+    ii, jj = torch.meshgrid(torch.arange(0, H, 4), torch.arange(0, W, 4), indexing="ij")
+    idx = (torch.stack([ii.reshape(-1), jj.reshape(-1)], 1) - 1).to(torch.int32).to(DEV).contiguous()
+    out = torch.zeros(B, C, H, W, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
+    wp = ops.pack_conv_weight(w, dtype)
+    d = _fused_desc(ops, x, wp, bias, idx, out, R=6, k=3, stride=1, off=1)
+    ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+    dense = torch.nn.functional.conv2d(x.float(), w.float(), bias, 1, 1)
+    assert float((out.float() - dense).abs().max() / dense.abs().max()) <= 1e-3
+    x2 = torch.randn_like(x)
+    o1, o2, o3 = (torch.zeros_like(out) for _ in range(3))
+    for src, dst in ((x, o1), (x2, o2), ((0.5 * x + x2).contiguous(memory_format=torch.channels_last), o3)):
+        d = _fused_desc(ops, src, wp, None, idx, dst, R=6, k=3, stride=1, off=1)
+        ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+    lin = 0.5 * o1.float() + o2.float()
+    assert float((o3.float() - lin).abs().max() / lin.abs().max()) <= 3e-3

@@ -1,0 +1,139 @@
+"""End-to-end GPU parity through the operator surface: example.py's flow and the DDPM U-Net sparse
+step vs golden outputs of the reference (its Python + its compiled CPU backend, see
+tests/golden/make_golden.py).  fp32 bar 1e-4 rel for a full network (the per-layer 1e-5 bar
+compounds over ~60 layers of fp32 reassociation); fp16 bar stated per test."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _example_model():
+    from sige.nn import Gather, Scatter, SIGEConv2d, SIGEModel, SIGEModule
+
+    class ExampleModule(SIGEModule):
+        def __init__(self):
+            super().__init__()
+            self.conv = SIGEConv2d(16, 32, 3, 1, 1, bias=True)
+            self.gather = Gather(self.conv, block_size=6)
+            self.scatter = Scatter(self.gather)
+
+        def forward(self, x):
+            return self.scatter(self.conv(self.gather(x)))
+
+    class ExampleModel(SIGEModel):
+        def __init__(self):
+            super().__init__()
+            self.example_module = ExampleModule()
+
+        def forward(self, x):
+            return self.example_module(x)
+
+    return ExampleModel()
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_example_flow_matches_reference_golden(cl):
+    """reference example.py:55-98 with assets/mask.npy: 783 tiles, dense == sparse (atol 1e-4)."""
+    from sige_b200.workloads.ddpm import init_deterministic
+
+    G = golden("example_golden.npz")
+    rng = np.random.default_rng(7)
+    mask = G["mask"]
+    orig = rng.standard_normal((1, 16, 256, 256)).astype(np.float32)
+    edit = orig + rng.standard_normal((1, 16, 256, 256)).astype(np.float32) * mask[None, None]
+    model = init_deterministic(_example_model(), seed=3).eval().to(DEV)
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    to = lambda a: torch.from_numpy(a).to(DEV).contiguous(memory_format=fmt)  # noqa: E731
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        model.set_mode("full")
+        std = model(to(edit))
+        model(to(orig))
+        model.set_mode("sparse")
+        model.set_masks({(256, 256): torch.from_numpy(mask).to(DEV)})
+        sp = model(to(edit))
+    idx = model.example_module.gather.active_indices
+    assert idx.shape[0] == 783 and idx[0].tolist() == [-1, 107]
+    assert np.array_equal(idx.cpu().numpy(), G["idx"])
+    assert torch.isclose(std, sp, atol=1e-4).all()                      # the reference's own assert (example.py:95)
+    got = sp.cpu().numpy()
+    np.testing.assert_allclose(got[:, ::4, ::4, ::4], G["sparse_out_sub"], rtol=0, atol=2e-5)
+    assert abs(float(np.abs(got.astype(np.float64)).sum()) - float(G["out_abs_sum"][0])) <= 1e-5 * float(G["out_abs_sum"][0])
+
+
+def _ddpm(cfg, dtype, cl):
+    from sige_b200.workloads.ddpm import SIGEDDPMUNet, init_deterministic
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = init_deterministic(SIGEDDPMUNet(cfg), seed=0).eval()
+    model = model.to(DEV).to(dtype)
+    if cl:
+        model = model.to(memory_format=torch.channels_last)
+    return model
+
+
+def _sparse_step(model, cfg, ratio, dtype, cl):
+    from sige.utils import downsample_mask
+    from sige_b200.workloads.ddpm import synthetic_inputs
+
+    x0, x1, mask, t = synthetic_inputs(cfg, ratio, seed=0)
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    x0, x1, t = (x0.to(DEV).to(dtype).contiguous(memory_format=fmt), x1.to(DEV).to(dtype).contiguous(memory_format=fmt), t.to(DEV))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        model.set_mode("full")
+        model(x0, t)
+        model.set_masks(downsample_mask(mask.to(DEV), min_res=8))
+        model.set_mode("sparse")
+        return model(x1, t)
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_ddpm_small_sparse_step_fp32(cl):
+    from sige_b200.workloads.ddpm import DDPMConfig
+
+    G = golden("ddpm_small_golden.npz")
+    cfg = DDPMConfig.small()
+    out = _sparse_step(_ddpm(cfg, torch.float32, cl), cfg, float(G["ratio"][0]), torch.float32, cl)
+    ref = G["sparse_out"]
+    err = float(np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max())
+    assert err <= 1e-4, err
+
+
+def test_ddpm256_sparse_step_fp32_matches_reference():
+    """The benchmark configuration (BASELINE.json configs[1]) in fp32 vs the reference's output."""
+    from sige.nn import Gather
+    from sige_b200.workloads.ddpm import DDPMConfig
+
+    G = golden("ddpm256_golden.npz")
+    cfg = DDPMConfig()
+    model = _ddpm(cfg, torch.float32, False)
+    out = _sparse_step(model, cfg, float(G["ratio"][0]), torch.float32, False)
+    counts = {n: int(m.active_indices.shape[0]) for n, m in model.named_modules() if isinstance(m, Gather) and m.active_indices is not None}
+    assert [counts[k] for k in sorted(counts)] == G["gather_counts"].tolist()
+    ref = G["sparse_out"]
+    err = float(np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max())
+    assert err <= 1e-4, err
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-2), (torch.bfloat16, 1e-1)])
+def test_ddpm256_sparse_step_half_channels_last(dtype, tol):
+    """fp16/bf16 storage through ~60 stacked layers: per-layer error is <= 1e-3 (test_gpu_conv.py);
+    end to end the roundings compound, the bar here is the network-level one."""
+    from sige_b200.workloads.ddpm import DDPMConfig
+
+    G = golden("ddpm256_golden.npz")
+    cfg = DDPMConfig()
+    out = _sparse_step(_ddpm(cfg, dtype, True), cfg, float(G["ratio"][0]), dtype, True)
+    ref = G["sparse_out"]
+    err = float(np.abs(out.float().cpu().numpy() - ref).max() / np.abs(ref).max())
+    assert err <= tol, err
