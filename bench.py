@@ -34,6 +34,14 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.time() - _T0, msg))
+    sys.stderr.flush()
+
+
 def _env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -205,6 +213,7 @@ def run_ours(args):
         except Exception:  # noqa: BLE001
             path = "modules"
 
+    log("model built; dense pass on the original image")
     with torch.no_grad():
         model.set_mode("full")
         model(x0d, td)                       # every rank records shapes; rank 0's caches are authoritative
@@ -217,6 +226,7 @@ def run_ours(args):
         model.set_masks(downsample_mask(mask.to(dev), min_res=8))
         model.set_mode("sparse")
 
+    log("masks set; building the step runner (path=%s)" % path)
     x_host = x1.to(dtype).contiguous(memory_format=fmt).pin_memory()
     x_dev = torch.empty_like(x_host, device=dev)
     x_dev.copy_(x_host)
@@ -269,7 +279,9 @@ def run_ours(args):
             dist.barrier()
         return ms
 
+    log("runner ready: %d launches of our kernels per step; warm-up" % launches_per_step)
     region(max(3, args.warmup), False)
+    log("timing %d steps (device-resident), then %d steps end-to-end" % (args.steps, args.steps))
     sampler = ClockSampler(local)
     sampler.start()
     ms = region(args.steps, False)
@@ -279,15 +291,17 @@ def run_ours(args):
     value = world * args.steps / (ms / 1e3)
     e2e_value = world * args.steps / (ms_e2e / 1e3)
 
+    log("timed: %.3f ms/step resident, %.3f ms/step e2e; roofline + cpu baseline" % (ms / args.steps, ms_e2e / args.steps))
     roof = None
     cpu = None
     if rank == 0:
         try:
-            from sige_b200.roofline import measure_dominant_kernel
+            from sige_b200 import roofline
 
-            roof = measure_dominant_kernel(model, dtype, flush)
+            roof = roofline.measure_engine(runner, flush) if path == "engine" else roofline.measure_dominant_kernel(model, dtype, flush)
         except Exception as e:  # noqa: BLE001
             roof = {"error": repr(e)}
+        log("roofline done")
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cpu = cpu_reference_steps(args.ratio, args.cpu_steps, 3)

@@ -1,0 +1,318 @@
+"""Fused step engine: the whole sparse DDPM step as a short list of fused sm_100a launches,
+captured once into a CUDA graph.
+
+The operator modules (``sige_b200.nn``) keep the reference's three-call structure per layer
+(Gather -> SIGEConv2d -> Scatter, reference diffusion/models/ddpm_arch/sige_fused_unet.py:100-131)
+so that unmodified model files run; that costs a tile stack round trip through HBM per call, a
+full-tensor clone per Scatter (reference sige/cuda/scatter_kernel.cu:89), a dense ``torch.cat`` per
+skip connection and a dense nearest-upsample per SIGEUpsample — at a 1.2 % edit ~75 % of all bytes
+touched.  The engine executes the SAME graph of layers with
+
+  * one ``sige_tile_conv`` launch per wrapped conv: gather (+GroupNorm affine, +SiLU) -> tensor-core
+    conv -> (+bias, +residual) -> in-place scatter into a persistent NHWC buffer that was initialised
+    from the layer's cached original output (== the reference's ``sparse_update`` form of Scatter,
+    sige/nn/scatter.py:59-60: no clone);
+  * ScatterGather for free: conv2 gathers from the buffer conv1 just scattered into;
+  * ``torch.cat`` and ``F.interpolate`` folded into the gather stage (two channel segments /
+    half-resolution source), never materialised;
+  * the dense low-resolution blocks (below ``sparse_resolution_threshold``) through the same kernel
+    with an all-tiles index list.
+
+Dense glue that is not tile-shaped (3-channel conv_in, the final GroupNorm+conv_out, the 16x16
+attention core) is issued as library calls inside the same graph.
+
+Numerics: every value is computed by the same formulas as the module path; the only reassociations
+are (i) fp32 FMA for the affine, (ii) the 1x1 shortcut of Cin != Cout blocks is evaluated on every
+main tile instead of being patched by (fresh - cached) on its own tile list
+(reference sige/cuda/scatter_kernel.cu:46-74) — equal up to rounding because the shortcut's active
+tiles are a subset of the main conv's.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.nn import functional as F
+
+from . import ops
+from .nn import SIGEConv2d
+from .workloads.ddpm import AttnBlock, DenseDownsample, ResBlock, SIGEDDPMUNet, SparseDownsample, Upsample
+
+AVAILABLE = True
+
+Src = Tuple[torch.Tensor, int]  # (NHWC tensor [1, C, H, W] channels_last, upsample flag)
+
+
+class FusedConv:
+    """One prepared ``sige_tile_conv`` launch."""
+
+    __slots__ = ("desc", "keep", "name", "bytes", "flops", "tiles")
+
+    def __init__(self, desc, keep, name, nbytes, flops, tiles):
+        self.desc, self.keep, self.name, self.bytes, self.flops, self.tiles = desc, keep, name, nbytes, flops, tiles
+
+    def launch(self, stream: int) -> None:
+        ops.launch_tile_conv(self.desc, stream)
+
+
+class DDPMStepEngine:
+    def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True):
+        if model.mode != "sparse":
+            raise RuntimeError("DDPMStepEngine: run the dense pass, set_masks() and set_mode('sparse') first")
+        p = next(model.parameters())
+        if not p.is_cuda or p.dtype not in (torch.float16, torch.bfloat16):
+            raise RuntimeError("DDPMStepEngine needs a CUDA fp16/bf16 model (tensor-core path)")
+        self.model, self.dev, self.dtype = model, p.device, p.dtype
+        self.x = x_static
+        assert x_static.is_cuda and x_static.dtype == self.dtype and x_static.is_contiguous(memory_format=torch.channels_last)
+        self.steps: List = []          # callables taking the stream handle
+        self.fused: List[FusedConv] = []
+        self._all_idx = {}
+        self._build(model)
+        self.graph = None
+        self.launches_per_step = 0
+        self._finalize(use_graph)
+
+    # ------------------------------------------------------------------ buffers / helpers
+    def _empty(self, c: int, h: int, w: int) -> torch.Tensor:
+        return torch.empty((1, c, h, w), dtype=self.dtype, device=self.dev, memory_format=torch.channels_last)
+
+    def _from_cache(self, cached: torch.Tensor) -> torch.Tensor:
+        """Engine-owned NHWC copy of a module cache (the module's own cache stays pristine)."""
+        assert cached.shape[0] == 1, "the step engine handles batch 1 (DDPM asserts it too, models/common.py:39)"
+        return cached.detach().to(self.dtype).clone(memory_format=torch.channels_last)
+
+    def _vec(self, v: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        return None if v is None else v.detach().reshape(-1).float().contiguous()
+
+    def all_tiles(self, h: int, w: int, off: int) -> torch.Tensor:
+        """Index list covering the whole image with stride-4 tiles (dense layers as 'everything active')."""
+        key = (h, w, off)
+        if key not in self._all_idx:
+            assert h % 4 == 0 and w % 4 == 0
+            ii, jj = torch.meshgrid(torch.arange(0, h, 4), torch.arange(0, w, 4), indexing="ij")
+            idx = torch.stack([ii.reshape(-1), jj.reshape(-1)], 1) - off
+            self._all_idx[key] = idx.to(torch.int32).to(self.dev).contiguous()
+        return self._all_idx[key]
+
+    def _pack(self, conv, out_scale_rows: int = 0, row_scale: float = 1.0):
+        w = conv.weight.detach().float()
+        b = None if conv.bias is None else conv.bias.detach().float().clone()
+        if out_scale_rows:
+            w = w.clone()
+            w[:out_scale_rows] *= row_scale
+            if b is not None:
+                b[:out_scale_rows] *= row_scale
+        return ops.pack_conv_weight(w.contiguous(), self.dtype), (None if b is None else b.contiguous())
+
+    def conv(self, name: str, srcs: Sequence[Src], hw: Tuple[int, int], idx: torch.Tensor, block: int, conv, stride: int, off: int,
+             dst: torch.Tensor, scale=None, shift=None, act: str = "identity", residual: Optional[torch.Tensor] = None,
+             packed=None) -> None:
+        """Emit one fused gather->conv->scatter launch."""
+        n = int(idx.shape[0])
+        if n == 0:
+            return
+        wp, b32 = packed if packed is not None else self._pack(conv)
+        taps, cout, cin = wp.shape
+        k = int(round(taps ** 0.5))
+        d = ops.tile_conv_descriptor()
+        d.dtype = ops._dt(dst)
+        d.n_src = len(srcs)
+        csum = 0
+        for s, (t, up) in enumerate(srcs):
+            assert t.is_contiguous(memory_format=torch.channels_last) and t.dtype == self.dtype
+            d.src[s].ptr, d.src[s].C, d.src[s].up = t.data_ptr(), t.shape[1], up
+            assert (t.shape[2] << up, t.shape[3] << up) == tuple(hw), (name, t.shape, up, hw)
+            csum += t.shape[1]
+        assert csum == cin, (name, csum, cin)
+        d.B, d.H, d.W = 1, hw[0], hw[1]
+        d.src_is_stack = 0
+        d.idx, d.N = idx.data_ptr(), n
+        d.R = d.S = block
+        sc, sh = self._vec(scale), self._vec(shift)
+        d.scale = None if sc is None else sc.data_ptr()
+        d.shift = None if sh is None else sh.data_ptr()
+        d.affine_bstride = 0
+        d.act = ops._act(act)
+        d.w_packed = wp.data_ptr()
+        d.bias = None if b32 is None else b32.data_ptr()
+        d.Cin, d.Cout, d.kH, d.kW, d.stride = cin, cout, k, k, stride
+        d.dst, d.dst_is_stack = dst.data_ptr(), 0
+        d.dH, d.dW, d.dC, d.dst_c0 = dst.shape[2], dst.shape[3], dst.shape[1], 0
+        d.offH = d.offW = off
+        if residual is not None:
+            assert residual.shape == dst.shape and residual.is_contiguous(memory_format=torch.channels_last)
+            d.residual, d.rC, d.res_c0 = residual.data_ptr(), residual.shape[1], 0
+        else:
+            d.residual, d.rC, d.res_c0 = None, 0, 0
+        ro = (block - k) // stride + 1
+        e = 2
+        nbytes = e * (n * cin * block * block + taps * cout * cin + n * cout * ro * ro * (2 if residual is not None else 1))
+        flops = 2 * n * ro * ro * cout * cin * taps
+        fc = FusedConv(d, (idx, sc, sh, wp, b32, dst, residual, [t for t, _ in srcs]), name, nbytes, flops, n)
+        self.fused.append(fc)
+        self.steps.append(fc.launch)
+
+    # ------------------------------------------------------------------ graph construction
+    def _resblock(self, name: str, blk: ResBlock, srcs: Sequence[Src], hw: Tuple[int, int]) -> torch.Tensor:
+        cid = blk.cache_id
+        h, w = hw
+        cout = blk.out_channels
+        if blk.main_sparse:
+            g = blk.main_gather
+            idx, bs, off = g.active_indices, g.block_size[0], g.offset[0]
+            t1 = self._from_cache(blk.scatter_gather.original_outputs[cid])
+            t2 = self._from_cache(blk.scatter.original_outputs[cid])
+        else:
+            idx, bs, off = self.all_tiles(h, w, 1), 6, 1
+            t1, t2 = self._empty(cout, h, w), self._empty(cout, h, w)
+        if blk.in_channels != blk.out_channels:
+            if blk.shortcut_sparse:
+                sg = blk.shortcut_gather
+                sidx, sbs, soff = sg.active_indices, sg.block_size[0], sg.offset[0]
+                skip = self._from_cache(blk.scatter.original_residuals[cid])
+            else:
+                sidx, sbs, soff = self.all_tiles(h, w, 0), 4, 0
+                skip = self._empty(cout, h, w)
+            self.conv(name + ".nin_shortcut", srcs, hw, sidx, sbs, blk.nin_shortcut, 1, soff, skip)
+        else:
+            assert len(srcs) == 1 and srcs[0][1] == 0
+            skip = srcs[0][0]
+        self.conv(name + ".conv1", srcs, hw, idx, bs, blk.conv1, 1, off, t1, blk.scale1s[cid], blk.shift1s[cid], "swish")
+        self.conv(name + ".conv2", [(t1, 0)], hw, idx, bs, blk.conv2, 1, off, t2, blk.scale2s[cid], blk.shift2s[cid], "swish",
+                  residual=skip)
+        return t2
+
+    def _attn(self, name: str, blk: AttnBlock, x: torch.Tensor, hw: Tuple[int, int]) -> torch.Tensor:
+        if blk.support_sparse:
+            raise NotImplementedError("step engine: sparse attention blocks are not fused yet; use the module path")
+        cid = blk.cache_id
+        h, w = hw
+        c = blk.in_channels
+        # reference quirk (sige_fused_unet.py:170-175): scales is a [C] tensor indexed by cache_id -> one scalar
+        sc = blk.scales[cid].reshape(1).float().expand(c).contiguous()
+        sh = blk.shifts[cid].reshape(1).float().expand(c).contiguous()
+        qkv = self._empty(3 * c, h, w)
+        idx = self.all_tiles(h, w, 0)
+        # fold the attention scale c^-0.5 into the q rows of the qkv weights
+        self.conv(name + ".qkv", [(x, 0)], hw, idx, 4, blk.qkv, 1, 0, qkv, sc, sh, "identity",
+                  packed=self._pack(blk.qkv, out_scale_rows=c, row_scale=float(int(c) ** (-0.5))))
+        att_out = self._empty(c, h, w)
+        tok = qkv.permute(0, 2, 3, 1).reshape(h * w, 3 * c)            # [HW, 3C] view of the NHWC buffer
+        q, k, v = tok[:, :c], tok[:, c:2 * c], tok[:, 2 * c:]
+        o_tok = att_out.permute(0, 2, 3, 1).reshape(h * w, c)
+
+        def attention(_stream):
+            att = torch.softmax(torch.matmul(q, k.t()), dim=-1)
+            torch.matmul(att, v, out=o_tok)
+
+        self.steps.append(attention)
+        out = self._empty(c, h, w)
+        self.conv(name + ".proj_out", [(att_out, 0)], hw, idx, 4, blk.proj_out, 1, 0, out, residual=x)
+        return out
+
+    def _build(self, m: SIGEDDPMUNet) -> None:
+        cfg = m.cfg
+        res = cfg.image_size
+        dt = self.dtype
+        # ---- conv_in: dense, 3 input channels (library call inside the graph)
+        w_in, b_in = m.conv_in.weight.detach().to(dt).contiguous(memory_format=torch.channels_last), m.conv_in.bias.detach().to(dt)
+        h0 = self._empty(cfg.ch, res, res)
+
+        def conv_in(_stream):
+            h0.copy_(F.conv2d(self.x, w_in, b_in, 1, 1))
+
+        self.steps.append(conv_in)
+        hs: List[Tuple[torch.Tensor, int]] = [(h0, res)]
+        # ---- down
+        for lvl in range(m.num_resolutions):
+            level = m.down[lvl]
+            for i, blk in enumerate(level.block):
+                src, r = hs[-1]
+                h = self._resblock("down.%d.block.%d" % (lvl, i), blk, [(src, 0)], (r, r))
+                if len(level.attn) > 0:
+                    h = self._attn("down.%d.attn.%d" % (lvl, i), level.attn[i], h, (r, r))
+                hs.append((h, r))
+            if lvl != m.num_resolutions - 1:
+                src, r = hs[-1]
+                ds = level.downsample
+                c = src.shape[1]
+                if isinstance(ds, SparseDownsample):
+                    g = ds.gather
+                    dst = self._from_cache(ds.scatter.original_outputs[ds.scatter.cache_id])
+                    self.conv("down.%d.downsample" % lvl, [(src, 0)], (r, r), g.active_indices, g.block_size[0], ds.conv, 2, g.offset[0], dst)
+                else:
+                    assert isinstance(ds, DenseDownsample)
+                    dst = self._empty(c, r // 2, r // 2)
+                    self.conv("down.%d.downsample" % lvl, [(src, 0)], (r, r), self.all_tiles(r, r, 0), 5, ds.conv, 2, 0, dst)
+                hs.append((dst, r // 2))
+        # ---- middle
+        h, r = hs[-1]
+        h = self._resblock("mid.block_1", m.mid.block_1, [(h, 0)], (r, r))
+        h = self._attn("mid.attn_1", m.mid.attn_1, h, (r, r))
+        h = self._resblock("mid.block_2", m.mid.block_2, [(h, 0)], (r, r))
+        # ---- up
+        for lvl in reversed(range(m.num_resolutions)):
+            level = m.up[lvl]
+            for i, blk in enumerate(level.block):
+                skip, rs = hs.pop()
+                assert rs == r
+                h = self._resblock("up.%d.block.%d" % (lvl, i), blk, [(h, 0), (skip, 0)], (r, r))
+                if len(level.attn) > 0:
+                    h = self._attn("up.%d.attn.%d" % (lvl, i), level.attn[i], h, (r, r))
+            if lvl != 0:
+                up: Upsample = level.upsample
+                g = up.gather
+                dst = self._from_cache(up.scatter.original_outputs[up.scatter.cache_id])
+                self.conv("up.%d.upsample" % lvl, [(h, 1)], (2 * r, 2 * r), g.active_indices, g.block_size[0], up.conv, 1, g.offset[0], dst)
+                h, r = dst, 2 * r
+        # ---- end: real GroupNorm on the edited activation + SiLU + conv_out (dense, library calls)
+        gn_w, gn_b, gn_eps, gn_g = m.norm_out.weight.detach(), m.norm_out.bias.detach(), m.norm_out.eps, m.norm_out.num_groups
+        w_out = m.conv_out.weight.detach().contiguous(memory_format=torch.channels_last)
+        b_out = m.conv_out.bias.detach()
+        self.output = torch.empty((1, cfg.out_ch, res, res), dtype=dt, device=self.dev)
+        h_last = h
+
+        def tail(_stream):
+            y = F.silu(F.group_norm(h_last, gn_g, gn_w, gn_b, gn_eps))
+            self.output.copy_(F.conv2d(y, w_out, b_out, 1, 1))
+
+        self.steps.append(tail)
+
+    # ------------------------------------------------------------------ execution
+    def run_eager(self) -> torch.Tensor:
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        with torch.no_grad():
+            for s in self.steps:
+                s(stream)
+        return self.output
+
+    def _finalize(self, use_graph: bool) -> None:
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.run_eager()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        before = ops.launch_count
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.run_eager()
+        else:
+            self.run_eager()
+        self.launches_per_step = ops.launch_count - before
+
+    def replay(self) -> torch.Tensor:
+        if self.graph is not None:
+            self.graph.replay()
+            return self.output
+        return self.run_eager()
+
+    # ------------------------------------------------------------------ accounting
+    def algorithmic_bytes(self) -> int:
+        return sum(f.bytes for f in self.fused)
+
+    def algorithmic_flops(self) -> int:
+        return sum(f.flops for f in self.fused)

@@ -106,3 +106,38 @@ def measure_dominant_kernel(model, dtype, flush):
     x = x1.to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
     layers = conv_layers_of_step(model, x, t.to(dev))
     return measure_layers(layers, dtype, flush)
+
+
+def measure_engine(engine, flush, reps: int = 5):
+    """Per-launch CUDA-event timing of every fused tile-conv launch of the step engine (cold L2).
+    achieved = sum(algorithmic bytes) / sum(launch durations)."""
+    dev = engine.dev
+    stream = torch.cuda.current_stream(dev)
+    tot_ms = 0.0
+    per = []
+    for f in engine.fused:
+        ms = 0.0
+        for i in range(reps):
+            if flush is not None:
+                flush.fill_(i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            f.launch(stream.cuda_stream)
+            b.record(stream)
+            b.synchronize()
+            ms += a.elapsed_time(b)
+        per.append((f.name, ms / reps, f.bytes, f.flops, f.tiles))
+        tot_ms += ms / reps
+    pk = peaks()
+    tot_bytes, tot_flops = float(engine.algorithmic_bytes()), float(engine.algorithmic_flops())
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+    slow = sorted(per, key=lambda r: -r[1])[:5]
+    return {
+        "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+        "kernel": "sige::tile_conv_mma_kernel (all %d fused gather-conv-scatter launches of one step)" % len(per),
+        "avg_launch_us": 1e3 * tot_ms / max(1, len(per)), "algorithmic_bytes_per_step": tot_bytes, "peak_source": pk["source"],
+        "tensor": {"achieved_tflops": tot_flops / (tot_ms * 1e-3) / 1e12, "peak_tflops": pk["bf16_tflops"],
+                   "frac": tot_flops / (tot_ms * 1e-3) / 1e12 / pk["bf16_tflops"]},
+        "slowest": [{"layer": n, "us": 1e3 * ms, "tiles": t, "GBps": by / (ms * 1e-3) / 1e9} for n, ms, by, fl, t in slow],
+        "note": "cold L2 (flushed before every launch); launch latency included in the event bracket",
+    }

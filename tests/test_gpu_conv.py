@@ -111,6 +111,7 @@ def _fused_desc(ops, x, wp, bias, idx, out, *, R, k, stride, off, scale=None, sh
     d.offH = d.offW = off
     d.residual = None if residual is None else residual.data_ptr()
     d.rC, d.res_c0 = (0 if residual is None else residual.shape[1]), 0
+    d._keep = (x, wp, bias, idx, out, scale, shift, residual, x2)   # descriptors hold raw pointers: keep the tensors alive
     return d
 
 
@@ -168,8 +169,6 @@ def test_fused_concat_and_upsample_sources(oracle):
     out = T(y, dtype, cl=True).clone(memory_format=torch.channels_last)
     d = _fused_desc(ops, T(x1, dtype, cl=True), ops.pack_conv_weight(T(w, dtype), dtype), None, T(idx), out, R=6, k=3, stride=1, off=1,
                     x2=T(x2, dtype, cl=True))
-    a, b2 = T(x1, dtype, cl=True), T(x2, dtype, cl=True)
-    d.src[0].ptr, d.src[1].ptr = a.data_ptr(), b2.data_ptr()
     ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert rel_err(out, want) <= 1e-3
