@@ -16,7 +16,7 @@ from . import ops
 class GraphedStep:
     """Static-input, static-output replay of ``model(x, t)`` in sparse mode."""
 
-    def __init__(self, model, x: torch.Tensor, t: torch.Tensor, warmup: int = 3):
+    def __init__(self, model, x: torch.Tensor, t: torch.Tensor, warmup: int = 3, use_graph: bool = True):
         self.model, self.x, self.t = model, x, t
         side = torch.cuda.Stream(device=x.device)
         side.wait_stream(torch.cuda.current_stream(x.device))
@@ -25,12 +25,21 @@ class GraphedStep:
                 model(x, t)
         torch.cuda.current_stream(x.device).wait_stream(side)
         torch.cuda.synchronize(x.device)
-        self.graph = torch.cuda.CUDAGraph()
         before = ops.launch_count
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.output = model(x, t)
-        self.launches_per_step = ops.launch_count - before   # launches of OUR kernels inside the graph
+        self.graph = None
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self.output = model(x, t)
+        else:
+            with torch.no_grad():
+                self.output = model(x, t)
+        self.launches_per_step = ops.launch_count - before   # launches of OUR kernels inside one step
 
     def replay(self) -> torch.Tensor:
-        self.graph.replay()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with torch.no_grad():
+                self.output = self.model(self.x, self.t)
         return self.output
