@@ -180,7 +180,15 @@ typedef struct {
     int offH, offW;         /* output origin = (off + idx) / stride  (scatter_kernel.cu:29,33) */
     const void *residual;   /* NHWC, same geometry as dst (rC channels), added in the epilogue; or NULL */
     int rC, res_c0;
+    /* ---- scheduling ---- */
+    int ksplit;             /* split-K factor = thread-block-cluster size (partials reduced over distributed
+                               shared memory): 0 = auto, or 1 / 2 / 4 / 8 */
+    int flags;              /* SIGE_CONV_* */
 } sige_tile_conv_t;
+
+/* Launch with programmatic dependent launch: the kernel prefetches its weights while the previous kernel
+ * of the stream drains, and waits (griddepcontrol.wait) before touching activations. */
+#define SIGE_CONV_PDL 1
 
 /* Fused gather -> (affine+SiLU) -> conv (+bias) -> (+residual) -> scatter, one launch. */
 int sige_tile_conv(const sige_tile_conv_t *p, sige_stream_t stream);

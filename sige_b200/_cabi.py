@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libsige_b200.so")
 F32, F16, BF16 = 0, 1, 2
 NCHW, NHWC = 0, 1
 ACT_IDENTITY, ACT_SWISH = 0, 1
+CONV_PDL = 1
 
 
 class SigeLibraryMissing(ImportError):
@@ -59,6 +60,7 @@ class TileConv(Structure):
         ("offH", c_int), ("offW", c_int),
         ("residual", c_void_p),
         ("rC", c_int), ("res_c0", c_int),
+        ("ksplit", c_int), ("flags", c_int),
     ]
 
 

@@ -21,14 +21,17 @@
 // Tensor-core instruction: mma.sync.m16n8k16 (HMMA on sm_100a).  The tcgen05/TMEM variant
 // for large edit ratios lives in tile_conv_tc5.cu (when built); this kernel is the latency-
 // oriented path used when the GEMM M dimension is a few hundred rows.
+#include <cooperative_groups.h>
+
 #include <type_traits>
 
 #include "common.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace sige {
 
 constexpr int KC = 64;        // channels per K chunk (128 bytes of fp16/bf16 per pixel row)
-constexpr int NSTAGE = 4;     // cp.async ring depth for the weight tiles
 
 struct ConvSeg {
     const void *ptr;
@@ -52,6 +55,8 @@ struct ConvParams {
     int Cin, Cout, kH, kW, taps, stride;
     int Ro, So, P;          // output tile extent, pixels per tile
     int tpc;                // tiles per CTA
+    int ksplit;             // split-K factor == cluster size along z (1, 2, 4 or 8)
+    int pdl;                // launched with programmatic dependent launch
     void *dst;
     int dst_is_stack;
     int dH, dW, dC, dst_c0;
@@ -96,7 +101,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // for all 8 -> conflict-free ldmatrix.
 __device__ __forceinline__ int halo_key(int y, int x) { return (x & 3) | ((y & 1) << 2); }
 
-template <typename T, int WM, int WN, int WARPS_M, int WARPS_N, int HALO_PIX>
+template <typename T, int WM, int WN, int WARPS_M, int WARPS_N, int HALO_PIX, int NSTAGE>
 struct ConvCfg {
     static constexpr int BM = WARPS_M * WM * 16;
     static constexpr int BN = WARPS_N * WN * 8;
@@ -111,10 +116,10 @@ struct ConvCfg {
     static constexpr int LOADS = (HALO_UNITS + NTHREADS - 1) / NTHREADS;
 };
 
-template <typename T, int WM, int WN, int WARPS_M, int WARPS_N, int HALO_PIX>
+template <typename T, int WM, int WN, int WARPS_M, int WARPS_N, int HALO_PIX, int NSTAGE>
 __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N)
 tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<T, WM, WN, WARPS_M, WARPS_N, HALO_PIX>;
+    using Cfg = ConvCfg<T, WM, WN, WARPS_M, WARPS_N, HALO_PIX, NSTAGE>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, NTHREADS = Cfg::NTHREADS, LOADS = Cfg::LOADS;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *halo[2] = {smem, smem + Cfg::HALO_BYTES};
@@ -126,7 +131,11 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
     const int n0 = blockIdx.y * BN;                // first output channel of this CTA
     const int ntile = min(p.tpc, p.NT - tile0);    // tiles actually present
     const int NC = p.Cin / KC;                     // K chunks
-    const int J = NC * p.taps;                     // weight tiles to stream
+    const int J = NC * p.taps;                     // (chunk, tap) steps of the whole K loop
+    // split-K: the cluster's CTAs (rank = blockIdx.z) each take a contiguous slice of the K loop
+    const int kr = blockIdx.z;
+    const int j_begin = (int)(((long long)J * kr) / p.ksplit), j_end = (int)(((long long)J * (kr + 1)) / p.ksplit);
+    const int c_first = j_begin / p.taps, c_last = (j_end - 1) / p.taps;
 
     // ---------------- halo loader bookkeeping (fixed per thread) ----------------
     // unit q -> (pixel, 16B unit u); pixel -> (tile_local, y, x)
@@ -211,9 +220,9 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
 
     // ---------------- weight tile loader ----------------
     auto b_issue = [&](int j) {
-        if (j < J) {
+        if (j < j_end) {
             const int c = j / p.taps, tap = j - c * p.taps;
-            unsigned char *st = bst + (j % NSTAGE) * Cfg::B_STAGE_BYTES;
+            unsigned char *st = bst + ((j - j_begin) % NSTAGE) * Cfg::B_STAGE_BYTES;
             const T *wbase = reinterpret_cast<const T *>(p.w) + ((long long)tap * p.Cout) * p.Cin + c * KC;
             for (int q = tid; q < BN * 8; q += NTHREADS) {
                 const int n = q >> 3, u = q & 7;
@@ -250,49 +259,56 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
             for (int z = 0; z < 4; ++z) acc[i][jn][z] = 0.f;
 
     // ---------------- prologue ----------------
-    halo_issue(0);
+    // weights do not depend on the previous kernel: start streaming them before the grid dependency wait
 #pragma unroll
-    for (int s = 0; s < NSTAGE - 1; ++s) b_issue(s);
-    halo_store(0, halo[0]);
+    for (int s = 0; s < NSTAGE - 1; ++s) b_issue(j_begin + s);
+    if (p.pdl) {
+        asm volatile("griddepcontrol.launch_dependents;\n" ::);   // let the next layer begin ITS weight prefetch
+        asm volatile("griddepcontrol.wait;\n" ::: "memory");       // previous layer's activations are now visible
+    }
+    halo_issue(c_first);
+    halo_store(c_first, halo[0]);
 
-    // ---------------- main loop ----------------
-    int j = 0;
-    for (int c = 0; c < NC; ++c) {
-        if (c + 1 < NC) halo_issue(c + 1);
-        const uint32_t hbase = smem_u32(halo[c & 1]);
-        for (int tap = 0; tap < p.taps; ++tap, ++j) {
-            cp_async_wait<NSTAGE - 2>();
-            __syncthreads();
-            b_issue(j + NSTAGE - 1);
-            const int ky = tap / p.kW, kx = tap - ky * p.kW;
-            const uint32_t bbase = smem_u32(bst + (j % NSTAGE) * Cfg::B_STAGE_BYTES);
-            uint32_t a_addr[WM];
-            int a_key[WM];
+    // ---------------- main loop over this CTA's K slice ----------------
+    int hb = 0;
+    for (int j = j_begin; j < j_end; ++j) {
+        const int c = j / p.taps, tap = j - c * p.taps;
+        if ((j == j_begin || tap == 0) && c < c_last) halo_issue(c + 1);   // prefetch the next chunk into registers
+        const uint32_t hbase = smem_u32(halo[hb]);
+        cp_async_wait<NSTAGE - 2>();
+        __syncthreads();
+        b_issue(j + NSTAGE - 1);
+        const int ky = tap / p.kW, kx = tap - ky * p.kW;
+        const uint32_t bbase = smem_u32(bst + ((j - j_begin) % NSTAGE) * Cfg::B_STAGE_BYTES);
+        uint32_t a_addr[WM];
+        int a_key[WM];
 #pragma unroll
-            for (int i = 0; i < WM; ++i) {
-                a_addr[i] = hbase + (a_pix0[i] + ky * p.S + kx) * 128;
-                a_key[i] = halo_key(a_y0[i] + ky, a_x0[i] + kx);
-            }
+        for (int i = 0; i < WM; ++i) {
+            a_addr[i] = hbase + (a_pix0[i] + ky * p.S + kx) * 128;
+            a_key[i] = halo_key(a_y0[i] + ky, a_x0[i] + kx);
+        }
 #pragma unroll
-            for (int kk = 0; kk < KC / 16; ++kk) {
-                uint32_t af[WM][4];
+        for (int kk = 0; kk < KC / 16; ++kk) {
+            uint32_t af[WM][4];
 #pragma unroll
-                for (int i = 0; i < WM; ++i)
-                    ldmatrix_x4(a_addr[i] + ((((kk << 1) | a_khalf) ^ a_key[i]) << 4), af[i][0], af[i][1], af[i][2], af[i][3]);
+            for (int i = 0; i < WM; ++i)
+                ldmatrix_x4(a_addr[i] + ((((kk << 1) | a_khalf) ^ a_key[i]) << 4), af[i][0], af[i][1], af[i][2], af[i][3]);
 #pragma unroll
-                for (int jp = 0; jp < WN / 2; ++jp) {
-                    const int n = warp_n * (WN * 8) + jp * 16 + b_nl;
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4(bbase + n * 128 + ((((kk << 1) | b_khalf) ^ (n & 7)) << 4), b0, b1, b2, b3);
+            for (int jp = 0; jp < WN / 2; ++jp) {
+                const int n = warp_n * (WN * 8) + jp * 16 + b_nl;
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(bbase + n * 128 + ((((kk << 1) | b_khalf) ^ (n & 7)) << 4), b0, b1, b2, b3);
 #pragma unroll
-                    for (int i = 0; i < WM; ++i) {
-                        mma16816<T>(acc[i][2 * jp], af[i], b0, b1);
-                        mma16816<T>(acc[i][2 * jp + 1], af[i], b2, b3);
-                    }
+                for (int i = 0; i < WM; ++i) {
+                    mma16816<T>(acc[i][2 * jp], af[i], b0, b1);
+                    mma16816<T>(acc[i][2 * jp + 1], af[i], b2, b3);
                 }
             }
         }
-        if (c + 1 < NC) halo_store(c + 1, halo[(c + 1) & 1]);
+        if ((tap == p.taps - 1 || j == j_end - 1) && c < c_last) {   // chunk finished: publish the prefetched one
+            halo_store(c + 1, halo[hb ^ 1]);
+            hb ^= 1;
+        }
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -310,8 +326,22 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
         }
     __syncthreads();
 
+    // split-K reduction over distributed shared memory: every CTA of the cluster staged its partial tile;
+    // rank r then sums ALL partials for its share of the rows (fixed order -> deterministic) and stores them.
     const int rows = ntile * p.P;
-    for (int q = tid; q < rows * (BN / 8); q += NTHREADS) {
+    int m_lo = 0, m_hi = rows;
+    const float *part[8];
+    part[0] = cst;
+    if (p.ksplit > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        const int per = (rows + p.ksplit - 1) / p.ksplit;
+        m_lo = min(rows, kr * per);
+        m_hi = min(rows, m_lo + per);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) part[r] = r < p.ksplit ? cluster.map_shared_rank(cst, r) : cst;
+    }
+    for (int q = tid + m_lo * (BN / 8); q < m_hi * (BN / 8); q += NTHREADS) {
         const int m = q / (BN / 8), nv = q - m * (BN / 8);
         const int n = n0 + nv * 8;
         if (n >= p.Cout) continue;
@@ -326,10 +356,14 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
             img = t / p.N;
         }
         if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) continue;
-        const float *cs = cst + m * Cfg::EPI_PITCH + nv * 8;
         float v[8];
-        const float4 c0 = *reinterpret_cast<const float4 *>(cs), c1 = *reinterpret_cast<const float4 *>(cs + 4);
-        v[0] = c0.x; v[1] = c0.y; v[2] = c0.z; v[3] = c0.w; v[4] = c1.x; v[5] = c1.y; v[6] = c1.z; v[7] = c1.w;
+#pragma unroll
+        for (int z = 0; z < 8; ++z) v[z] = 0.f;
+        for (int r = 0; r < p.ksplit; ++r) {
+            const float *cs = part[r] + m * Cfg::EPI_PITCH + nv * 8;
+            const float4 c0 = *reinterpret_cast<const float4 *>(cs), c1 = *reinterpret_cast<const float4 *>(cs + 4);
+            v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+        }
         if (p.bias) {
             const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
             const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
@@ -348,12 +382,13 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
         for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(v[z]);
         *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.dst) + pixel * p.dC + p.dst_c0 + n) = o;
     }
+    if (p.ksplit > 1) cg::this_cluster().sync();   // nobody leaves while a peer still reads its partial tile
 }
 
-template <typename T, int WM, int WN, int WARPS_M, int WARPS_N, int HALO_PIX>
+template <typename T, int WM, int WN, int WARPS_M, int WARPS_N, int HALO_PIX, int NSTAGE>
 static int launch_cfg(ConvParams &p, cudaStream_t st) {
-    using Cfg = ConvCfg<T, WM, WN, WARPS_M, WARPS_N, HALO_PIX>;
-    auto kern = tile_conv_mma_kernel<T, WM, WN, WARPS_M, WARPS_N, HALO_PIX>;
+    using Cfg = ConvCfg<T, WM, WN, WARPS_M, WARPS_N, HALO_PIX, NSTAGE>;
+    auto kern = tile_conv_mma_kernel<T, WM, WN, WARPS_M, WARPS_N, HALO_PIX, NSTAGE>;
     static int attr_dev = -1;   // per instantiation; one process drives one GPU, but stay correct if not
     int dev = 0;
     cudaGetDevice(&dev);
@@ -371,9 +406,48 @@ static int launch_cfg(ConvParams &p, cudaStream_t st) {
                   p.P, Cfg::BM, HALO_PIX);
         return 1;
     }
-    dim3 grid(ceil_div(p.NT, p.tpc), ceil_div(p.Cout, Cfg::BN));
-    kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(p);
-    return check_launch("sige_tile_conv");
+    const int J = (p.Cin / KC) * p.taps;
+    const long long base = (long long)ceil_div(p.NT, p.tpc) * ceil_div(p.Cout, Cfg::BN);
+    if (p.ksplit <= 0) {
+        // auto split-K: aim for ~2 CTAs per SM, keep >= 4 K steps per slice, cluster size <= 8 (portable limit)
+        int ks = 1;
+        while (ks < 8 && base * (ks * 2) <= 2 * 148 && J / (ks * 2) >= 4) ks *= 2;
+        p.ksplit = ks;
+    }
+    if (p.ksplit > J) p.ksplit = 1;
+    if (p.ksplit != 1 && p.ksplit != 2 && p.ksplit != 4 && p.ksplit != 8) {
+        set_error("sige_tile_conv: ksplit must be 1, 2, 4 or 8 (got %d)", p.ksplit);
+        return 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ceil_div(p.NT, p.tpc), ceil_div(p.Cout, Cfg::BN), p.ksplit);
+    cfg.blockDim = dim3(Cfg::NTHREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    if (p.ksplit > 1) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = 1;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = p.ksplit;
+        ++na;
+    }
+    if (p.pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) {
+        set_error("sige_tile_conv: launch failed (grid %d x %d x %d, %d threads, %d B smem): %s", cfg.gridDim.x, cfg.gridDim.y,
+                  cfg.gridDim.z, Cfg::NTHREADS, Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return 2;
+    }
+    return 0;
 }
 
 // CTA-count estimate used to pick a configuration: small grids want small CTA tiles.
@@ -384,15 +458,17 @@ static inline long long ctas_for(int NT, int P, int RS, int Cout, int BM, int BN
 }
 
 template <typename T> static int launch_tile_conv(ConvParams &p, cudaStream_t st) {
-    // L: 128x128 CTA tile, 8 warps;  M: 64x64, 4 warps;  S: 32x64, 4 warps.
+    // L: 128x128 CTA tile, 8 warps, 5-stage weight ring; M: 64x64, 4 warps, 8 stages; S: 32x64, 4 warps, 8 stages.
+    // Prefer the largest tile that still fills the machine; below that, the smallest tile plus split-K.
     const long long cL = ctas_for(p.NT, p.P, p.RS, p.Cout, 128, 128, 288);
     const long long cM = ctas_for(p.NT, p.P, p.RS, p.Cout, 64, 64, 144);
-    if (cL >= 296) return launch_cfg<T, 2, 8, 4, 2, 288>(p, st);
-    if (cM >= 148 || ctas_for(p.NT, p.P, p.RS, p.Cout, 32, 64, 72) < 0) {
-        if (cM > 0) return launch_cfg<T, 2, 4, 2, 2, 144>(p, st);
-        return launch_cfg<T, 2, 8, 4, 2, 288>(p, st);
+    const long long cS = ctas_for(p.NT, p.P, p.RS, p.Cout, 32, 64, 72);
+    if (cL >= 296) return launch_cfg<T, 2, 8, 4, 2, 288, 5>(p, st);
+    if (cM >= 148 || cS < 0) {
+        if (cM > 0) return launch_cfg<T, 2, 4, 2, 2, 144, 8>(p, st);
+        return launch_cfg<T, 2, 8, 4, 2, 288, 5>(p, st);
     }
-    return launch_cfg<T, 2, 2, 1, 4, 72>(p, st);
+    return launch_cfg<T, 2, 2, 1, 4, 72, 8>(p, st);
 }
 
 }  // namespace sige
@@ -434,6 +510,7 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     if (a->bias) SIGE_REQUIRE(((uintptr_t)a->bias & 15) == 0, "sige_tile_conv: bias not 16-byte aligned");
     SIGE_REQUIRE(a->affine_bstride == 0 || a->affine_bstride == a->Cin, "sige_tile_conv: affine_bstride must be 0 or Cin");
     SIGE_REQUIRE(a->act == SIGE_ACT_IDENTITY || a->act == SIGE_ACT_SWISH, "sige_tile_conv: unknown activation %d", a->act);
+    SIGE_REQUIRE(a->ksplit >= 0 && a->ksplit <= 8, "sige_tile_conv: ksplit out of range");
 
     ConvParams p;
     p.seg[0] = ConvSeg{a->src[0].ptr, a->src[0].C, a->src[0].up};
@@ -459,6 +536,8 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     p.offH = a->offH; p.offW = a->offW;
     p.residual = a->residual; p.rC = a->rC; p.res_c0 = a->res_c0;
     p.tpc = 1;
+    p.ksplit = a->ksplit;
+    p.pdl = (a->flags & SIGE_CONV_PDL) ? 1 : 0;
     if (a->dtype == SIGE_F16) return launch_tile_conv<__half>(p, (cudaStream_t)stream);
     return launch_tile_conv<__nv_bfloat16>(p, (cudaStream_t)stream);
 }

@@ -40,6 +40,12 @@ from .workloads.ddpm import AttnBlock, DenseDownsample, ResBlock, SIGEDDPMUNet, 
 
 AVAILABLE = True
 
+
+def _cabi_flags(pdl: bool) -> int:
+    from ._cabi import CONV_PDL
+
+    return CONV_PDL if pdl else 0
+
 Src = Tuple[torch.Tensor, int]  # (NHWC tensor [1, C, H, W] channels_last, upsample flag)
 
 
@@ -56,7 +62,7 @@ class FusedConv:
 
 
 class DDPMStepEngine:
-    def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True):
+    def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True, pdl: bool = False, ksplit: int = 0):
         if model.mode != "sparse":
             raise RuntimeError("DDPMStepEngine: run the dense pass, set_masks() and set_mode('sparse') first")
         p = next(model.parameters())
@@ -64,6 +70,7 @@ class DDPMStepEngine:
             raise RuntimeError("DDPMStepEngine needs a CUDA fp16/bf16 model (tensor-core path)")
         self.model, self.dev, self.dtype = model, p.device, p.dtype
         self.x = x_static
+        self.pdl, self.ksplit = pdl, ksplit
         assert x_static.is_cuda and x_static.dtype == self.dtype and x_static.is_contiguous(memory_format=torch.channels_last)
         self.steps: List = []          # callables taking the stream handle
         self.fused: List[FusedConv] = []
@@ -145,6 +152,8 @@ class DDPMStepEngine:
             d.residual, d.rC, d.res_c0 = residual.data_ptr(), residual.shape[1], 0
         else:
             d.residual, d.rC, d.res_c0 = None, 0, 0
+        d.ksplit = self.ksplit
+        d.flags = _cabi_flags(self.pdl)
         ro = (block - k) // stride + 1
         e = 2
         nbytes = e * (n * cin * block * block + taps * cout * cin + n * cout * ro * ro * (2 if residual is not None else 1))
