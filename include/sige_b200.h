@@ -189,6 +189,9 @@ typedef struct {
 /* Launch with programmatic dependent launch: the kernel prefetches its weights while the previous kernel
  * of the stream drains, and waits (griddepcontrol.wait) before touching activations. */
 #define SIGE_CONV_PDL 1
+/* Use the tcgen05 / TMEM / TMA kernel when the geometry allows (3x3 s1 on 6x6 tiles, 1x1 on 4x4 tiles,
+ * Cout % 64 == 0); otherwise the mma.sync kernel runs. */
+#define SIGE_CONV_TC5 2
 
 /* Fused gather -> (affine+SiLU) -> conv (+bias) -> (+residual) -> scatter, one launch. */
 int sige_tile_conv(const sige_tile_conv_t *p, sige_stream_t stream);

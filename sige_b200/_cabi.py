@@ -21,6 +21,7 @@ F32, F16, BF16 = 0, 1, 2
 NCHW, NHWC = 0, 1
 ACT_IDENTITY, ACT_SWISH = 0, 1
 CONV_PDL = 1
+CONV_TC5 = 2
 
 
 class SigeLibraryMissing(ImportError):

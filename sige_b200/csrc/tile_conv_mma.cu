@@ -471,6 +471,9 @@ template <typename T> static int launch_tile_conv(ConvParams &p, cudaStream_t st
     return launch_cfg<T, 2, 2, 1, 4, 72, 8>(p, st);
 }
 
+bool tc5_supported(const sige_tile_conv_t *a);
+int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st);
+
 }  // namespace sige
 
 using namespace sige;
@@ -511,6 +514,9 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     SIGE_REQUIRE(a->affine_bstride == 0 || a->affine_bstride == a->Cin, "sige_tile_conv: affine_bstride must be 0 or Cin");
     SIGE_REQUIRE(a->act == SIGE_ACT_IDENTITY || a->act == SIGE_ACT_SWISH, "sige_tile_conv: unknown activation %d", a->act);
     SIGE_REQUIRE(a->ksplit >= 0 && a->ksplit <= 8, "sige_tile_conv: ksplit out of range");
+
+    // Blackwell-native path (tcgen05 + TMEM + TMA, tile_conv_tc5.cu) when requested and the geometry fits
+    if ((a->flags & SIGE_CONV_TC5) && tc5_supported(a)) return tc5_launch(a, (cudaStream_t)stream);
 
     ConvParams p;
     p.seg[0] = ConvSeg{a->src[0].ptr, a->src[0].C, a->src[0].up};

@@ -1,0 +1,590 @@
+// tile_conv_tc5.cu — Blackwell-native fused gather -> (affine + SiLU) -> tile conv -> (+bias, +residual)
+// -> scatter: tcgen05.mma with the accumulator in TMEM, weights staged by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle), warp-specialised producer / MMA / epilogue roles,
+// mbarrier pipelines, split-K over a thread-block cluster with a distributed-shared-memory reduction.
+//
+// Same contract as tile_conv_mma.cu (one launch == the reference's Gather -> SIGEConv2d -> Scatter
+// triple, reference sige/nn/gather.py:76-89, base.py:88-89, scatter.py:41-60); this file covers the
+// two geometries that make up >90 % of a DDPM step: 3x3 stride-1 on 6x6 halo tiles and 1x1 on 4x4
+// tiles.  Everything else stays on the mma.sync kernel.
+//
+// GEMM view per CTA: D[128 x BN] += A[128 x K] * B[K x BN], K = taps * Cin, UMMA 128 x BN x 16.
+//   * 128 rows = 8 active tiles x 16 output pixels.  For the 3x3 case the row order is
+//     m = oy*32 + tile*4 + ox and the A operand of tap (ky,kx) must be a plainly strided
+//     [128 rows x 64 ch] K-major matrix (UMMA descriptors cannot express a gather).  Trick: keep
+//     THREE column-shifted copies of the halo tiles in shared memory, copy kx laid out as
+//     [y = 0..5][tile = 0..7][x' = 0..3] rows of 128 bytes holding halo pixel (y, kx + x').  Then
+//     tap (ky,kx) is copy kx shifted by ky*32 rows: row m of the MMA reads row m + 32*ky — a pure
+//     start-address offset of ky*4096 bytes, which is a multiple of the 1024-byte swizzle atom.
+//     Cost: each gathered pixel is stored ~2x instead of the 9x of an im2col.
+//   * B (weights, pre-packed [tap][Cout][Cin]) is a 2-D tensor map {Cin, taps*Cout}; one TMA box
+//     {64, BN} per (tap, 64-channel chunk) lands in a 128B-swizzled stage of an mbarrier ring.
+//   * one elected thread issues tcgen05.mma; tcgen05.commit releases weight stages / halo buffers and
+//     finally signals the epilogue, which pulls the fp32 accumulator out of TMEM with tcgen05.ld.
+#include <cooperative_groups.h>
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sige {
+namespace tc5 {
+
+constexpr int KC = 64;                 // channels per K chunk = one 128-byte swizzle row
+constexpr int TILES = 8;               // tiles per CTA  (8 x 16 output pixels = 128 GEMM rows)
+constexpr int NPROD_WARPS = 8;         // A-operand producer warps (also the epilogue warps)
+constexpr int NTHREADS = 32 * (2 + NPROD_WARPS);
+constexpr int NPROD = 32 * NPROD_WARPS;
+constexpr int A_COPY_BYTES = 6 * TILES * 4 * 128;        // one kx-copy: [6][8][4] rows x 128 B = 24576
+constexpr int A_BUF_BYTES = 3 * A_COPY_BYTES;            // 73728 per 64-channel chunk
+constexpr int EPI_PAD = 4;
+
+struct Seg {
+    const void *ptr;
+    int C;
+    int up;
+};
+
+struct Params {
+    Seg seg[2];
+    int C0;
+    int H, W;
+    int src_is_stack;
+    const int32_t *idx;
+    int N, NT;
+    const float *scale, *shift;
+    int affine_bstride;
+    int act;
+    const float *bias;
+    int Cin, Cout, taps;       // taps = 9 (3x3 on 6x6 tiles) or 1 (1x1 on 4x4 tiles)
+    void *dst;
+    int dst_is_stack;
+    int dH, dW, dC, dst_c0;
+    int offH, offW;
+    const void *residual;
+    int rC, res_c0;
+    int ksplit;
+    int pdl;
+    int is_bf16;
+};
+
+template <int BN> struct Cfg {
+    static constexpr int NSTB = (BN == 128) ? 4 : 8;           // weight ring depth
+    static constexpr int B_STAGE_BYTES = BN * 128;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = 2 * A_BUF_BYTES;
+    static constexpr int OFF_BAR = OFF_B + NSTB * B_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;    // barriers + slack for the 1024-byte alignment
+    static constexpr int EPI_PITCH = BN + EPI_PAD;             // floats
+    static_assert(128 * EPI_PITCH * 4 <= 2 * A_BUF_BYTES, "epilogue staging must fit in the halo buffers");
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+        "l"(tmap), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups) | [46,48) version = 1
+//   [49,52) base offset = 0 (all operand bases are 1024-byte aligned) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, fp32 accumulate, K-major A and B:
+//   [4,6) c_format = 1 (F32) | [7,10) a_format | [10,13) b_format (0 = F16, 1 = BF16)
+//   [15] a_major = 0 | [16] b_major = 0 | [17,23) N >> 3 | [24,29) M >> 4
+__device__ __forceinline__ uint32_t make_idesc(int bn, int bf16) {
+    return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+template <typename T, int BN, int TAPS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap) {
+    using C = Cfg<BN>;
+    constexpr int NSTB = C::NSTB;
+    constexpr int R = (TAPS == 9) ? 6 : 4;            // halo tile extent
+    constexpr int RS = R * R;
+    constexpr int UNITS = TILES * RS * 8;             // 16-byte units gathered per chunk
+    constexpr int LOADS = (UNITS + NPROD - 1) / NPROD;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = s32(smem);
+    const uint32_t bar0 = sbase + C::OFF_BAR;
+    // barrier layout (8 bytes each): b_full[NSTB] | b_empty[NSTB] | a_full[2] | a_empty[2] | acc_full | tmem slot
+    auto B_FULL = [&](int s) { return bar0 + 8 * s; };
+    auto B_EMPTY = [&](int s) { return bar0 + 8 * (NSTB + s); };
+    auto A_FULL = [&](int b) { return bar0 + 8 * (2 * NSTB + b); };
+    auto A_EMPTY = [&](int b) { return bar0 + 8 * (2 * NSTB + 2 + b); };
+    const uint32_t ACC_FULL = bar0 + 8 * (2 * NSTB + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::OFF_BAR + 8 * (2 * NSTB + 5));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile0 = blockIdx.x * TILES;
+    const int n0 = blockIdx.y * BN;
+    const int ntile = min(TILES, p.NT - tile0);
+    const int NC = p.Cin / KC;
+    const int J = NC * TAPS;
+    const int kr = blockIdx.z;
+    const int j_begin = (int)(((long long)J * kr) / p.ksplit), j_end = (int)(((long long)J * (kr + 1)) / p.ksplit);
+    const int c_first = j_begin / TAPS, c_last = (j_end - 1) / TAPS;
+
+    // ---------------- one-time setup ----------------
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&wmap) : "memory");
+            for (int s = 0; s < NSTB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+            for (int b = 0; b < 2; ++b) { mbar_init(A_FULL(b), NPROD); mbar_init(A_EMPTY(b), 1); }
+            mbar_init(ACC_FULL, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(s32(tmem_slot), BN);     // BN fp32 accumulator columns (power of two >= 32)
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (p.pdl) asm volatile("griddepcontrol.launch_dependents;\n" ::);   // the next layer may start prefetching ITS weights
+
+    if (warp == 0) {
+        // ================= TMA producer: weights =================
+        if (lane == 0) {
+            for (int j = j_begin; j < j_end; ++j) {
+                const int it = j - j_begin, s = it % NSTB, k = it / NSTB;
+                mbar_wait(B_EMPTY(s), (k & 1) ^ 1);
+                mbar_expect_tx(B_FULL(s), C::B_STAGE_BYTES);
+                const int c = j / TAPS, tap = j - c * TAPS;
+                tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES, &wmap, c * KC, tap * p.Cout + n0, B_FULL(s));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BN, p.is_bf16);
+            int ab = 0, ause = 0;             // halo buffer index and how many times it has been used
+            for (int j = j_begin; j < j_end; ++j) {
+                const int c = j / TAPS, tap = j - c * TAPS;
+                if (j == j_begin || tap == 0) {                       // a new chunk starts: wait for its halo buffer
+                    mbar_wait(A_FULL(ab), (ause >> 1) & 1);
+                    tc_fence_after();
+                }
+                const int it = j - j_begin, s = it % NSTB, k = it / NSTB;
+                mbar_wait(B_FULL(s), k & 1);
+                tc_fence_after();
+                const int ky = (TAPS == 9) ? tap / 3 : 0, kx = (TAPS == 9) ? tap - 3 * ky : 0;
+                const uint32_t a_addr = sbase + C::OFF_A + ab * A_BUF_BYTES + kx * A_COPY_BYTES + ky * (32 * 128);
+                const uint32_t b_addr = sbase + C::OFF_B + s * C::B_STAGE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk)
+                    umma_f16(tmem_base, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), idesc, (j > j_begin || kk > 0) ? 1u : 0u);
+                umma_commit(B_EMPTY(s));                              // weight stage free once these MMAs retire
+                if (tap == TAPS - 1 || j == j_end - 1) {              // chunk done: halo buffer free
+                    umma_commit(A_EMPTY(ab));
+                    ab ^= 1;
+                    ++ause;
+                }
+            }
+            umma_commit(ACC_FULL);
+        }
+        __syncwarp();
+    } else {
+        // ================= A-operand producers: gather + pre-op + swizzled stores =================
+        const int ptid = tid - 64;
+        // per-thread gather list (fixed for the whole kernel)
+        int g_pix[LOADS];     // (hh << 16) | ww in the logical source image, -1 = zero fill, -2 = nothing to do
+        int g_img[LOADS], g_ab[LOADS];
+        int g_xyt[LOADS];     // x | y << 4 | tile << 8
+#pragma unroll
+        for (int k = 0; k < LOADS; ++k) {
+            const int q = ptid + k * NPROD;
+            g_pix[k] = -2; g_img[k] = 0; g_ab[k] = 0; g_xyt[k] = 0;
+            if (q < UNITS) {
+                const int pix = q >> 3;
+                const int tl = pix / RS, rem = pix - tl * RS;
+                const int y = rem / R, x = rem - y * R;
+                g_xyt[k] = x | (y << 4) | (tl << 8);
+                g_pix[k] = -1;
+                const int t = tile0 + tl;
+                if (t < p.NT) {
+                    const int n = t % p.N, b = t / p.N;
+                    int hh = y, ww = x, img = t;
+                    if (!p.src_is_stack) { hh += __ldg(p.idx + 2 * n); ww += __ldg(p.idx + 2 * n + 1); img = b; }
+                    g_img[k] = img; g_ab[k] = b;
+                    if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) g_pix[k] = (hh << 16) | ww;
+                }
+            }
+        }
+        uint4 regs[LOADS];
+        auto issue = [&](int c) {
+            const int cbase = c * KC;
+            const int sg = cbase >= p.C0 ? 1 : 0;
+            const Seg &seg = p.seg[sg];
+            const int cl = cbase - (sg ? p.C0 : 0);
+            const int Hs = p.H >> seg.up, Ws = p.W >> seg.up;
+#pragma unroll
+            for (int k = 0; k < LOADS; ++k) {
+                regs[k] = make_uint4(0, 0, 0, 0);
+                if (g_pix[k] >= 0) {
+                    const int hh = (g_pix[k] >> 16) >> seg.up, ww = (g_pix[k] & 0xffff) >> seg.up;
+                    const int u = (ptid + k * NPROD) & 7;
+                    const T *src = reinterpret_cast<const T *>(seg.ptr) + (((long long)g_img[k] * Hs + hh) * Ws + ww) * seg.C + cl + u * 8;
+                    regs[k] = __ldg(reinterpret_cast<const uint4 *>(src));
+                }
+            }
+        };
+        const bool pre = (p.scale != nullptr) || (p.shift != nullptr) || (p.act != SIGE_ACT_IDENTITY);
+        auto store = [&](int c, unsigned char *abuf) {
+#pragma unroll
+            for (int k = 0; k < LOADS; ++k) {
+                if (g_pix[k] == -2) continue;
+                uint4 v = regs[k];
+                const int u = (ptid + k * NPROD) & 7;
+                if (pre && g_pix[k] >= 0) {
+                    const int ch = c * KC + u * 8;
+                    T *e = reinterpret_cast<T *>(&v);
+                    float sc[8], sh[8];
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) { sc[z] = 1.f; sh[z] = 0.f; }
+                    if (p.scale) {
+                        const float4 *s4 = reinterpret_cast<const float4 *>(p.scale + (long long)g_ab[k] * p.affine_bstride + ch);
+                        const float4 a = __ldg(s4), b = __ldg(s4 + 1);
+                        sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+                    }
+                    if (p.shift) {
+                        const float4 *s4 = reinterpret_cast<const float4 *>(p.shift + (long long)g_ab[k] * p.affine_bstride + ch);
+                        const float4 a = __ldg(s4), b = __ldg(s4 + 1);
+                        sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w; sh[4] = b.x; sh[5] = b.y; sh[6] = b.z; sh[7] = b.w;
+                    }
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) {
+                        float f = fmaf(DT<T>::to_f(e[z]), sc[z], sh[z]);
+                        f = activate<true>(p.act, f);
+                        e[z] = DT<T>::from_f(f);
+                    }
+                }
+                const int x = g_xyt[k] & 15, y = (g_xyt[k] >> 4) & 15, tl = g_xyt[k] >> 8;
+                if (TAPS == 9) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int xp = x - kx;
+                        if (xp >= 0 && xp < 4) {
+                            const int row = y * 32 + tl * 4 + xp;
+                            *reinterpret_cast<uint4 *>(abuf + kx * A_COPY_BYTES + row * 128 + ((u ^ (row & 7)) << 4)) = v;
+                        }
+                    }
+                } else {
+                    const int row = tl * 16 + y * 4 + x;
+                    *reinterpret_cast<uint4 *>(abuf + row * 128 + ((u ^ (row & 7)) << 4)) = v;
+                }
+            }
+        };
+        if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");   // activations of the previous layer are complete
+        issue(c_first);
+        int ab = 0, ause = 0;
+        for (int c = c_first; c <= c_last; ++c) {
+            mbar_wait(A_EMPTY(ab), ((ause >> 1) & 1) ^ 1);            // the MMAs that read this buffer have retired
+            store(c, smem + C::OFF_A + ab * A_BUF_BYTES);
+            fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(A_FULL(ab));
+            if (c < c_last) issue(c + 1);
+            ab ^= 1;
+            ++ause;
+        }
+    }
+
+    // ---------------- epilogue ----------------
+    float *cst = reinterpret_cast<float *>(smem + C::OFF_A);
+    if (warp >= 2 && warp < 6) {
+        // four warps cover the 128 TMEM lanes; warp w may only touch lanes 32*(w%4)..+31
+        mbar_wait(ACC_FULL, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
+            float4 *dstv = reinterpret_cast<float4 *>(cst + m * C::EPI_PITCH + c0);
+#pragma unroll
+            for (int z = 0; z < 8; ++z)
+                dstv[z] = make_float4(__uint_as_float(r[4 * z]), __uint_as_float(r[4 * z + 1]), __uint_as_float(r[4 * z + 2]),
+                                      __uint_as_float(r[4 * z + 3]));
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, BN);
+
+    if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    // split-K reduction over distributed shared memory + coalesced scatter stores (all warps)
+    int m_lo = 0, m_hi = 128;
+    const float *part[8];
+    part[0] = cst;
+    if (p.ksplit > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        const int per = 128 / p.ksplit;
+        m_lo = kr * per;
+        m_hi = m_lo + per;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) part[r] = r < p.ksplit ? cluster.map_shared_rank(cst, r) : cst;
+    }
+    for (int q = tid + m_lo * (BN / 8); q < m_hi * (BN / 8); q += NTHREADS) {
+        const int m = q / (BN / 8), nv = q - m * (BN / 8);
+        const int n = n0 + nv * 8;
+        if (n >= p.Cout) continue;
+        int tl, oy, ox;
+        if (TAPS == 9) { oy = m >> 5; tl = (m >> 2) & 7; ox = m & 3; } else { tl = m >> 4; oy = (m >> 2) & 3; ox = m & 3; }
+        if (tl >= ntile) continue;
+        const int t = tile0 + tl;
+        int hh = oy, ww = ox, img = t;
+        if (!p.dst_is_stack) {
+            const int nn = t % p.N;
+            hh += p.offH + __ldg(p.idx + 2 * nn);
+            ww += p.offW + __ldg(p.idx + 2 * nn + 1);
+            img = t / p.N;
+        }
+        if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) continue;
+        float v[8];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) v[z] = 0.f;
+        for (int r = 0; r < p.ksplit; ++r) {
+            const float *cs = part[r] + m * C::EPI_PITCH + nv * 8;
+            const float4 c0 = *reinterpret_cast<const float4 *>(cs), c1 = *reinterpret_cast<const float4 *>(cs + 4);
+            v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+        }
+        if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        const long long pixel = ((long long)img * p.dH + hh) * p.dW + ww;
+        if (p.residual) {
+            const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(p.residual) + pixel * p.rC + p.res_c0 + n));
+            const T *re = reinterpret_cast<const T *>(&rr);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) v[z] += DT<T>::to_f(re[z]);
+        }
+        uint4 o;
+        T *oe = reinterpret_cast<T *>(&o);
+#pragma unroll
+        for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(v[z]);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.dst) + pixel * p.dC + p.dst_c0 + n) = o;
+    }
+    if (p.ksplit > 1) cg::this_cluster().sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// host: tensor map + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+template <typename T, int BN, int TAPS> static int launch(Params &p, const void *w_packed, cudaStream_t st) {
+    using C = Cfg<BN>;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        set_error("sige_tile_conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
+        return 2;
+    }
+    CUtensorMap wmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)p.Cin, (cuuint64_t)TAPS * p.Cout};
+    const cuuint64_t gstr[1] = {(cuuint64_t)p.Cin * 2};
+    const cuuint32_t box[2] = {KC, (cuuint32_t)BN};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&wmap, p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w_packed),
+                     gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("sige_tile_conv(tcgen05): cuTensorMapEncodeTiled failed with %d", (int)r);
+        return 2;
+    }
+    auto kern = tile_conv_tc5_kernel<T, BN, TAPS>;
+    static int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("sige_tile_conv(tcgen05): cannot reserve %d bytes of shared memory: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+            return 2;
+        }
+        attr_dev = dev;
+    }
+    const int J = (p.Cin / KC) * TAPS;
+    const long long base = (long long)ceil_div(p.NT, TILES) * (p.Cout / BN);
+    if (p.ksplit <= 0) {
+        int ks = 1;
+        while (ks < 8 && base * (ks * 2) <= 148 && J / (ks * 2) >= 3) ks *= 2;
+        p.ksplit = ks;
+    }
+    if (p.ksplit > J) p.ksplit = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ceil_div(p.NT, TILES), p.Cout / BN, p.ksplit);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    if (p.ksplit > 1) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = 1;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = p.ksplit;
+        ++na;
+    }
+    if (p.pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, wmap);
+    if (e != cudaSuccess) {
+        set_error("sige_tile_conv(tcgen05): launch failed (grid %d x %d x %d): %s", cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z,
+                  cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return 2;
+    }
+    return 0;
+}
+
+}  // namespace tc5
+
+// Can the tcgen05 kernel take this layer?  (3x3 stride 1 on 6x6 tiles, or 1x1 on 4x4 tiles; Cout % 64 == 0)
+bool tc5_supported(const sige_tile_conv_t *a) {
+    const bool g3 = a->kH == 3 && a->kW == 3 && a->stride == 1 && a->R == 6 && a->S == 6;
+    const bool g1 = a->kH == 1 && a->kW == 1 && a->stride == 1 && a->R == 4 && a->S == 4;
+    return (g3 || g1) && a->Cout % 64 == 0 && a->Cin % 64 == 0 && (a->ksplit == 0 || a->ksplit == 1 || a->ksplit == 2 || a->ksplit == 4 || a->ksplit == 8);
+}
+
+// Arguments were validated by sige_tile_conv (tile_conv_mma.cu) before this is called.
+int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
+    tc5::Params p;
+    p.seg[0] = tc5::Seg{a->src[0].ptr, a->src[0].C, a->src[0].up};
+    p.seg[1] = a->n_src == 2 ? tc5::Seg{a->src[1].ptr, a->src[1].C, a->src[1].up} : p.seg[0];
+    p.C0 = a->src[0].C;
+    p.src_is_stack = a->src_is_stack;
+    p.H = a->src_is_stack ? a->R : a->H;
+    p.W = a->src_is_stack ? a->S : a->W;
+    p.idx = a->idx;
+    p.N = a->N;
+    p.NT = a->B * a->N;
+    p.scale = a->scale; p.shift = a->shift; p.affine_bstride = a->affine_bstride; p.act = a->act;
+    p.bias = a->bias;
+    p.Cin = a->Cin; p.Cout = a->Cout; p.taps = a->kH * a->kW;
+    p.dst = a->dst; p.dst_is_stack = a->dst_is_stack;
+    p.dH = a->dst_is_stack ? 4 : a->dH;
+    p.dW = a->dst_is_stack ? 4 : a->dW;
+    p.dC = a->dC; p.dst_c0 = a->dst_c0;
+    p.offH = a->offH; p.offW = a->offW;
+    p.residual = a->residual; p.rC = a->rC; p.res_c0 = a->res_c0;
+    p.ksplit = a->ksplit;
+    p.pdl = (a->flags & SIGE_CONV_PDL) ? 1 : 0;
+    p.is_bf16 = a->dtype == SIGE_BF16;
+    // BN = 128 only when that still leaves enough CTAs; small problems want more, narrower CTAs
+    const long long m_blocks = ceil_div(p.NT, tc5::TILES);
+    const bool wide = (a->Cout % 128 == 0) && (m_blocks * (a->Cout / 128) >= 148);
+    const bool three = p.taps == 9;
+#define SIGE_TC5(T)                                                                              \
+    (wide ? (three ? tc5::launch<T, 128, 9>(p, a->w_packed, st) : tc5::launch<T, 128, 1>(p, a->w_packed, st)) \
+          : (three ? tc5::launch<T, 64, 9>(p, a->w_packed, st) : tc5::launch<T, 64, 1>(p, a->w_packed, st)))
+    if (a->dtype == SIGE_F16) return SIGE_TC5(__half);
+    return SIGE_TC5(__nv_bfloat16);
+#undef SIGE_TC5
+}
+
+}  // namespace sige

@@ -41,10 +41,11 @@ from .workloads.ddpm import AttnBlock, DenseDownsample, ResBlock, SIGEDDPMUNet, 
 AVAILABLE = True
 
 
-def _cabi_flags(pdl: bool) -> int:
-    from ._cabi import CONV_PDL
+def _cabi_flags(pdl: bool, tc5: bool) -> int:
+    from ._cabi import CONV_PDL, CONV_TC5
 
-    return CONV_PDL if pdl else 0
+    return (CONV_PDL if pdl else 0) | (CONV_TC5 if tc5 else 0)
+
 
 Src = Tuple[torch.Tensor, int]  # (NHWC tensor [1, C, H, W] channels_last, upsample flag)
 
@@ -62,7 +63,8 @@ class FusedConv:
 
 
 class DDPMStepEngine:
-    def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True, pdl: bool = False, ksplit: int = 0):
+    def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True, pdl: bool = False, ksplit: int = 0,
+                 tc5: bool = False):
         if model.mode != "sparse":
             raise RuntimeError("DDPMStepEngine: run the dense pass, set_masks() and set_mode('sparse') first")
         p = next(model.parameters())
@@ -70,7 +72,7 @@ class DDPMStepEngine:
             raise RuntimeError("DDPMStepEngine needs a CUDA fp16/bf16 model (tensor-core path)")
         self.model, self.dev, self.dtype = model, p.device, p.dtype
         self.x = x_static
-        self.pdl, self.ksplit = pdl, ksplit
+        self.pdl, self.ksplit, self.tc5 = pdl, ksplit, tc5
         assert x_static.is_cuda and x_static.dtype == self.dtype and x_static.is_contiguous(memory_format=torch.channels_last)
         self.steps: List = []          # callables taking the stream handle
         self.fused: List[FusedConv] = []
@@ -153,7 +155,7 @@ class DDPMStepEngine:
         else:
             d.residual, d.rC, d.res_c0 = None, 0, 0
         d.ksplit = self.ksplit
-        d.flags = _cabi_flags(self.pdl)
+        d.flags = _cabi_flags(self.pdl, self.tc5)
         ro = (block - k) // stride + 1
         e = 2
         nbytes = e * (n * cin * block * block + taps * cout * cin + n * cout * ro * ro * (2 if residual is not None else 1))

@@ -320,7 +320,7 @@ def launch_tile_conv(desc: TileConv, stream: int) -> None:
 
 
 def tile_conv_stack(x: torch.Tensor, w_packed: torch.Tensor, bias_f32: Optional[torch.Tensor], ksize: Tuple[int, int],
-                    stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    stride: int, out: Optional[torch.Tensor] = None, flags: int = 0, ksplit: int = 0) -> torch.Tensor:
     """Tensor-core conv on a stack: x (M, Cin, R, S) channels-last -> (M, Cout, Ro, So) channels-last.
     Equivalent of F.conv2d(x, w, b, stride, padding=0) (reference sige/nn/base.py:88-89)."""
     _require_cuda(x, w_packed, bias_f32)
@@ -353,6 +353,7 @@ def tile_conv_stack(x: torch.Tensor, w_packed: torch.Tensor, bias_f32: Optional[
     d.dH, d.dW, d.dC, d.dst_c0 = Ro, So, Cout, 0
     d.offH = d.offW = 0
     d.residual = None; d.rC = 0; d.res_c0 = 0
+    d.flags, d.ksplit = flags, ksplit
     with torch.cuda.device(x.device):
         launch_tile_conv(d, _stream(x))
     return out

@@ -225,3 +225,61 @@ def test_linearity_and_dense_equals_sparse_at_full_size(oracle):
         ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
     lin = 0.5 * o1.float() + o2.float()
     assert float((o3.float() - lin).abs().max() / lin.abs().max()) <= 3e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# Blackwell-native kernel (tcgen05.mma + TMEM + TMA weights), flags = SIGE_CONV_TC5
+# ---------------------------------------------------------------------------------------------------
+TC5 = 2
+TC5_STACK_CASES = [(64, 128, 128, 6, 3), (8, 64, 64, 6, 3), (1, 64, 64, 6, 3), (13, 128, 192, 6, 3), (32, 384, 128, 6, 3), (16, 512, 256, 6, 3),
+                   (700, 128, 128, 6, 3), (1300, 64, 256, 6, 3), (64, 256, 128, 4, 1), (12, 384, 256, 4, 1), (5, 64, 64, 4, 1), (300, 128, 512, 4, 1)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_tc5_conv_on_stacks(oracle, dtype):
+    from sige_b200 import ops
+
+    rng = np.random.default_rng(13)
+    for (M, Ci, Co, R, k) in TC5_STACK_CASES:
+        x = _round(rng.standard_normal((M, Ci, R, R)).astype(np.float32), dtype)
+        w = _round(rng.standard_normal((Co, Ci, k, k)).astype(np.float32) / np.sqrt(Ci * k * k), dtype)
+        b = rng.standard_normal((Co,)).astype(np.float32)
+        want = oracle.conv2d_tiles(x, w, b, (1, 1))
+        wp = ops.pack_conv_weight(T(w, dtype), dtype)
+        tx, tb = T(x, dtype, cl=True), T(b)
+        for ks in (1, 0, 2, 4, 8):
+            got = ops.tile_conv_stack(tx, wp, tb, (k, k), 1, flags=TC5, ksplit=ks)
+            torch.cuda.synchronize()
+            e = rel_err(got, want)
+            assert e <= TOL[dtype], "tc5 stack case %s ksplit %d: rel err %g" % ((M, Ci, Co, R, k), ks, e)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_tc5_fused_gather_conv_scatter_vs_oracle(oracle, dtype):
+    from sige_b200 import ops
+
+    rng = np.random.default_rng(14)
+    for (B, C, Co, H, W, bs, ts, k, off, p) in [(1, 128, 128, 64, 64, 6, 4, 3, 1, 0.02), (2, 64, 192, 24, 40, 6, 4, 3, 1, 0.1),
+                                                (1, 256, 128, 32, 32, 4, 4, 1, 0, 0.05), (1, 64, 64, 16, 16, 6, 4, 3, 1, 1.0)]:
+        mask = rng.random((H, W)) < p
+        mask[0, 0] = mask[H - 1, W - 1] = True
+        idx = oracle.reduce_mask(mask, bs, ts, off)
+        x = _round(rng.standard_normal((B, C, H, W)).astype(np.float32), dtype)
+        w = _round(rng.standard_normal((Co, C, k, k)).astype(np.float32) / np.sqrt(C * k * k), dtype)
+        b = rng.standard_normal((Co,)).astype(np.float32)
+        sc = (1 + 0.2 * rng.standard_normal((B, C, 1, 1))).astype(np.float32)
+        sh = (0.2 * rng.standard_normal((B, C, 1, 1))).astype(np.float32)
+        y = _round(rng.standard_normal((B, Co, H, W)).astype(np.float32), dtype)
+        res = _round(rng.standard_normal((B, Co, H, W)).astype(np.float32), dtype)
+        g = _round(oracle.gather(x, bs, bs, idx, sc, sh, "swish", False), dtype)
+        want = oracle.scatter(oracle.conv2d_tiles(g, w, b, (1, 1)), y, off, off, 1, 1, idx, res)
+        out = T(y, dtype, cl=True).clone(memory_format=torch.channels_last)
+        d = _fused_desc(ops, T(x, dtype, cl=True), ops.pack_conv_weight(T(w, dtype), dtype), T(b), T(idx), out, R=bs, k=k, stride=1, off=off,
+                        scale=T(sc).reshape(B, C).contiguous(), shift=T(sh).reshape(B, C).contiguous(), act=1, residual=T(res, dtype, cl=True))
+        for ks, flags in ((1, TC5), (0, TC5), (4, TC5), (0, TC5 | 1)):
+            out.copy_(T(y, dtype, cl=True))
+            d.ksplit, d.flags = ks, flags
+            ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            e = rel_err(out, want)
+            assert e <= 2 * TOL[dtype], "tc5 fused case %s ksplit %d flags %d: rel err %g" % ((B, C, Co, H, W, bs, k), ks, flags, e)
