@@ -203,6 +203,25 @@ int sige_tile_conv_generic(const void *x, const void *w, const void *bias, void 
                            int strideH, int strideW, int dilH, int dilW, int groups,
                            sige_stream_t stream);
 
+/* ------------------------------------------------------------------------- */
+/* dense glue of a step (not tile-shaped), NHWC f16/bf16                      */
+/*   reference diffusion/models/ddpm_arch/sige_fused_unet.py:395 (conv_in),    */
+/*   :431-433 (norm_out -> swish -> conv_out), models/common.py:37-57 (fold)   */
+/* ------------------------------------------------------------------------- */
+/* 3x3 / stride 1 / pad 1 convolution with Cin <= 4 (the RGB stem): x NHWC (B,H,W,Cin), w OIHW, out NHWC. */
+int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out, int dtype, int B,
+                      int H, int W, int Cin, int Cout, sige_stream_t stream);
+/* GroupNorm statistics folded to per-channel fp32 (scale, shift) [B, C]: GroupNorm(x) == x*scale + shift.
+ * Deterministic two-stage reduction; `workspace` holds sige_group_norm_fold_workspace(B, C) floats. */
+int sige_group_norm_fold_workspace(int B, int C);
+int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, int groups, float eps,
+                         const void *gamma, const void *beta, float *scale, float *shift,
+                         float *workspace, int workspace_floats, sige_stream_t stream);
+/* out(NCHW, B x Cout x H x W) = conv3x3_pad1( act(x*scale + shift) ), Cout <= 4; scale/shift fp32 [B, C] or NULL. */
+int sige_conv_out_nhwc(const void *x, const float *scale, const float *shift, int act, const void *w,
+                       const void *bias, void *out, int dtype, int B, int H, int W, int C, int Cout,
+                       sige_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,286 @@
+// dense_glue.cu — the three dense, non-tile-shaped layers of a DDPM step, NHWC fp16/bf16:
+//   conv_in   3x3, 3 -> C channels on the full image        (reference sige_fused_unet.py:395)
+//   GroupNorm statistics of the final activation, folded to per-channel (scale, shift)
+//   conv_out  SiLU(x*scale+shift) -> 3x3, C -> 3 channels   (reference sige_fused_unet.py:431-433)
+// The reference leaves these to cuDNN / ATen; at a 1.2 % edit they are ~20 % of the step
+// (profiles/r01a_launches_engine_step.csv: 244 us for the channels-last GroupNorm alone), and
+// they are pure HBM streams: 16.8 MB written (conv_in) or read (stats, conv_out) at 256x256x128.
+//
+// All three are deterministic (fixed reduction order), stream-ordered and allocation-free.
+#include "common.cuh"
+
+namespace sige {
+
+// ------------------------------------------------------------------------------------------
+// conv_in: Cin <= 4, Cout % 8 == 0.  One thread = one pixel x 8 output channels (one 16-byte store);
+// the 9*Cin inputs come through L1, the 9*Cin*8 weights of the thread's channel octet from shared.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *__restrict__ bias,
+                                                      T *__restrict__ out, int B, int H, int W, int Cin, int Cout) {
+    extern __shared__ float wsm[];   // [Cout/8][9*Cin][8] + bias [Cout]
+    const int K = 9 * Cin, OV = Cout / 8;
+    for (int e = threadIdx.x; e < Cout * K; e += blockDim.x) {
+        const int co = e / K, k = e - co * K;              // k = ci*9 + tap in OIHW
+        const int ci = k / 9, tap = k - ci * 9;
+        wsm[((co >> 3) * K + tap * Cin + ci) * 8 + (co & 7)] = DT<T>::to_f(w[e]);
+    }
+    float *bsm = wsm + Cout * K;
+    for (int e = threadIdx.x; e < Cout; e += blockDim.x) bsm[e] = bias ? DT<T>::to_f(bias[e]) : 0.f;
+    __syncthreads();
+    const long long total = (long long)B * H * W * OV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ov = i % OV;
+        long long pix = i / OV;
+        const int ww = pix % W; pix /= W;
+        const int hh = pix % H;
+        const int b = pix / H;
+        float acc[8];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) acc[z] = bsm[ov * 8 + z];
+        const float *wv = wsm + (long long)ov * K * 8;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int y = hh + ky - 1;
+            if (y < 0 || y >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = ww + kx - 1;
+                if (xx < 0 || xx >= W) continue;
+                const T *px = x + (((long long)b * H + y) * W + xx) * Cin;
+                const float *wt = wv + (ky * 3 + kx) * Cin * 8;
+                for (int ci = 0; ci < Cin; ++ci) {
+                    const float v = DT<T>::to_f(px[ci]);
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) acc[z] = fmaf(v, wt[ci * 8 + z], acc[z]);
+                }
+            }
+        }
+        uint4 o;
+        T *oe = reinterpret_cast<T *>(&o);
+#pragma unroll
+        for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(acc[z]);
+        *reinterpret_cast<uint4 *>(out + i * 8) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm fold.  Stage 1: every CTA reduces a contiguous pixel range to per-channel (sum, sumsq);
+// stage 2: one CTA adds the partials in a fixed order and emits scale = gamma*rstd,
+// shift = beta - mean*rstd*gamma  (GroupNorm(x) == x*scale + shift, reference models/common.py:37-57).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gn_partial_kernel(const T *__restrict__ x, int HW, int C, float *__restrict__ part, int nblk) {
+    // grid = (nblk, B); thread = (pixel slot, channel octet)
+    const int CV = C / 8;
+    const int slots = blockDim.x / CV;
+    const int cv = threadIdx.x % CV, slot = threadIdx.x / CV;
+    const int b = blockIdx.y;
+    const int per = (HW + nblk - 1) / nblk;
+    const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+    float s[8], q[8];
+#pragma unroll
+    for (int z = 0; z < 8; ++z) { s[z] = 0.f; q[z] = 0.f; }
+    if (slot < slots) {
+        for (int p = p0 + slot; p < p1; p += slots) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(x + ((long long)b * HW + p) * C + cv * 8));
+            const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) { const float f = DT<T>::to_f(e[z]); s[z] += f; q[z] = fmaf(f, f, q[z]); }
+        }
+    }
+    extern __shared__ float red[];   // [slots][C][2]
+    if (slot < slots) {
+#pragma unroll
+        for (int z = 0; z < 8; ++z) { red[(slot * C + cv * 8 + z) * 2] = s[z]; red[(slot * C + cv * 8 + z) * 2 + 1] = q[z]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float ss = 0.f, qq = 0.f;
+        for (int sl = 0; sl < slots; ++sl) { ss += red[(sl * C + c) * 2]; qq += red[(sl * C + c) * 2 + 1]; }
+        float *o = part + (((long long)b * nblk + blockIdx.x) * C + c) * 2;
+        o[0] = ss; o[1] = qq;
+    }
+}
+
+template <typename T>
+__global__ void gn_finalize_kernel(const float *__restrict__ part, int nblk, int HW, int C, int G, float eps, const T *__restrict__ gamma,
+                                   const T *__restrict__ beta, float *__restrict__ scale, float *__restrict__ shift) {
+    // grid = B, block = C threads (C <= 1024)
+    extern __shared__ float sm[];   // [C][2]
+    const int b = blockIdx.x, c = threadIdx.x;
+    if (c < C) {
+        double ss = 0.0, qq = 0.0;
+        for (int k = 0; k < nblk; ++k) {
+            const float *p = part + (((long long)b * nblk + k) * C + c) * 2;
+            ss += p[0]; qq += p[1];
+        }
+        sm[2 * c] = (float)ss; sm[2 * c + 1] = (float)qq;
+    }
+    __syncthreads();
+    if (c < C) {
+        const int per = C / G, g = c / per;
+        double ss = 0.0, qq = 0.0;
+        for (int k = 0; k < per; ++k) { ss += sm[2 * (g * per + k)]; qq += sm[2 * (g * per + k) + 1]; }
+        const double n = (double)per * HW;
+        const double mean = ss / n;
+        double var = qq / n - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float ga = gamma ? DT<T>::to_f(gamma[c]) : 1.f, be = beta ? DT<T>::to_f(beta[c]) : 0.f;
+        scale[(long long)b * C + c] = ga * rstd;
+        shift[(long long)b * C + c] = be - (float)mean * rstd * ga;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// conv_out: y = conv3x3(act(x*scale+shift)), C -> Cout <= 4, output NCHW.
+// CTA = 8 x 32 output pixels; the (8+2) x (32+2) halo is transformed ONCE into shared memory
+// (row pitch C*2+16 bytes -> conflict-free 16-byte reads), then one thread = one output pixel.
+// ------------------------------------------------------------------------------------------
+constexpr int CO_TH = 8, CO_TW = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(CO_TH *CO_TW) conv_out_kernel(const T *__restrict__ x, const float *__restrict__ scale,
+                                                                  const float *__restrict__ shift, int act, const T *__restrict__ w,
+                                                                  const T *__restrict__ bias, T *__restrict__ out, int B, int H, int W,
+                                                                  int C, int Cout) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int pitch = C * 2 + 16;
+    const int HP = CO_TH + 2, WP = CO_TW + 2;
+    unsigned char *tile = smraw;                                             // [HP*WP][pitch]
+    float *wsm = reinterpret_cast<float *>(smraw + ((HP * WP * pitch + 15) & ~15));   // [9][C][4]
+    const int b = blockIdx.z, ty0 = blockIdx.y * CO_TH, tx0 = blockIdx.x * CO_TW;
+    for (int e = threadIdx.x; e < 9 * C * 4; e += blockDim.x) {
+        const int co = e & 3, rest = e >> 2;
+        const int ci = rest % C, tap = rest / C;
+        wsm[e] = co < Cout ? DT<T>::to_f(w[((long long)co * C + ci) * 9 + tap]) : 0.f;
+    }
+    const int CV = C / 8;
+    const bool pre = scale || shift || act != SIGE_ACT_IDENTITY;
+    for (int e = threadIdx.x; e < HP * WP * CV; e += blockDim.x) {
+        const int cv = e % CV, pp = e / CV;
+        const int py = pp / WP, px = pp - py * WP;
+        const int hh = ty0 + py - 1, ww = tx0 + px - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            v = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)b * H + hh) * W + ww) * C + cv * 8));
+            if (pre) {
+                T *el = reinterpret_cast<T *>(&v);
+#pragma unroll
+                for (int z = 0; z < 8; ++z) {
+                    const int c = cv * 8 + z;
+                    float f = DT<T>::to_f(el[z]);
+                    f = fmaf(f, scale ? scale[(long long)b * C + c] : 1.f, shift ? shift[(long long)b * C + c] : 0.f);
+                    el[z] = DT<T>::from_f(activate<true>(act, f));
+                }
+            }
+        }
+        *reinterpret_cast<uint4 *>(tile + pp * pitch + cv * 16) = v;       // zero padding AFTER the pre-op
+    }
+    __syncthreads();
+    const int ly = threadIdx.x / CO_TW, lx = threadIdx.x % CO_TW;
+    const int hh = ty0 + ly, ww = tx0 + lx;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        const unsigned char *row = tile + ((ly + ky) * WP + lx + kx) * pitch;
+        const float4 *wt = reinterpret_cast<const float4 *>(wsm + tap * C * 4);
+        for (int cv = 0; cv < CV; ++cv) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(row + cv * 16);
+            const T *el = reinterpret_cast<const T *>(&v);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) {
+                const float f = DT<T>::to_f(el[z]);
+                const float4 wv = wt[cv * 8 + z];
+                acc[0] = fmaf(f, wv.x, acc[0]); acc[1] = fmaf(f, wv.y, acc[1]); acc[2] = fmaf(f, wv.z, acc[2]); acc[3] = fmaf(f, wv.w, acc[3]);
+            }
+        }
+    }
+    if (hh < H && ww < W)
+        for (int co = 0; co < Cout; ++co)
+            out[(((long long)b * Cout + co) * H + hh) * W + ww] = DT<T>::from_f(acc[co] + (bias ? DT<T>::to_f(bias[co]) : 0.f));
+}
+
+}  // namespace sige
+
+using namespace sige;
+
+extern "C" {
+
+int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out, int dtype, int B, int H, int W, int Cin, int Cout,
+                      sige_stream_t stream) {
+    SIGE_REQUIRE(x && w && out, "sige_conv_in_nhwc: null pointer");
+    SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 4 && Cout > 0 && Cout % 8 == 0, "sige_conv_in_nhwc: needs Cin <= 4 and Cout %% 8 == 0");
+    SIGE_REQUIRE(((uintptr_t)out & 15) == 0, "sige_conv_in_nhwc: output not 16-byte aligned");
+    const size_t smem = sizeof(float) * ((size_t)Cout * 9 * Cin + Cout);
+    SIGE_REQUIRE(smem <= 48 * 1024, "sige_conv_in_nhwc: weights do not fit in shared memory");
+    const long long total = (long long)B * H * W * (Cout / 8);
+    const long long want_blocks = (total + 255) / 256;
+    const int grid = (int)(want_blocks < 148LL * 16 ? want_blocks : 148LL * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case SIGE_F16: conv_in_kernel<__half><<<grid, 256, smem, st>>>((const __half *)x, (const __half *)w, (const __half *)bias, (__half *)out, B, H, W, Cin, Cout); break;
+        case SIGE_BF16: conv_in_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)w, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)out, B, H, W, Cin, Cout); break;
+        default: set_error("sige_conv_in_nhwc: dtype must be f16/bf16"); return 1;
+    }
+    return check_launch("sige_conv_in_nhwc");
+}
+
+int sige_group_norm_fold_workspace(int B, int C) { return B * 296 * C * 2; }
+
+int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, int groups, float eps, const void *gamma, const void *beta,
+                         float *scale, float *shift, float *workspace, int workspace_floats, sige_stream_t stream) {
+    SIGE_REQUIRE(x && scale && shift && workspace, "sige_group_norm_fold: null pointer");
+    SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 1024 && groups > 0 && C % groups == 0, "sige_group_norm_fold: bad shape (C %% 8, C <= 1024)");
+    SIGE_REQUIRE(((uintptr_t)x & 15) == 0, "sige_group_norm_fold: input not 16-byte aligned");
+    const int HW = H * W;
+    int nblk = min(296, max(1, HW / 64));
+    SIGE_REQUIRE(workspace_floats >= B * nblk * C * 2, "sige_group_norm_fold: workspace too small (%d floats, need %d)", workspace_floats, B * nblk * C * 2);
+    const int CV = C / 8;
+    SIGE_REQUIRE(CV <= 256, "sige_group_norm_fold: too many channels");
+    const int slots = 256 / CV;
+    const size_t smem1 = sizeof(float) * (size_t)slots * C * 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 g1(nblk, B);
+#define SIGE_GN(T)                                                                                                                       \
+    do {                                                                                                                                 \
+        if (smem1 > 48 * 1024) cudaFuncSetAttribute(gn_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);        \
+        gn_partial_kernel<T><<<g1, 256, smem1, st>>>((const T *)x, HW, C, workspace, nblk);                                               \
+        gn_finalize_kernel<T><<<B, ((C + 31) / 32) * 32, sizeof(float) * 2 * C, st>>>(workspace, nblk, HW, C, groups, eps, (const T *)gamma, \
+                                                                                      (const T *)beta, scale, shift);                   \
+    } while (0)
+    switch (dtype) {
+        case SIGE_F16: SIGE_GN(__half); break;
+        case SIGE_BF16: SIGE_GN(__nv_bfloat16); break;
+        default: set_error("sige_group_norm_fold: dtype must be f16/bf16"); return 1;
+    }
+#undef SIGE_GN
+    return check_launch("sige_group_norm_fold");
+}
+
+int sige_conv_out_nhwc(const void *x, const float *scale, const float *shift, int act, const void *w, const void *bias, void *out, int dtype,
+                       int B, int H, int W, int C, int Cout, sige_stream_t stream) {
+    SIGE_REQUIRE(x && w && out, "sige_conv_out_nhwc: null pointer");
+    SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && Cout >= 1 && Cout <= 4, "sige_conv_out_nhwc: needs C %% 8 == 0 and Cout <= 4");
+    SIGE_REQUIRE(act == SIGE_ACT_IDENTITY || act == SIGE_ACT_SWISH, "sige_conv_out_nhwc: unknown activation %d", act);
+    SIGE_REQUIRE(((uintptr_t)x & 15) == 0, "sige_conv_out_nhwc: input not 16-byte aligned");
+    const int pitch = C * 2 + 16;
+    const size_t smem = (((size_t)(CO_TH + 2) * (CO_TW + 2) * pitch + 15) & ~(size_t)15) + sizeof(float) * 9 * C * 4;
+    SIGE_REQUIRE(smem <= 227 * 1024, "sige_conv_out_nhwc: %d channels do not fit in shared memory", C);
+    dim3 grid((W + CO_TW - 1) / CO_TW, (H + CO_TH - 1) / CO_TH, B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SIGE_CO(T)                                                                                                        \
+    do {                                                                                                                  \
+        cudaFuncSetAttribute(conv_out_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
+        conv_out_kernel<T><<<grid, CO_TH * CO_TW, smem, st>>>((const T *)x, scale, shift, act, (const T *)w, (const T *)bias, (T *)out, B, H, W, \
+                                                              C, Cout);                                                  \
+    } while (0)
+    switch (dtype) {
+        case SIGE_F16: SIGE_CO(__half); break;
+        case SIGE_BF16: SIGE_CO(__nv_bfloat16); break;
+        default: set_error("sige_conv_out_nhwc: dtype must be f16/bf16"); return 1;
+    }
+#undef SIGE_CO
+    return check_launch("sige_conv_out_nhwc");
+}
+
+}  // extern "C"

@@ -227,11 +227,11 @@ class DDPMStepEngine:
         res = cfg.image_size
         dt = self.dtype
         # ---- conv_in: dense, 3 input channels (library call inside the graph)
-        w_in, b_in = m.conv_in.weight.detach().to(dt).contiguous(memory_format=torch.channels_last), m.conv_in.bias.detach().to(dt)
+        w_in, b_in = m.conv_in.weight.detach().to(dt).contiguous(), m.conv_in.bias.detach().to(dt).contiguous()
         h0 = self._empty(cfg.ch, res, res)
 
         def conv_in(_stream):
-            h0.copy_(F.conv2d(self.x, w_in, b_in, 1, 1))
+            ops.conv_in_nhwc(self.x, w_in, b_in, out=h0)
 
         self.steps.append(conv_in)
         hs: List[Tuple[torch.Tensor, int]] = [(h0, res)]
@@ -278,15 +278,19 @@ class DDPMStepEngine:
                 self.conv("up.%d.upsample" % lvl, [(h, 1)], (2 * r, 2 * r), g.active_indices, g.block_size[0], up.conv, 1, g.offset[0], dst)
                 h, r = dst, 2 * r
         # ---- end: real GroupNorm on the edited activation + SiLU + conv_out (dense, library calls)
-        gn_w, gn_b, gn_eps, gn_g = m.norm_out.weight.detach(), m.norm_out.bias.detach(), m.norm_out.eps, m.norm_out.num_groups
-        w_out = m.conv_out.weight.detach().contiguous(memory_format=torch.channels_last)
-        b_out = m.conv_out.bias.detach()
+        gn_w, gn_b = m.norm_out.weight.detach().to(dt).contiguous(), m.norm_out.bias.detach().to(dt).contiguous()
+        gn_eps, gn_g = m.norm_out.eps, m.norm_out.num_groups
+        w_out, b_out = m.conv_out.weight.detach().to(dt).contiguous(), m.conv_out.bias.detach().to(dt).contiguous()
         self.output = torch.empty((1, cfg.out_ch, res, res), dtype=dt, device=self.dev)
         h_last = h
+        c_last = h_last.shape[1]
+        gn_scale = torch.empty((1, c_last), dtype=torch.float32, device=self.dev)
+        gn_shift = torch.empty((1, c_last), dtype=torch.float32, device=self.dev)
+        gn_ws = torch.empty((ops._cabi.lib().sige_group_norm_fold_workspace(1, c_last),), dtype=torch.float32, device=self.dev)
 
         def tail(_stream):
-            y = F.silu(F.group_norm(h_last, gn_g, gn_w, gn_b, gn_eps))
-            self.output.copy_(F.conv2d(y, w_out, b_out, 1, 1))
+            ops.group_norm_fold(h_last, gn_g, gn_eps, gn_w, gn_b, scale=gn_scale, shift=gn_shift, workspace=gn_ws)
+            ops.conv_out_nhwc(h_last, gn_scale, gn_shift, "swish", w_out, b_out, out=self.output)
 
         self.steps.append(tail)
 

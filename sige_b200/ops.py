@@ -391,3 +391,65 @@ def tile_conv_generic(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torc
         )
     _bump()
     return out
+
+
+# --------------------------------------------------------------------------------------
+# dense glue of a step (conv_in / GroupNorm fold / conv_out), NHWC f16/bf16
+# --------------------------------------------------------------------------------------
+def conv_in_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 pad-1 conv with Cin <= 4 on a channels-last image (reference sige_fused_unet.py:395)."""
+    _require_cuda(x, weight, bias)
+    x, _ = _dense(x, NHWC)
+    B, Cin, H, W = x.shape
+    w = weight.detach().to(x.dtype).contiguous()
+    b = None if bias is None else bias.detach().to(x.dtype).contiguous()
+    Cout = w.shape[0]
+    if out is None:
+        out = _empty_like_layout((B, Cout, H, W), x, NHWC)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().sige_conv_in_nhwc(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), _dt(x), B, H, W,
+                                                 Cin, Cout, _stream(x)), "sige_conv_in_nhwc")
+    _bump()
+    return out
+
+
+def group_norm_fold(x: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+                    scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """(scale, shift) fp32 [B, C] with GroupNorm(x) == x*scale + shift (reference models/common.py:37-57)."""
+    _require_cuda(x, gamma, beta)
+    x, _ = _dense(x, NHWC)
+    B, C, H, W = x.shape
+    g = None if gamma is None else gamma.detach().to(x.dtype).contiguous()
+    bt = None if beta is None else beta.detach().to(x.dtype).contiguous()
+    if scale is None:
+        scale = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    if shift is None:
+        shift = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    need = _cabi.lib().sige_group_norm_fold_workspace(B, C)
+    if workspace is None:
+        workspace = torch.empty((need,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().sige_group_norm_fold(x.data_ptr(), _dt(x), B, H, W, C, groups, float(eps), None if g is None else g.data_ptr(),
+                                                    None if bt is None else bt.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                    workspace.data_ptr(), workspace.numel(), _stream(x)), "sige_group_norm_fold")
+    _bump(2)
+    return scale, shift
+
+
+def conv_out_nhwc(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], activation_name: str, weight: torch.Tensor,
+                  bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NCHW out = conv3x3_pad1(act(x*scale+shift)), Cout <= 4 (reference sige_fused_unet.py:431-433)."""
+    _require_cuda(x, scale, shift, weight, bias)
+    x, _ = _dense(x, NHWC)
+    B, C, H, W = x.shape
+    w = weight.detach().to(x.dtype).contiguous()
+    b = None if bias is None else bias.detach().to(x.dtype).contiguous()
+    Cout = w.shape[0]
+    if out is None:
+        out = torch.empty((B, Cout, H, W), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().sige_conv_out_nhwc(x.data_ptr(), None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
+                                                  _act(activation_name), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), _dt(x), B,
+                                                  H, W, C, Cout, _stream(x)), "sige_conv_out_nhwc")
+    _bump()
+    return out

@@ -59,4 +59,4 @@ def test_engine_matches_modules_and_reference(tag, tc5):
     print("%s: engine-vs-modules %.3g, engine-vs-reference %.3g, modules-vs-reference %.3g, %d fused launches" %
           (tag, e_mod, e_ref, m_ref, len(eng.fused)))
     assert e_mod <= 2e-2 and e_ref <= 2e-2
-    assert eng.launches_per_step == len(eng.fused) > 0
+    assert eng.launches_per_step >= len(eng.fused) > 0

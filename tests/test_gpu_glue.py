@@ -1,0 +1,50 @@
+"""Dense glue kernels (conv_in, GroupNorm fold, conv_out) vs a plain PyTorch fp32 reference of the same
+op (these are floating-point kernels with no counterpart in the reference's native code: the reference
+calls ATen/cuDNN for them, sige_fused_unet.py:395,431-433)."""
+import pytest
+import torch
+from torch.nn import functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-3), (torch.bfloat16, 8e-3)])
+def test_conv_in(dtype, tol):
+    from sige_b200 import ops
+
+    torch.manual_seed(0)
+    for (B, Cin, Cout, H, W) in [(1, 3, 128, 256, 256), (2, 3, 64, 37, 53), (1, 4, 8, 8, 8), (1, 1, 16, 5, 9)]:
+        x = torch.randn(B, Cin, H, W, device=DEV).to(dtype)
+        w = (torch.randn(Cout, Cin, 3, 3, device=DEV) / (Cin * 9) ** 0.5).to(dtype)
+        b = torch.randn(Cout, device=DEV).to(dtype)
+        want = F.conv2d(x.float(), w.float(), b.float(), 1, 1)
+        got = ops.conv_in_nhwc(x.contiguous(memory_format=torch.channels_last), w, b)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+        assert float((got.float() - want).abs().max() / want.abs().max()) <= tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+def test_group_norm_fold_and_conv_out(dtype, tol):
+    from sige_b200 import ops
+
+    torch.manual_seed(1)
+    for (B, C, G, H, W, Cout) in [(1, 128, 32, 256, 256, 3), (2, 64, 32, 24, 40, 3), (1, 256, 32, 16, 16, 4), (1, 32, 32, 7, 9, 1)]:
+        x = (torch.randn(B, C, H, W, device=DEV) * 1.5 + 0.3).to(dtype).contiguous(memory_format=torch.channels_last)
+        gamma = (1 + 0.1 * torch.randn(C, device=DEV)).to(dtype)
+        beta = (0.1 * torch.randn(C, device=DEV)).to(dtype)
+        w = (torch.randn(Cout, C, 3, 3, device=DEV) / (C * 9) ** 0.5).to(dtype)
+        b = torch.randn(Cout, device=DEV).to(dtype)
+        scale, shift = ops.group_norm_fold(x, G, 1e-6, gamma, beta)
+        gn = F.group_norm(x.float(), G, gamma.float(), beta.float(), 1e-6)
+        folded = x.float() * scale.view(B, C, 1, 1) + shift.view(B, C, 1, 1)
+        assert float((folded - gn).abs().max() / gn.abs().max()) <= 1e-4      # fp32 statistics
+        s1, h1 = ops.group_norm_fold(x, G, 1e-6, gamma, beta)
+        assert torch.equal(s1, scale) and torch.equal(h1, shift), "deterministic reduction"
+        want = F.conv2d(F.silu(gn), w.float(), b.float(), 1, 1)
+        got = ops.conv_out_nhwc(x, scale, shift, "swish", w, b)
+        assert got.shape == want.shape and got.is_contiguous()
+        assert float((got.float() - want).abs().max() / want.abs().max()) <= tol
+        plain = ops.conv_out_nhwc(x, None, None, "identity", w, None)
+        want2 = F.conv2d(x.float(), w.float(), None, 1, 1)
+        assert float((plain.float() - want2).abs().max() / want2.abs().max()) <= tol
