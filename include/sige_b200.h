@@ -142,8 +142,9 @@ int sige_scatter_gather(const void *x, const void *y, int dtype, int layout, int
 /*    diffusion/models/ddpm_arch/sige_fused_unet.py:111-128)                   */
 /* ------------------------------------------------------------------------- */
 
-/* Weight repack for the tensor-core path: OIHW (any dtype) -> [kH*kW][Cout][Cin]
- * in `dst_dtype` (f16/bf16).  Run once per weight. */
+/* Weight repack for the tensor-core path: OIHW (any dtype) -> [kH*kW][Cin/64][Cout][64]
+ * in `dst_dtype` (f16/bf16) — the slab of one (tap, 64-channel chunk, Cout block) is contiguous.
+ * Run once per weight.  (Cin not a multiple of 64: plain [kH*kW][Cout][Cin].) */
 int sige_pack_conv_weight(const void *w_oihw, int src_dtype, int Cout, int Cin, int kH, int kW,
                           void *w_packed, int dst_dtype, sige_stream_t stream);
 
@@ -153,6 +154,18 @@ typedef struct {
     int C;           /* channels in this segment (multiple of 64 on the tensor-core path) */
     int up;          /* 0, or 1 = nearest-neighbour x2 upsample applied on read */
 } sige_conv_src_t;
+
+/* Extra destination of the fused epilogue: aux = act(out * scale[c] + shift[c]) written next to `dst` (same
+ * geometry).  Lets the PRODUCER of an activation apply the consumer's GroupNorm affine + SiLU once per
+ * element, so the consumer's gather stage is a pure copy (reference applies it in every gather,
+ * sige/cuda/gather_kernel.cu:45-65). */
+typedef struct {
+    void *ptr;          /* NHWC, C channels per pixel, same B/H/W (or stack shape) as dst */
+    int C, c0;          /* writes channels [c0, c0 + Cout) */
+    const float *scale; /* fp32 [Cout] or NULL */
+    const float *shift; /* fp32 [Cout] or NULL */
+    int act;            /* sige_act_t */
+} sige_conv_aux_t;
 
 typedef struct {
     int dtype; /* SIGE_F16 / SIGE_BF16 (tensor cores) */
@@ -170,7 +183,7 @@ typedef struct {
     int affine_bstride;     /* 0 (shared) or Cin (per batch element) */
     int act;                /* sige_act_t */
     /* ---- conv ---- */
-    const void *w_packed;   /* [kH*kW][Cout][Cin], from sige_pack_conv_weight */
+    const void *w_packed;   /* from sige_pack_conv_weight */
     const float *bias;      /* fp32 [Cout] or NULL */
     int Cin, Cout, kH, kW, stride;
     /* ---- destination ---- */
@@ -184,6 +197,9 @@ typedef struct {
     int ksplit;             /* split-K factor = thread-block-cluster size (partials reduced over distributed
                                shared memory): 0 = auto, or 1 / 2 / 4 / 8 */
     int flags;              /* SIGE_CONV_* */
+    /* ---- optional extra destinations ---- */
+    int n_aux;              /* 0, 1 or 2 */
+    sige_conv_aux_t aux[2];
 } sige_tile_conv_t;
 
 /* Launch with programmatic dependent launch: the kernel prefetches its weights while the previous kernel
@@ -208,9 +224,11 @@ int sige_tile_conv_generic(const void *x, const void *w, const void *bias, void 
 /*   reference diffusion/models/ddpm_arch/sige_fused_unet.py:395 (conv_in),    */
 /*   :431-433 (norm_out -> swish -> conv_out), models/common.py:37-57 (fold)   */
 /* ------------------------------------------------------------------------- */
-/* 3x3 / stride 1 / pad 1 convolution with Cin <= 4 (the RGB stem): x NHWC (B,H,W,Cin), w OIHW, out NHWC. */
+/* 3x3 / stride 1 / pad 1 convolution with Cin <= 4 (the RGB stem): x NHWC (B,H,W,Cin), w OIHW, out NHWC;
+ * up to two extra outputs aux[i] = act(out*scale+shift) (NHWC, Cout channels). */
 int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out, int dtype, int B,
-                      int H, int W, int Cin, int Cout, sige_stream_t stream);
+                      int H, int W, int Cin, int Cout, int n_aux, const sige_conv_aux_t *aux,
+                      sige_stream_t stream);
 /* GroupNorm statistics folded to per-channel fp32 (scale, shift) [B, C]: GroupNorm(x) == x*scale + shift.
  * Deterministic two-stage reduction; `workspace` holds sige_group_norm_fold_workspace(B, C) floats. */
 int sige_group_norm_fold_workspace(int B, int C);

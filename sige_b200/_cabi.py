@@ -40,6 +40,10 @@ class ConvSrc(Structure):
     _fields_ = [("ptr", c_void_p), ("C", c_int), ("up", c_int)]
 
 
+class ConvAux(Structure):
+    _fields_ = [("ptr", c_void_p), ("C", c_int), ("c0", c_int), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int)]
+
+
 class TileConv(Structure):
     _fields_ = [
         ("dtype", c_int),
@@ -62,6 +66,7 @@ class TileConv(Structure):
         ("residual", c_void_p),
         ("rC", c_int), ("res_c0", c_int),
         ("ksplit", c_int), ("flags", c_int),
+        ("n_aux", c_int), ("aux", ConvAux * 2),
     ]
 
 
@@ -85,7 +90,7 @@ PROTOTYPES = {
     "sige_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "sige_tile_conv": (_I, [POINTER(TileConv), _P]),
     "sige_tile_conv_generic": (_I, [_P, _P, _P, _P] + [_I] * 14 + [_P]),
-    "sige_conv_in_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "sige_conv_in_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "sige_group_norm_fold_workspace": (_I, [_I, _I]),
     "sige_group_norm_fold": (_I, [_P, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P, _P, _I, _P]),
     "sige_conv_out_nhwc": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

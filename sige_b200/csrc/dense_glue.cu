@@ -15,9 +15,16 @@ namespace sige {
 // conv_in: Cin <= 4, Cout % 8 == 0.  One thread = one pixel x 8 output channels (one 16-byte store);
 // the 9*Cin inputs come through L1, the 9*Cin*8 weights of the thread's channel octet from shared.
 // ------------------------------------------------------------------------------------------
+struct InAux {
+    void *ptr;
+    const float *scale, *shift;
+    int act;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *__restrict__ bias,
-                                                      T *__restrict__ out, int B, int H, int W, int Cin, int Cout) {
+                                                      T *__restrict__ out, int B, int H, int W, int Cin, int Cout, int n_aux, InAux a0,
+                                                      InAux a1) {
     extern __shared__ float wsm[];   // [Cout/8][9*Cin][8] + bias [Cout]
     const int K = 9 * Cin, OV = Cout / 8;
     for (int e = threadIdx.x; e < Cout * K; e += blockDim.x) {
@@ -59,6 +66,19 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, c
 #pragma unroll
         for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(acc[z]);
         *reinterpret_cast<uint4 *>(out + i * 8) = o;
+        for (int ax = 0; ax < n_aux; ++ax) {   // the consumers' GroupNorm affine + SiLU, applied once here
+            const InAux &A = ax == 0 ? a0 : a1;
+            uint4 oa;
+            T *ae = reinterpret_cast<T *>(&oa);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) {
+                float f = acc[z];
+                if (A.scale) f *= __ldg(A.scale + ov * 8 + z);
+                if (A.shift) f += __ldg(A.shift + ov * 8 + z);
+                ae[z] = DT<T>::from_f(activate<true>(A.act, f));
+            }
+            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + i * 8) = oa;
+        }
     }
 }
 
@@ -207,7 +227,7 @@ using namespace sige;
 extern "C" {
 
 int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out, int dtype, int B, int H, int W, int Cin, int Cout,
-                      sige_stream_t stream) {
+                      int n_aux, const sige_conv_aux_t *aux, sige_stream_t stream) {
     SIGE_REQUIRE(x && w && out, "sige_conv_in_nhwc: null pointer");
     SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 4 && Cout > 0 && Cout % 8 == 0, "sige_conv_in_nhwc: needs Cin <= 4 and Cout %% 8 == 0");
     SIGE_REQUIRE(((uintptr_t)out & 15) == 0, "sige_conv_in_nhwc: output not 16-byte aligned");
@@ -217,9 +237,15 @@ int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out,
     const long long want_blocks = (total + 255) / 256;
     const int grid = (int)(want_blocks < 148LL * 16 ? want_blocks : 148LL * 16);
     cudaStream_t st = (cudaStream_t)stream;
+    SIGE_REQUIRE(n_aux >= 0 && n_aux <= 2 && (n_aux == 0 || aux), "sige_conv_in_nhwc: n_aux must be 0..2");
+    InAux ia[2] = {{nullptr, nullptr, nullptr, 0}, {nullptr, nullptr, nullptr, 0}};
+    for (int i = 0; i < n_aux; ++i) {
+        SIGE_REQUIRE(aux[i].ptr && aux[i].C == Cout && aux[i].c0 == 0 && ((uintptr_t)aux[i].ptr & 15) == 0, "sige_conv_in_nhwc: bad aux destination %d", i);
+        ia[i] = InAux{aux[i].ptr, aux[i].scale, aux[i].shift, aux[i].act};
+    }
     switch (dtype) {
-        case SIGE_F16: conv_in_kernel<__half><<<grid, 256, smem, st>>>((const __half *)x, (const __half *)w, (const __half *)bias, (__half *)out, B, H, W, Cin, Cout); break;
-        case SIGE_BF16: conv_in_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)w, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)out, B, H, W, Cin, Cout); break;
+        case SIGE_F16: conv_in_kernel<__half><<<grid, 256, smem, st>>>((const __half *)x, (const __half *)w, (const __half *)bias, (__half *)out, B, H, W, Cin, Cout, n_aux, ia[0], ia[1]); break;
+        case SIGE_BF16: conv_in_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)w, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)out, B, H, W, Cin, Cout, n_aux, ia[0], ia[1]); break;
         default: set_error("sige_conv_in_nhwc: dtype must be f16/bf16"); return 1;
     }
     return check_launch("sige_conv_in_nhwc");

@@ -14,7 +14,7 @@
 // pointwise pre-op is applied on the way in; out-of-image pixels are zero AFTER the pre-op,
 // reference gather_kernel.cu:33-42) and re-used by all kH*kW taps: the A fragments of tap
 // (ky,kx) are just ldmatrix row pointers into the halo tile shifted by (ky,kx).  Weights are
-// pre-packed [tap][Cout][Cin] and streamed through a cp.async ring.  The epilogue stages the
+// pre-packed [tap][Cin/64][Cout][64] and streamed through a cp.async ring.  The epilogue stages the
 // fp32 accumulators in shared memory and writes 16-byte channel vectors straight into the
 // destination tensor (coalesced 128-byte lines per pixel), adding bias and the residual.
 //
@@ -39,6 +39,13 @@ struct ConvSeg {
     int up;   // nearest x2 upsample on read
 };
 
+struct AuxDst {
+    void *ptr;
+    int C, c0;
+    const float *scale, *shift;
+    int act;
+};
+
 struct ConvParams {
     ConvSeg seg[2];
     int C0;                 // channels of segment 0 (segment 1 starts here)
@@ -50,7 +57,7 @@ struct ConvParams {
     const float *scale, *shift;
     int affine_bstride;
     int act;
-    const void *w;          // [taps][Cout][Cin]
+    const void *w;          // [taps][Cin/64][Cout][64]
     const float *bias;
     int Cin, Cout, kH, kW, taps, stride;
     int Ro, So, P;          // output tile extent, pixels per tile
@@ -63,6 +70,8 @@ struct ConvParams {
     int offH, offW;
     const void *residual;
     int rC, res_c0;
+    int n_aux;
+    AuxDst aux[2];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -223,11 +232,12 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
         if (j < j_end) {
             const int c = j / p.taps, tap = j - c * p.taps;
             unsigned char *st = bst + ((j - j_begin) % NSTAGE) * Cfg::B_STAGE_BYTES;
-            const T *wbase = reinterpret_cast<const T *>(p.w) + ((long long)tap * p.Cout) * p.Cin + c * KC;
+            // packed [tap][Cin/64][Cout][64]: this CTA's slab is one contiguous run of BN*128 bytes
+            const T *wbase = reinterpret_cast<const T *>(p.w) + (((long long)tap * NC + c) * p.Cout) * KC;
             for (int q = tid; q < BN * 8; q += NTHREADS) {
                 const int n = q >> 3, u = q & 7;
                 const bool ok = (n0 + n) < p.Cout;
-                const T *src = wbase + (long long)(ok ? (n0 + n) : 0) * p.Cin + u * 8;
+                const T *src = wbase + (long long)(ok ? (n0 + n) : 0) * KC + u * 8;
                 cp_async16(smem_u32(st + n * 128 + ((u ^ (n & 7)) << 4)), src, ok);
             }
         }
@@ -380,7 +390,26 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
         T *oe = reinterpret_cast<T *>(&o);
 #pragma unroll
         for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(v[z]);
-        *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.dst) + pixel * p.dC + p.dst_c0 + n) = o;
+        if (p.dst) *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.dst) + pixel * p.dC + p.dst_c0 + n) = o;
+        for (int ax = 0; ax < p.n_aux; ++ax) {   // extra destinations: the consumer's pre-op applied by the producer
+            const AuxDst &A = p.aux[ax];
+            float w8[8];
+#pragma unroll
+            for (int z = 0; z < 8; ++z) w8[z] = v[z];
+            if (A.scale) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.scale + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.scale + n + 4));
+                w8[0] *= s0.x; w8[1] *= s0.y; w8[2] *= s0.z; w8[3] *= s0.w; w8[4] *= s1.x; w8[5] *= s1.y; w8[6] *= s1.z; w8[7] *= s1.w;
+            }
+            if (A.shift) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.shift + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.shift + n + 4));
+                w8[0] += s0.x; w8[1] += s0.y; w8[2] += s0.z; w8[3] += s0.w; w8[4] += s1.x; w8[5] += s1.y; w8[6] += s1.z; w8[7] += s1.w;
+            }
+            uint4 oa;
+            T *ae = reinterpret_cast<T *>(&oa);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(A.act, w8[z]));
+            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + pixel * A.C + A.c0 + n) = oa;
+        }
     }
     if (p.ksplit > 1) cg::this_cluster().sync();   // nobody leaves while a peer still reads its partial tile
 }
@@ -497,13 +526,15 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     }
     SIGE_REQUIRE(csum == a->Cin, "sige_tile_conv: source channels (%d) != Cin (%d)", csum, a->Cin);
     SIGE_REQUIRE(a->Cout > 0 && a->Cout % 8 == 0, "sige_tile_conv: Cout (%d) must be a multiple of 8", a->Cout);
-    SIGE_REQUIRE(a->w_packed && a->dst, "sige_tile_conv: null weight/destination");
+    SIGE_REQUIRE(a->w_packed && (a->dst || a->n_aux > 0), "sige_tile_conv: null weight/destination");
     SIGE_REQUIRE(a->src_is_stack || a->idx, "sige_tile_conv: index list missing");
     SIGE_REQUIRE(a->dst_is_stack || a->idx, "sige_tile_conv: index list missing");
     SIGE_REQUIRE(!(a->src_is_stack && a->n_src != 1), "sige_tile_conv: a stack source cannot be concatenated");
     SIGE_REQUIRE(a->H < 65536 && a->W < 65536, "sige_tile_conv: extent too large");
-    SIGE_REQUIRE(a->dC % 8 == 0 && a->dst_c0 % 8 == 0 && ((uintptr_t)a->dst & 15) == 0, "sige_tile_conv: destination must be 16-byte aligned per pixel");
-    SIGE_REQUIRE(a->dst_c0 + a->Cout <= a->dC, "sige_tile_conv: destination channel window out of range");
+    if (a->dst) {
+        SIGE_REQUIRE(a->dC % 8 == 0 && a->dst_c0 % 8 == 0 && ((uintptr_t)a->dst & 15) == 0, "sige_tile_conv: destination must be 16-byte aligned per pixel");
+        SIGE_REQUIRE(a->dst_c0 + a->Cout <= a->dC, "sige_tile_conv: destination channel window out of range");
+    }
     if (a->residual)
         SIGE_REQUIRE(a->rC % 8 == 0 && a->res_c0 % 8 == 0 && a->res_c0 + a->Cout <= a->rC && ((uintptr_t)a->residual & 15) == 0,
                      "sige_tile_conv: bad residual channel window");
@@ -514,6 +545,13 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     SIGE_REQUIRE(a->affine_bstride == 0 || a->affine_bstride == a->Cin, "sige_tile_conv: affine_bstride must be 0 or Cin");
     SIGE_REQUIRE(a->act == SIGE_ACT_IDENTITY || a->act == SIGE_ACT_SWISH, "sige_tile_conv: unknown activation %d", a->act);
     SIGE_REQUIRE(a->ksplit >= 0 && a->ksplit <= 8, "sige_tile_conv: ksplit out of range");
+    SIGE_REQUIRE(a->n_aux >= 0 && a->n_aux <= 2, "sige_tile_conv: n_aux must be 0, 1 or 2");
+    for (int i = 0; i < a->n_aux; ++i) {
+        const sige_conv_aux_t &x = a->aux[i];
+        SIGE_REQUIRE(x.ptr && ((uintptr_t)x.ptr & 15) == 0 && x.C % 8 == 0 && x.c0 % 8 == 0 && x.c0 + a->Cout <= x.C, "sige_tile_conv: bad aux destination %d", i);
+        SIGE_REQUIRE((!x.scale || ((uintptr_t)x.scale & 15) == 0) && (!x.shift || ((uintptr_t)x.shift & 15) == 0), "sige_tile_conv: aux %d affine not 16-byte aligned", i);
+        SIGE_REQUIRE(x.act == SIGE_ACT_IDENTITY || x.act == SIGE_ACT_SWISH, "sige_tile_conv: aux %d unknown activation", i);
+    }
 
     // Blackwell-native path (tcgen05 + TMEM + TMA, tile_conv_tc5.cu) when requested and the geometry fits
     if ((a->flags & SIGE_CONV_TC5) && tc5_supported(a)) return tc5_launch(a, (cudaStream_t)stream);
@@ -541,6 +579,8 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     p.dC = a->dC; p.dst_c0 = a->dst_c0;
     p.offH = a->offH; p.offW = a->offW;
     p.residual = a->residual; p.rC = a->rC; p.res_c0 = a->res_c0;
+    p.n_aux = a->n_aux;
+    for (int i = 0; i < a->n_aux; ++i) p.aux[i] = AuxDst{a->aux[i].ptr, a->aux[i].C, a->aux[i].c0, a->aux[i].scale, a->aux[i].shift, a->aux[i].act};
     p.tpc = 1;
     p.ksplit = a->ksplit;
     p.pdl = (a->flags & SIGE_CONV_PDL) ? 1 : 0;

@@ -17,8 +17,8 @@
 //     tap (ky,kx) is copy kx shifted by ky*32 rows: row m of the MMA reads row m + 32*ky — a pure
 //     start-address offset of ky*4096 bytes, which is a multiple of the 1024-byte swizzle atom.
 //     Cost: each gathered pixel is stored ~2x instead of the 9x of an im2col.
-//   * B (weights, pre-packed [tap][Cout][Cin]) is a 2-D tensor map {Cin, taps*Cout}; one TMA box
-//     {64, BN} per (tap, 64-channel chunk) lands in a 128B-swizzled stage of an mbarrier ring.
+//   * B (weights, pre-packed [tap][Cin/64][Cout][64]) is a 2-D tensor map {64, taps*Cin/64*Cout}; one TMA
+//     box {64, BN} (a contiguous BN*128-byte run) per (tap, 64-channel chunk) lands in a 128B-swizzled stage of an mbarrier ring.
 //   * one elected thread issues tcgen05.mma; tcgen05.commit releases weight stages / halo buffers and
 //     finally signals the epilogue, which pulls the fp32 accumulator out of TMEM with tcgen05.ld.
 #include <cooperative_groups.h>
@@ -48,6 +48,13 @@ struct Seg {
     int up;
 };
 
+struct AuxDst {
+    void *ptr;
+    int C, c0;
+    const float *scale, *shift;
+    int act;
+};
+
 struct Params {
     Seg seg[2];
     int C0;
@@ -66,9 +73,12 @@ struct Params {
     int offH, offW;
     const void *residual;
     int rC, res_c0;
+    int n_aux;
+    AuxDst aux[2];
     int ksplit;
     int pdl;
     int is_bf16;
+    long long *trace;          // development aid: per-CTA clock stamps (16 slots), or nullptr
 };
 
 template <int BN> struct Cfg {
@@ -172,6 +182,16 @@ __device__ __forceinline__ uint32_t make_idesc(int bn, int bf16) {
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+#define SIGE_TRACE(slot)                                                                                          \
+    do {                                                                                                          \
+        if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); \
+    } while (0)
+
 template <typename T, int BN, int TAPS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap) {
@@ -204,6 +224,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     const int j_begin = (int)(((long long)J * kr) / p.ksplit), j_end = (int)(((long long)J * (kr + 1)) / p.ksplit);
     const int c_first = j_begin / TAPS, c_last = (j_end - 1) / TAPS;
 
+    if (tid == 0) SIGE_TRACE(0);
     // ---------------- one-time setup ----------------
     if (warp == 0) {
         if (lane == 0) {
@@ -220,6 +241,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) SIGE_TRACE(1);
     if (p.pdl) asm volatile("griddepcontrol.launch_dependents;\n" ::);   // the next layer may start prefetching ITS weights
 
     if (warp == 0) {
@@ -230,7 +252,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 mbar_wait(B_EMPTY(s), (k & 1) ^ 1);
                 mbar_expect_tx(B_FULL(s), C::B_STAGE_BYTES);
                 const int c = j / TAPS, tap = j - c * TAPS;
-                tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES, &wmap, c * KC, tap * p.Cout + n0, B_FULL(s));
+                tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES, &wmap, 0, (tap * NC + c) * p.Cout + n0, B_FULL(s));
             }
         }
         __syncwarp();
@@ -244,6 +266,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 if (j == j_begin || tap == 0) {                       // a new chunk starts: wait for its halo buffer
                     mbar_wait(A_FULL(ab), (ause >> 1) & 1);
                     tc_fence_after();
+                    if (j == j_begin) SIGE_TRACE(5);
                 }
                 const int it = j - j_begin, s = it % NSTB, k = it / NSTB;
                 mbar_wait(B_FULL(s), k & 1);
@@ -262,6 +285,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 }
             }
             umma_commit(ACC_FULL);
+            SIGE_TRACE(6);
         }
         __syncwarp();
     } else {
@@ -291,6 +315,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 }
             }
         }
+        if (ptid == 0) SIGE_TRACE(2);   // bookkeeping (idx loads) done
         uint4 regs[LOADS];
         auto issue = [&](int c) {
             const int cbase = c * KC;
@@ -360,7 +385,9 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         int ab = 0, ause = 0;
         for (int c = c_first; c <= c_last; ++c) {
             mbar_wait(A_EMPTY(ab), ((ause >> 1) & 1) ^ 1);            // the MMAs that read this buffer have retired
+            if (ptid == 0 && c == c_first) SIGE_TRACE(3);
             store(c, smem + C::OFF_A + ab * A_BUF_BYTES);
+            if (ptid == 0 && c == c_first) SIGE_TRACE(4);
             fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core
             mbar_arrive(A_FULL(ab));
             if (c < c_last) issue(c + 1);
@@ -375,6 +402,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         // four warps cover the 128 TMEM lanes; warp w may only touch lanes 32*(w%4)..+31
         mbar_wait(ACC_FULL, 0);
         tc_fence_after();
+        if (tid == 64) SIGE_TRACE(7);
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
 #pragma unroll
@@ -390,6 +418,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         tc_fence_before();
     }
     __syncthreads();
+    if (tid == 0) SIGE_TRACE(8);
     if (warp == 0) tmem_dealloc(tmem_base, BN);
 
     if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -406,6 +435,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
 #pragma unroll
         for (int r = 0; r < 8; ++r) part[r] = r < p.ksplit ? cluster.map_shared_rank(cst, r) : cst;
     }
+    if (tid == 0) SIGE_TRACE(9);
     for (int q = tid + m_lo * (BN / 8); q < m_hi * (BN / 8); q += NTHREADS) {
         const int m = q / (BN / 8), nv = q - m * (BN / 8);
         const int n = n0 + nv * 8;
@@ -446,9 +476,30 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         T *oe = reinterpret_cast<T *>(&o);
 #pragma unroll
         for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(v[z]);
-        *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.dst) + pixel * p.dC + p.dst_c0 + n) = o;
+        if (p.dst) *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.dst) + pixel * p.dC + p.dst_c0 + n) = o;
+        for (int ax = 0; ax < p.n_aux; ++ax) {   // extra destinations: the consumer's pre-op applied by the producer
+            const AuxDst &A = p.aux[ax];
+            float w8[8];
+#pragma unroll
+            for (int z = 0; z < 8; ++z) w8[z] = v[z];
+            if (A.scale) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.scale + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.scale + n + 4));
+                w8[0] *= s0.x; w8[1] *= s0.y; w8[2] *= s0.z; w8[3] *= s0.w; w8[4] *= s1.x; w8[5] *= s1.y; w8[6] *= s1.z; w8[7] *= s1.w;
+            }
+            if (A.shift) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.shift + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.shift + n + 4));
+                w8[0] += s0.x; w8[1] += s0.y; w8[2] += s0.z; w8[3] += s0.w; w8[4] += s1.x; w8[5] += s1.y; w8[6] += s1.z; w8[7] += s1.w;
+            }
+            uint4 oa;
+            T *ae = reinterpret_cast<T *>(&oa);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(A.act, w8[z]));
+            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + pixel * A.C + A.c0 + n) = oa;
+        }
     }
+    if (tid == 0) SIGE_TRACE(10);
     if (p.ksplit > 1) cg::this_cluster().sync();
+    if (tid == 0) SIGE_TRACE(11);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -480,8 +531,9 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
         return 2;
     }
     CUtensorMap wmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)p.Cin, (cuuint64_t)TAPS * p.Cout};
-    const cuuint64_t gstr[1] = {(cuuint64_t)p.Cin * 2};
+    // packed weights [tap][Cin/64][Cout][64] seen as a 2-D tensor {64, taps * Cin/64 * Cout}: a box is contiguous
+    const cuuint64_t gdim[2] = {(cuuint64_t)KC, (cuuint64_t)TAPS * (p.Cin / KC) * p.Cout};
+    const cuuint64_t gstr[1] = {(cuuint64_t)KC * 2};
     const cuuint32_t box[2] = {KC, (cuuint32_t)BN};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&wmap, p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w_packed),
@@ -544,6 +596,9 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
 
 }  // namespace tc5
 
+static long long *g_trace = nullptr;
+extern "C" void sige_debug_set_trace(void *buf) { g_trace = reinterpret_cast<long long *>(buf); }
+
 // Can the tcgen05 kernel take this layer?  (3x3 stride 1 on 6x6 tiles, or 1x1 on 4x4 tiles; Cout % 64 == 0)
 bool tc5_supported(const sige_tile_conv_t *a) {
     const bool g3 = a->kH == 3 && a->kW == 3 && a->stride == 1 && a->R == 6 && a->S == 6;
@@ -572,9 +627,12 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.dC = a->dC; p.dst_c0 = a->dst_c0;
     p.offH = a->offH; p.offW = a->offW;
     p.residual = a->residual; p.rC = a->rC; p.res_c0 = a->res_c0;
+    p.n_aux = a->n_aux;
+    for (int i = 0; i < a->n_aux; ++i) p.aux[i] = tc5::AuxDst{a->aux[i].ptr, a->aux[i].C, a->aux[i].c0, a->aux[i].scale, a->aux[i].shift, a->aux[i].act};
     p.ksplit = a->ksplit;
     p.pdl = (a->flags & SIGE_CONV_PDL) ? 1 : 0;
     p.is_bf16 = a->dtype == SIGE_BF16;
+    p.trace = g_trace;
     // BN = 128 only when that still leaves enough CTAs; small problems want more, narrower CTAs
     const long long m_blocks = ceil_div(p.NT, tc5::TILES);
     const bool wide = (a->Cout % 128 == 0) && (m_blocks * (a->Cout / 128) >= 148);

@@ -326,7 +326,9 @@ __global__ void reduce_mask_kernel(const uint8_t *__restrict__ mask, int H, int 
 }
 
 // ----------------------------------------------------------------------------
-// weight repack OIHW -> [tap][Cout][Cin]
+// weight repack OIHW -> [tap][Cin/64][Cout][64]: the slab a CTA streams for one (tap, 64-channel chunk,
+// Cout block) is ONE contiguous run of Cout_block*128 bytes (DRAM-page friendly, one TMA box).
+// If Cin is not a multiple of 64 the plain [tap][Cout][Cin] order is used (generic consumers only).
 // ----------------------------------------------------------------------------
 template <typename TS, typename TD>
 __global__ void pack_weight_kernel(long long total, const TS *__restrict__ w, TD *__restrict__ out, int Cout,
@@ -334,9 +336,18 @@ __global__ void pack_weight_kernel(long long total, const TS *__restrict__ w, TD
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= total) return;
     long long t = i;
-    const int ci = t % Cin; t /= Cin;
-    const int co = t % Cout; t /= Cout;
-    const int tap = t;
+    int ci, co, tap;
+    if (Cin % 64 == 0) {
+        const int k = t % 64; t /= 64;
+        co = t % Cout; t /= Cout;
+        const int chunk = t % (Cin / 64); t /= (Cin / 64);
+        tap = t;
+        ci = chunk * 64 + k;
+    } else {
+        ci = t % Cin; t /= Cin;
+        co = t % Cout; t /= Cout;
+        tap = t;
+    }
     out[i] = DT<TD>::from_f(DT<TS>::to_f(w[((long long)co * Cin + ci) * taps + tap]));
 }
 

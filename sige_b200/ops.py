@@ -280,7 +280,9 @@ def scatter_gather(x, y, bsize_h: int, bsize_w: int, active_indices, scatter_map
 # a3: tile convolution
 # --------------------------------------------------------------------------------------
 def pack_conv_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """OIHW -> [kH*kW, Cout, Cin] in `dtype` (f16/bf16) for the tensor-core kernel."""
+    """OIHW -> packed weights in `dtype` (f16/bf16) for the tensor-core kernels.  The returned tensor has the
+    bookkeeping shape (kH*kW, Cout, Cin); its memory order is [tap][Cin/64][Cout][64] (contiguous slabs per
+    (tap, 64-channel chunk)) when Cin % 64 == 0."""
     _require_cuda(weight)
     w = weight.detach().contiguous()
     Cout, Cin, kH, kW = w.shape
@@ -396,7 +398,8 @@ def tile_conv_generic(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torc
 # --------------------------------------------------------------------------------------
 # dense glue of a step (conv_in / GroupNorm fold / conv_out), NHWC f16/bf16
 # --------------------------------------------------------------------------------------
-def conv_in_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def conv_in_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                 aux=None) -> torch.Tensor:
     """3x3 pad-1 conv with Cin <= 4 on a channels-last image (reference sige_fused_unet.py:395)."""
     _require_cuda(x, weight, bias)
     x, _ = _dense(x, NHWC)
@@ -407,8 +410,12 @@ def conv_in_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     if out is None:
         out = _empty_like_layout((B, Cout, H, W), x, NHWC)
     with torch.cuda.device(x.device):
+        n_aux = 0 if aux is None else len(aux)
+        arr = (_cabi.ConvAux * 2)()
+        for i in range(n_aux):
+            arr[i] = aux[i]
         _cabi.check(_cabi.lib().sige_conv_in_nhwc(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), _dt(x), B, H, W,
-                                                 Cin, Cout, _stream(x)), "sige_conv_in_nhwc")
+                                                 Cin, Cout, n_aux, arr, _stream(x)), "sige_conv_in_nhwc")
     _bump()
     return out
 

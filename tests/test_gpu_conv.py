@@ -283,3 +283,48 @@ def test_tc5_fused_gather_conv_scatter_vs_oracle(oracle, dtype):
             torch.cuda.synchronize()
             e = rel_err(out, want)
             assert e <= 2 * TOL[dtype], "tc5 fused case %s ksplit %d flags %d: rel err %g" % ((B, C, Co, H, W, bs, k), ks, flags, e)
+
+
+@pytest.mark.parametrize("flags", [0, TC5])
+def test_aux_destinations_apply_the_consumers_preop(oracle, flags):
+    """Extra epilogue outputs: aux = act(out*scale+shift), primary destination optional."""
+    from sige_b200 import _cabi, ops
+
+    dtype = torch.float16
+    rng = np.random.default_rng(21)
+    B, C, Co, H, W = 1, 128, 128, 32, 32
+    mask = rng.random((H, W)) < 0.1
+    mask[0, 0] = True
+    idx = oracle.reduce_mask(mask, 6, 4, 1)
+    x = _round(rng.standard_normal((B, C, H, W)).astype(np.float32), dtype)
+    w = _round(rng.standard_normal((Co, C, 3, 3)).astype(np.float32) / np.sqrt(C * 9), dtype)
+    b = rng.standard_normal((Co,)).astype(np.float32)
+    y = _round(rng.standard_normal((B, Co, H, W)).astype(np.float32), dtype)
+    res = _round(rng.standard_normal((B, Co, H, W)).astype(np.float32), dtype)
+    sc = (1 + 0.2 * rng.standard_normal((1, Co, 1, 1))).astype(np.float32)
+    sh = (0.2 * rng.standard_normal((1, Co, 1, 1))).astype(np.float32)
+    tiles = oracle.conv2d_tiles(oracle.gather(x, 6, 6, idx), w, b, (1, 1))
+    want_raw = oracle.scatter(tiles, y, 1, 1, 1, 1, idx, res)
+    z = want_raw * sc + sh
+    want_aux = z / (1 + np.exp(-z))
+    fresh = want_raw != y                      # only active tiles are rewritten
+    out = T(y, dtype, cl=True).clone(memory_format=torch.channels_last)
+    aux0 = torch.zeros_like(out)
+    aux1 = torch.zeros_like(out)
+    tsc, tsh = T(sc).reshape(-1).contiguous(), T(sh).reshape(-1).contiguous()
+    d = _fused_desc(ops, T(x, dtype, cl=True), ops.pack_conv_weight(T(w, dtype), dtype), T(b), T(idx), out, R=6, k=3, stride=1, off=1,
+                    residual=T(res, dtype, cl=True))
+    d.flags, d.n_aux = flags, 2
+    d.aux[0].ptr, d.aux[0].C, d.aux[0].c0, d.aux[0].scale, d.aux[0].shift, d.aux[0].act = aux0.data_ptr(), Co, 0, tsc.data_ptr(), tsh.data_ptr(), 1
+    d.aux[1].ptr, d.aux[1].C, d.aux[1].c0, d.aux[1].scale, d.aux[1].shift, d.aux[1].act = aux1.data_ptr(), Co, 0, None, None, 0
+    ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_err(out, want_raw) <= 2e-3
+    g0, g1 = aux0.float().cpu().numpy(), aux1.float().cpu().numpy()
+    assert np.abs(g0 - want_aux)[fresh].max() / np.abs(want_aux).max() <= 2e-3 and (g0[~fresh] == 0).all()
+    assert np.abs(g1 - want_raw)[fresh].max() / np.abs(want_raw).max() <= 2e-3
+    d.dst = None                               # aux-only launch
+    aux0.zero_()
+    ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.abs(aux0.float().cpu().numpy() - want_aux)[fresh].max() / np.abs(want_aux).max() <= 2e-3

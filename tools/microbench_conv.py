@@ -66,6 +66,29 @@ def timeit(d, reps, flush):
     return 1e3 * tot / reps
 
 
+def time_graph(d, n=20, reps=10):
+    """True device time per launch: n launches captured in one CUDA graph, replayed."""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            ops.launch_tile_conv(d, st.cuda_stream)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        s = torch.cuda.current_stream().cuda_stream
+        for _ in range(n):
+            ops.launch_tile_conv(d, s)
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record()
+    b.synchronize()
+    return 1e3 * a.elapsed_time(b) / (reps * n)
+
+
 def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     shapes = [("64 tiles 128->128 3x3 @256", 8, 256, 128, 128, 3, False), ("16 tiles(all) 1024->512 3x3 @16", 4, 16, 1024, 512, 3, True),
@@ -74,15 +97,15 @@ def main():
     for name, n, H, Cin, Cout, k, allt in shapes:
         d = make(n, H, Cin, Cout, k, allt)
         print("== %s" % name)
-        for flags, kn in ((0, "mma.sync"), (2, "tcgen05 ")):
+        for flags, kn in ((0, "mma.sync"), (2, "tcgen05 "), (1, "mma+pdl "), (3, "tc5+pdl ")):
             row = []
             for ks in (1, 2, 4, 8, 0):
                 d.flags, d.ksplit = flags, ks
                 try:
-                    row.append("ks%d: %6.1f/%6.1f" % (ks, timeit(d, 50, None), timeit(d, 10, flush)))
+                    row.append("ks%d: %5.1f/%5.1f" % (ks, time_graph(d), timeit(d, 10, flush)))
                 except Exception as e:  # noqa: BLE001
                     row.append("ks%d: err %s" % (ks, str(e)[:40]))
-            print("  %s  warm/cold us  " % kn + " | ".join(row))
+            print("  %s  graph(warm)/cold us  " % kn + " | ".join(row))
     # empty-kernel launch floor for reference
     z = torch.zeros(1, device=DEV)
     st = torch.cuda.current_stream()
@@ -95,5 +118,40 @@ def main():
     print("tiny torch kernel back-to-back: %.2f us" % (1e3 * a.elapsed_time(b) / 200))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--trace" not in sys.argv:
     main()
+
+
+def trace(name, d, ks, flags=2):
+    """Per-stage timeline (globaltimer, ns) of the tcgen05 kernel: median over CTAs, relative to the first CTA's start."""
+    import ctypes
+    from sige_b200 import _cabi
+    lib = _cabi.lib()
+    lib.sige_debug_set_trace.argtypes = [ctypes.c_void_p]
+    buf = torch.zeros(4096 * 16, dtype=torch.int64, device=DEV)
+    d.flags, d.ksplit = flags, ks
+    s = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        ops.launch_tile_conv(d, s)
+    torch.cuda.synchronize()
+    lib.sige_debug_set_trace(buf.data_ptr())
+    ops.launch_tile_conv(d, s)
+    torch.cuda.synchronize()
+    lib.sige_debug_set_trace(None)
+    t = buf.view(-1, 16).cpu()
+    t = t[t[:, 0] > 0]
+    t0 = t[:, 0].min()
+    rel = (t - t0).float()
+    rel[t == 0] = float("nan")
+    names = ["start", "setup", "idx", "ldg", "store", "mmaA", "mmaEnd", "accRdy", "tmemLd", "clSync", "stored", "end"]
+    med = [float(torch.nanmedian(rel[:, i])) for i in range(12)]
+    mx = [float(rel[:, i][~torch.isnan(rel[:, i])].max()) if (~torch.isnan(rel[:, i])).any() else float("nan") for i in range(12)]
+    print("  trace %s ks=%d ctas=%d | " % (name, ks, t.shape[0]) + " ".join("%s %.0f/%.0f" % (n, a, b) for n, a, b in zip(names, med, mx)))
+
+
+if __name__ == "__main__" and "--trace" in sys.argv:
+    for name, n, H, Cin, Cout, k, allt in [("64t 128->128 3x3", 8, 256, 128, 128, 3, False), ("16t 1024->512 3x3", 4, 16, 1024, 512, 3, True),
+                                           ("64t 256->128 1x1", 8, 256, 256, 128, 1, False)]:
+        d = make(n, H, Cin, Cout, k, allt)
+        for ks in (1, 4, 8):
+            trace(name, d, ks)
