@@ -15,6 +15,12 @@ namespace sige {
 // conv_in: Cin <= 4, Cout % 8 == 0.  One thread = one pixel x 8 output channels (one 16-byte store);
 // the 9*Cin inputs come through L1, the 9*Cin*8 weights of the thread's channel octet from shared.
 // ------------------------------------------------------------------------------------------
+__host__ __device__ inline int conv_in_pitch(int Cin) {
+    int v = 9 * Cin * 2;          // row length in 16-byte units
+    if ((v & 1) == 0) ++v;        // make it odd
+    return v * 4;                 // floats
+}
+
 struct InAux {
     void *ptr;
     const float *scale, *shift;
@@ -25,14 +31,16 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *__restrict__ bias,
                                                       T *__restrict__ out, int B, int H, int W, int Cin, int Cout, int n_aux, InAux a0,
                                                       InAux a1) {
-    extern __shared__ float wsm[];   // [Cout/8][9*Cin][8] + bias [Cout]
+    extern __shared__ float wsm[];   // [Cout/8][pitch] (rows of 9*Cin*8 weights, padded) + bias [Cout]
     const int K = 9 * Cin, OV = Cout / 8;
+    // lanes of a warp hold different channel octets: rows 16 bytes * odd apart keep their 128-bit reads conflict-free
+    const int pitch = conv_in_pitch(Cin);
     for (int e = threadIdx.x; e < Cout * K; e += blockDim.x) {
         const int co = e / K, k = e - co * K;              // k = ci*9 + tap in OIHW
         const int ci = k / 9, tap = k - ci * 9;
-        wsm[((co >> 3) * K + tap * Cin + ci) * 8 + (co & 7)] = DT<T>::to_f(w[e]);
+        wsm[(co >> 3) * pitch + (tap * Cin + ci) * 8 + (co & 7)] = DT<T>::to_f(w[e]);
     }
-    float *bsm = wsm + Cout * K;
+    float *bsm = wsm + OV * pitch;
     for (int e = threadIdx.x; e < Cout; e += blockDim.x) bsm[e] = bias ? DT<T>::to_f(bias[e]) : 0.f;
     __syncthreads();
     const long long total = (long long)B * H * W * OV;
@@ -45,7 +53,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, c
         float acc[8];
 #pragma unroll
         for (int z = 0; z < 8; ++z) acc[z] = bsm[ov * 8 + z];
-        const float *wv = wsm + (long long)ov * K * 8;
+        const float *wv = wsm + ov * pitch;
         for (int ky = 0; ky < 3; ++ky) {
             const int y = hh + ky - 1;
             if (y < 0 || y >= H) continue;
@@ -122,24 +130,33 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const T *__restrict__ x
 }
 
 template <typename T>
-__global__ void gn_finalize_kernel(const float *__restrict__ part, int nblk, int HW, int C, int G, float eps, const T *__restrict__ gamma,
-                                   const T *__restrict__ beta, float *__restrict__ scale, float *__restrict__ shift) {
-    // grid = B, block = C threads (C <= 1024)
-    extern __shared__ float sm[];   // [C][2]
-    const int b = blockIdx.x, c = threadIdx.x;
-    if (c < C) {
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float *__restrict__ part, int nblk, int HW, int C, int G, float eps,
+                                                           const T *__restrict__ gamma, const T *__restrict__ beta,
+                                                           float *__restrict__ scale, float *__restrict__ shift) {
+    // grid = B, block = 1024 threads = S slices x C channels; fixed summation order -> deterministic
+    extern __shared__ double dsm[];   // [S][C][2]
+    const int b = blockIdx.x;
+    const int S = max(1, (int)blockDim.x / C);
+    const int c = threadIdx.x % C, sl = threadIdx.x / C;
+    if (sl < S) {
         double ss = 0.0, qq = 0.0;
-        for (int k = 0; k < nblk; ++k) {
+        for (int k = sl; k < nblk; k += S) {
             const float *p = part + (((long long)b * nblk + k) * C + c) * 2;
             ss += p[0]; qq += p[1];
         }
-        sm[2 * c] = (float)ss; sm[2 * c + 1] = (float)qq;
+        dsm[(sl * C + c) * 2] = ss; dsm[(sl * C + c) * 2 + 1] = qq;
     }
     __syncthreads();
-    if (c < C) {
+    if (threadIdx.x < C) {
+        double ss = 0.0, qq = 0.0;
+        for (int k = 0; k < S; ++k) { ss += dsm[(k * C + c) * 2]; qq += dsm[(k * C + c) * 2 + 1]; }
+        dsm[c * 2] = ss; dsm[c * 2 + 1] = qq;           // slice 0 row now holds the per-channel totals
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
         const int per = C / G, g = c / per;
         double ss = 0.0, qq = 0.0;
-        for (int k = 0; k < per; ++k) { ss += sm[2 * (g * per + k)]; qq += sm[2 * (g * per + k) + 1]; }
+        for (int k = 0; k < per; ++k) { ss += dsm[2 * (g * per + k)]; qq += dsm[2 * (g * per + k) + 1]; }
         const double n = (double)per * HW;
         const double mean = ss / n;
         double var = qq / n - mean * mean;
@@ -231,7 +248,7 @@ int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out,
     SIGE_REQUIRE(x && w && out, "sige_conv_in_nhwc: null pointer");
     SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 4 && Cout > 0 && Cout % 8 == 0, "sige_conv_in_nhwc: needs Cin <= 4 and Cout %% 8 == 0");
     SIGE_REQUIRE(((uintptr_t)out & 15) == 0, "sige_conv_in_nhwc: output not 16-byte aligned");
-    const size_t smem = sizeof(float) * ((size_t)Cout * 9 * Cin + Cout);
+    const size_t smem = sizeof(float) * ((size_t)(Cout / 8) * conv_in_pitch(Cin) + Cout);
     SIGE_REQUIRE(smem <= 48 * 1024, "sige_conv_in_nhwc: weights do not fit in shared memory");
     const long long total = (long long)B * H * W * (Cout / 8);
     const long long want_blocks = (total + 255) / 256;
@@ -271,7 +288,7 @@ int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, i
     do {                                                                                                                                 \
         if (smem1 > 48 * 1024) cudaFuncSetAttribute(gn_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);        \
         gn_partial_kernel<T><<<g1, 256, smem1, st>>>((const T *)x, HW, C, workspace, nblk);                                               \
-        gn_finalize_kernel<T><<<B, ((C + 31) / 32) * 32, sizeof(float) * 2 * C, st>>>(workspace, nblk, HW, C, groups, eps, (const T *)gamma, \
+        gn_finalize_kernel<T><<<B, 1024, sizeof(double) * 2 * C * (1024 / C > 0 ? 1024 / C : 1), st>>>(workspace, nblk, HW, C, groups, eps, (const T *)gamma, \
                                                                                       (const T *)beta, scale, shift);                   \
     } while (0)
     switch (dtype) {

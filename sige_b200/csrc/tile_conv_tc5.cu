@@ -257,6 +257,15 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
         __syncwarp();
     } else if (warp == 1) {
+        // the epilogue's small read-only vectors are cold in L2 on the first touch of a step: pull them in now
+        {
+            const int off = lane * 32;     // 128-byte lines of fp32
+            if (p.bias && n0 + off < p.Cout) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.bias + n0 + off));
+            for (int ax = 0; ax < p.n_aux; ++ax) {
+                if (p.aux[ax].scale && n0 + off < p.Cout) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.aux[ax].scale + n0 + off));
+                if (p.aux[ax].shift && n0 + off < p.Cout) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.aux[ax].shift + n0 + off));
+            }
+        }
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BN, p.is_bf16);
@@ -307,7 +316,8 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 g_pix[k] = -1;
                 const int t = tile0 + tl;
                 if (t < p.NT) {
-                    const int n = t % p.N, b = t / p.N;
+                    int n = t, b = 0;
+                    if (p.NT != p.N) { b = t / p.N; n = t - b * p.N; }      // batch > 1 only (SD); DDPM is batch 1
                     int hh = y, ww = x, img = t;
                     if (!p.src_is_stack) { hh += __ldg(p.idx + 2 * n); ww += __ldg(p.idx + 2 * n + 1); img = b; }
                     g_img[k] = img; g_ab[k] = b;
@@ -398,6 +408,99 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
 
     // ---------------- epilogue ----------------
     float *cst = reinterpret_cast<float *>(smem + C::OFF_A);
+    // v[8] (fp32 conv result of 8 consecutive channels starting at n) -> +bias, +residual -> dst and aux destinations
+    auto emit = [&](long long pixel, int n, float (&v)[8]) {
+        if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (p.residual) {
+            const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(p.residual) + pixel * p.rC + p.res_c0 + n));
+            const T *re = reinterpret_cast<const T *>(&rr);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) v[z] += DT<T>::to_f(re[z]);
+        }
+        if (p.dst) {
+            uint4 o;
+            T *oe = reinterpret_cast<T *>(&o);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(v[z]);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.dst) + pixel * p.dC + p.dst_c0 + n) = o;
+        }
+        for (int ax = 0; ax < p.n_aux; ++ax) {   // extra destinations: the consumer's pre-op applied by the producer
+            const AuxDst &A = p.aux[ax];
+            float w8[8];
+#pragma unroll
+            for (int z = 0; z < 8; ++z) w8[z] = v[z];
+            if (A.scale) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.scale + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.scale + n + 4));
+                w8[0] *= s0.x; w8[1] *= s0.y; w8[2] *= s0.z; w8[3] *= s0.w; w8[4] *= s1.x; w8[5] *= s1.y; w8[6] *= s1.z; w8[7] *= s1.w;
+            }
+            if (A.shift) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.shift + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.shift + n + 4));
+                w8[0] += s0.x; w8[1] += s0.y; w8[2] += s0.z; w8[3] += s0.w; w8[4] += s1.x; w8[5] += s1.y; w8[6] += s1.z; w8[7] += s1.w;
+            }
+            uint4 oa;
+            T *ae = reinterpret_cast<T *>(&oa);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(A.act, w8[z]));
+            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + pixel * A.C + A.c0 + n) = oa;
+        }
+    };
+    // GEMM row m -> destination pixel index, or -1 (row of a tile that does not exist / outside the image)
+    auto pixel_of = [&](int m) -> long long {
+        int tl, oy, ox;
+        if (TAPS == 9) { oy = m >> 5; tl = (m >> 2) & 7; ox = m & 3; } else { tl = m >> 4; oy = (m >> 2) & 3; ox = m & 3; }
+        if (tl >= ntile) return -1;
+        const int t = tile0 + tl;
+        int hh = oy, ww = ox, img = t;
+        if (!p.dst_is_stack) {
+            int nn = t;
+            img = 0;
+            if (p.NT != p.N) { img = t / p.N; nn = t - img * p.N; }
+            hh += p.offH + __ldg(p.idx + 2 * nn);
+            ww += p.offW + __ldg(p.idx + 2 * nn + 1);
+        }
+        if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) return -1;
+        return ((long long)img * p.dH + hh) * p.dW + ww;
+    };
+
+    if (p.ksplit == 1) {
+        // ---- no split-K: TMEM -> registers -> global, one thread per output pixel (its BN channels are one
+        //      contiguous BN*2-byte run in NHWC), no shared-memory staging and no CTA-wide barrier on the way out
+        if (warp >= 2 && warp < 6) {
+            const int quarter = warp & 3;
+            const int m = quarter * 32 + lane;
+            const long long pixel = pixel_of(m);
+            if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
+            mbar_wait(ACC_FULL, 0);
+            tc_fence_after();
+            if (tid == 64) SIGE_TRACE(7);
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);   // warp-collective: every lane takes part
+                if (pixel >= 0) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float v[8];
+#pragma unroll
+                        for (int z = 0; z < 8; ++z) v[z] = __uint_as_float(r[8 * g + z]);
+                        if (n0 + c0 + 8 * g < p.Cout) emit(pixel, n0 + c0 + 8 * g, v);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+        __syncthreads();
+        if (tid == 0) SIGE_TRACE(8);
+        if (warp == 0) tmem_dealloc(tmem_base, BN);
+        if (tid == 0) { SIGE_TRACE(9); SIGE_TRACE(10); SIGE_TRACE(11); }
+        return;
+    }
+
+    // ---- split-K: stage the partial tile in shared memory, reduce across the cluster through DSMEM
     if (warp >= 2 && warp < 6) {
         // four warps cover the 128 TMEM lanes; warp w may only touch lanes 32*(w%4)..+31
         mbar_wait(ACC_FULL, 0);
@@ -422,83 +525,42 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     if (warp == 0) tmem_dealloc(tmem_base, BN);
 
     if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
-    // split-K reduction over distributed shared memory + coalesced scatter stores (all warps)
-    int m_lo = 0, m_hi = 128;
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    const int per = 128 / p.ksplit;
+    const int m_lo = kr * per, m_hi = m_lo + per;
     const float *part[8];
-    part[0] = cst;
-    if (p.ksplit > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        cluster.sync();
-        const int per = 128 / p.ksplit;
-        m_lo = kr * per;
-        m_hi = m_lo + per;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) part[r] = r < p.ksplit ? cluster.map_shared_rank(cst, r) : cst;
-    }
+    for (int r = 0; r < 8; ++r) part[r] = r < p.ksplit ? cluster.map_shared_rank(cst, r) : cst;
     if (tid == 0) SIGE_TRACE(9);
     for (int q = tid + m_lo * (BN / 8); q < m_hi * (BN / 8); q += NTHREADS) {
         const int m = q / (BN / 8), nv = q - m * (BN / 8);
         const int n = n0 + nv * 8;
         if (n >= p.Cout) continue;
-        int tl, oy, ox;
-        if (TAPS == 9) { oy = m >> 5; tl = (m >> 2) & 7; ox = m & 3; } else { tl = m >> 4; oy = (m >> 2) & 3; ox = m & 3; }
-        if (tl >= ntile) continue;
-        const int t = tile0 + tl;
-        int hh = oy, ww = ox, img = t;
-        if (!p.dst_is_stack) {
-            const int nn = t % p.N;
-            hh += p.offH + __ldg(p.idx + 2 * nn);
-            ww += p.offW + __ldg(p.idx + 2 * nn + 1);
-            img = t / p.N;
+        const long long pixel = pixel_of(m);
+        if (pixel < 0) continue;
+        float4 c0[8], c1[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {             // all remote loads in flight before the first add
+            if (r < p.ksplit) {
+                const float *cs = part[r] + m * C::EPI_PITCH + nv * 8;
+                c0[r] = *reinterpret_cast<const float4 *>(cs);
+                c1[r] = *reinterpret_cast<const float4 *>(cs + 4);
+            }
         }
-        if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) continue;
         float v[8];
 #pragma unroll
         for (int z = 0; z < 8; ++z) v[z] = 0.f;
-        for (int r = 0; r < p.ksplit; ++r) {
-            const float *cs = part[r] + m * C::EPI_PITCH + nv * 8;
-            const float4 c0 = *reinterpret_cast<const float4 *>(cs), c1 = *reinterpret_cast<const float4 *>(cs + 4);
-            v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
-        }
-        if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        const long long pixel = ((long long)img * p.dH + hh) * p.dW + ww;
-        if (p.residual) {
-            const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(p.residual) + pixel * p.rC + p.res_c0 + n));
-            const T *re = reinterpret_cast<const T *>(&rr);
 #pragma unroll
-            for (int z = 0; z < 8; ++z) v[z] += DT<T>::to_f(re[z]);
-        }
-        uint4 o;
-        T *oe = reinterpret_cast<T *>(&o);
-#pragma unroll
-        for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(v[z]);
-        if (p.dst) *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(p.dst) + pixel * p.dC + p.dst_c0 + n) = o;
-        for (int ax = 0; ax < p.n_aux; ++ax) {   // extra destinations: the consumer's pre-op applied by the producer
-            const AuxDst &A = p.aux[ax];
-            float w8[8];
-#pragma unroll
-            for (int z = 0; z < 8; ++z) w8[z] = v[z];
-            if (A.scale) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.scale + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.scale + n + 4));
-                w8[0] *= s0.x; w8[1] *= s0.y; w8[2] *= s0.z; w8[3] *= s0.w; w8[4] *= s1.x; w8[5] *= s1.y; w8[6] *= s1.z; w8[7] *= s1.w;
+        for (int r = 0; r < 8; ++r) {
+            if (r < p.ksplit) {
+                v[0] += c0[r].x; v[1] += c0[r].y; v[2] += c0[r].z; v[3] += c0[r].w; v[4] += c1[r].x; v[5] += c1[r].y; v[6] += c1[r].z; v[7] += c1[r].w;
             }
-            if (A.shift) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.shift + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.shift + n + 4));
-                w8[0] += s0.x; w8[1] += s0.y; w8[2] += s0.z; w8[3] += s0.w; w8[4] += s1.x; w8[5] += s1.y; w8[6] += s1.z; w8[7] += s1.w;
-            }
-            uint4 oa;
-            T *ae = reinterpret_cast<T *>(&oa);
-#pragma unroll
-            for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(A.act, w8[z]));
-            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + pixel * A.C + A.c0 + n) = oa;
         }
+        emit(pixel, n, v);
     }
     if (tid == 0) SIGE_TRACE(10);
-    if (p.ksplit > 1) cg::this_cluster().sync();
+    cluster.sync();   // nobody leaves while a peer still reads its partial tile
     if (tid == 0) SIGE_TRACE(11);
 }
 
@@ -558,8 +620,12 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
     const int J = (p.Cin / KC) * TAPS;
     const long long base = (long long)ceil_div(p.NT, TILES) * (p.Cout / BN);
     if (p.ksplit <= 0) {
+        // one CTA per SM (214 KB smem): co-resident CTAs are 148 / 148 / 132 / 120 for cluster sizes 1 / 2 / 4 / 8
+        // (ncu 'Max Active Clusters': 74 x2, 15 x8); never spill into a second wave.  Splitting only pays when the K loop
+        // is long: each slice should keep >= 8 (tap, chunk) steps.
+        static const int kMaxCtas[9] = {0, 148, 148, 0, 132, 0, 0, 0, 120};
         int ks = 1;
-        while (ks < 8 && base * (ks * 2) <= 148 && J / (ks * 2) >= 3) ks *= 2;
+        while (ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && J / (ks * 2) >= 8) ks *= 2;
         p.ksplit = ks;
     }
     if (p.ksplit > J) p.ksplit = 1;
