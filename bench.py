@@ -64,9 +64,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=0, help="(reference arm) torch/OpenMP threads; 0 = sweep")
     ap.add_argument("--_cpu-child", dest="_cpu_child", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--tc5", action="store_true", help="engine: tcgen05/TMEM/TMA kernel where the geometry allows")
+    ap.add_argument("--no-tc5", action="store_true", help="engine: use the mma.sync kernel everywhere (default: tcgen05/TMEM/TMA kernel where the geometry allows)")
     ap.add_argument("--no-producer-preop", action="store_true", help="engine: apply GroupNorm affine + SiLU in every gather (reference order) instead of once in the producer's epilogue")
-    ap.add_argument("--pdl", action="store_true", help="engine: programmatic dependent launch between fused layers")
+    ap.add_argument("--no-branches", action="store_true", help="engine: keep the 1x1 shortcut convs on the main stream (no parallel graph branch)")
+    ap.add_argument("--no-pdl", action="store_true", help="engine: plain stream order between fused layers (default: programmatic dependent launch)")
     ap.add_argument("--ksplit", type=int, default=0, help="engine: force the split-K factor (0 = auto)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ncu", action="store_true",
@@ -291,7 +292,7 @@ def run_ours(args):
     if path == "engine":
         from sige_b200.engine import DDPMStepEngine
 
-        runner = DDPMStepEngine(model, x_dev, use_graph=not (args.no_graph or args.ncu), pdl=args.pdl, ksplit=args.ksplit, tc5=args.tc5, producer_preop=not args.no_producer_preop)
+        runner = DDPMStepEngine(model, x_dev, use_graph=not (args.no_graph or args.ncu), pdl=not args.no_pdl, ksplit=args.ksplit, tc5=not args.no_tc5, producer_preop=not args.no_producer_preop, branches=not args.no_branches)
     else:
         from sige_b200.graphs import GraphedStep
 

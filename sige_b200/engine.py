@@ -111,7 +111,7 @@ class ConvInRec:
 
 class DDPMStepEngine:
     def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True, pdl: bool = False, ksplit: int = 0,
-                 tc5: bool = False, producer_preop: bool = True):
+                 tc5: bool = False, producer_preop: bool = True, branches: bool = True):
         if model.mode != "sparse":
             raise RuntimeError("DDPMStepEngine: run the dense pass, set_masks() and set_mode('sparse') first")
         p = next(model.parameters())
@@ -119,7 +119,8 @@ class DDPMStepEngine:
             raise RuntimeError("DDPMStepEngine needs a CUDA fp16/bf16 model (tensor-core path)")
         self.model, self.dev, self.dtype = model, p.device, p.dtype
         self.x = x_static
-        self.pdl, self.ksplit, self.tc5, self.producer_preop = pdl, ksplit, tc5, producer_preop
+        self.pdl, self.ksplit, self.tc5, self.producer_preop, self.branches = pdl, ksplit, tc5, producer_preop, branches
+        self.side_stream = torch.cuda.Stream(device=p.device)
         assert x_static.is_cuda and x_static.dtype == self.dtype and x_static.is_contiguous(memory_format=torch.channels_last)
         self.steps: List = []          # callables taking the stream handle
         self.fused: List[FusedConv] = []
@@ -200,7 +201,7 @@ class DDPMStepEngine:
         return ops.pack_conv_weight(w.contiguous(), self.dtype), (None if b is None else b.contiguous())
 
     def conv(self, name: str, srcs: Sequence[Src], hw: Tuple[int, int], idx: torch.Tensor, block: int, conv, stride: int, off: int,
-             dst: Buf, residual: Optional[Buf] = None, packed=None) -> Optional[FusedConv]:
+             dst: Buf, residual: Optional[Buf] = None, packed=None, side: bool = False) -> Optional[FusedConv]:
         """Emit one fused gather->conv->scatter launch.  Each source is (buffer, upsample flag, affine); an affine
         source is read from the pre-transformed view its producer maintains, else the gather applies the pre-op."""
         n = int(idx.shape[0])
@@ -265,7 +266,7 @@ class DDPMStepEngine:
         fc = FusedConv(d, [idx, sc, sh, wp, b32, dst, residual, tensors], name, nbytes, flops, n, out_elems)
         dst.producers.append(fc)
         self.fused.append(fc)
-        self.steps.append(fc.launch)
+        self.steps.append(("side" if side else "main", fc.launch))
         return fc
 
     # ------------------------------------------------------------------ graph construction
@@ -275,6 +276,7 @@ class DDPMStepEngine:
         h, w = hw
         cout = blk.out_channels
         keep_t1_raw = not self.producer_preop
+        joined = False
         if blk.main_sparse:
             g = blk.main_gather
             idx, bs, off = g.active_indices, g.block_size[0], g.offset[0]
@@ -298,11 +300,17 @@ class DDPMStepEngine:
             else:
                 sidx, sbs, soff = self.all_tiles(h, w, 0), 4, 0
                 skip = self.fresh(cout, h, w)
-            self.conv(name + ".nin_shortcut", [(b, up, None) for (b, up) in ins], hw, sidx, sbs, blk.nin_shortcut, 1, soff, skip)
+            # the 1x1 shortcut only depends on the block input: it runs on a parallel branch next to conv1 and is
+            # joined before conv2 (which adds it as the residual)
+            self.conv(name + ".nin_shortcut", [(b, up, None) for (b, up) in ins], hw, sidx, sbs, blk.nin_shortcut, 1, soff, skip,
+                      side=self.branches)
+            joined = self.branches
         else:
             assert len(ins) == 1 and ins[0][1] == 0
             skip = ins[0][0]
         self.conv(name + ".conv1", segs, hw, idx, bs, blk.conv1, 1, off, t1)
+        if joined:
+            self.steps.append(("join", None))
         self.conv(name + ".conv2", [(t1, 0, (blk.scale2s[cid].reshape(-1), blk.shift2s[cid].reshape(-1), "swish"))], hw, idx, bs, blk.conv2, 1,
                   off, t2, residual=skip)
         return t2
@@ -330,7 +338,7 @@ class DDPMStepEngine:
             att = torch.softmax(torch.matmul(q, k.t()), dim=-1)
             torch.matmul(att, v, out=o_tok)
 
-        self.steps.append(attention)
+        self.steps.append(("main", attention))
         out = self.fresh(c, h, w)
         self.conv(name + ".proj_out", [(att_out, 0, None)], hw, idx, 4, blk.proj_out, 1, 0, out, residual=x)
         return out
@@ -348,7 +356,7 @@ class DDPMStepEngine:
         def conv_in(_stream):
             ops.conv_in_nhwc(self.x, w_in, b_in, out=h0.raw, aux=rec.aux)
 
-        self.steps.append(conv_in)
+        self.steps.append(("main", conv_in))
         hs: List[Tuple[Buf, int]] = [(h0, res)]
         # ---- down
         for lvl in range(m.num_resolutions):
@@ -407,14 +415,26 @@ class DDPMStepEngine:
             ops.group_norm_fold(h_last, gn_g, gn_eps, gn_w, gn_b, scale=gn_scale, shift=gn_shift, workspace=gn_ws)
             ops.conv_out_nhwc(h_last, gn_scale, gn_shift, "swish", w_out, b_out, out=self.output)
 
-        self.steps.append(tail)
+        self.steps.append(("main", tail))
 
     # ------------------------------------------------------------------ execution
     def run_eager(self) -> torch.Tensor:
-        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        main = torch.cuda.current_stream(self.dev)
+        side = self.side_stream
+        pending = False
         with torch.no_grad():
-            for s in self.steps:
-                s(stream)
+            for kind, fn in self.steps:
+                if kind == "main":
+                    fn(main.cuda_stream)
+                elif kind == "side":          # fork: the side branch starts after everything issued so far on main
+                    side.wait_stream(main)
+                    fn(side.cuda_stream)
+                    pending = True
+                elif kind == "join" and pending:
+                    main.wait_stream(side)
+                    pending = False
+            if pending:
+                main.wait_stream(side)
         return self.output
 
     def _finalize(self, use_graph: bool) -> None:
