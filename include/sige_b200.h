@@ -235,7 +235,7 @@ int sige_group_norm_fold_workspace(int B, int C);
 int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, int groups, float eps,
                          const void *gamma, const void *beta, float *scale, float *shift,
                          float *workspace, int workspace_floats, sige_stream_t stream);
-/* out(NCHW, B x Cout x H x W) = conv3x3_pad1( act(x*scale + shift) ), Cout <= 4; scale/shift fp32 [B, C] or NULL. */
+/* out(NCHW, B x Cout x H x W) = conv3x3_pad1( act(x*scale + shift) ), Cout <= 8, C % 16 == 0; scale/shift fp32 [B, C] or NULL. */
 int sige_conv_out_nhwc(const void *x, const float *scale, const float *shift, int act, const void *w,
                        const void *bias, void *out, int dtype, int B, int H, int W, int C, int Cout,
                        sige_stream_t stream);

@@ -7,6 +7,8 @@
 // they are pure HBM streams: 16.8 MB written (conv_in) or read (stats, conv_out) at 256x256x128.
 //
 // All three are deterministic (fixed reduction order), stream-ordered and allocation-free.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sige {
@@ -169,27 +171,31 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float *__restri
 }
 
 // ------------------------------------------------------------------------------------------
-// conv_out: y = conv3x3(act(x*scale+shift)), C -> Cout <= 4, output NCHW.
-// CTA = 8 x 32 output pixels; the (8+2) x (32+2) halo is transformed ONCE into shared memory
-// (row pitch C*2+16 bytes -> conflict-free 16-byte reads), then one thread = one output pixel.
+// conv_out: y = conv3x3(act(x*scale+shift)), C -> Cout <= 8, output NCHW.
+// CTA = 8 x 32 output pixels, one warp per output row.  The (8+2) x (32+2) halo is transformed ONCE into shared
+// memory (row pitch C*2+16 bytes -> conflict-free ldmatrix), then the conv is an implicit GEMM on the legacy tensor
+// path: M = 16 consecutive pixels of the row, N = 8 (Cout zero-padded), K = 9*C, mma.sync.m16n8k16; the A fragment of
+// tap (ky,kx) is a set of ldmatrix row pointers into the halo tile shifted by (ky,kx).
 // ------------------------------------------------------------------------------------------
 constexpr int CO_TH = 8, CO_TW = 32;
 
 template <typename T>
-__global__ void __launch_bounds__(CO_TH *CO_TW) conv_out_kernel(const T *__restrict__ x, const float *__restrict__ scale,
-                                                                  const float *__restrict__ shift, int act, const T *__restrict__ w,
-                                                                  const T *__restrict__ bias, T *__restrict__ out, int B, int H, int W,
-                                                                  int C, int Cout) {
+__global__ void __launch_bounds__(CO_TH * 32) conv_out_kernel(const T *__restrict__ x, const float *__restrict__ scale,
+                                                                const float *__restrict__ shift, int act, const T *__restrict__ w,
+                                                                const T *__restrict__ bias, T *__restrict__ out, int B, int H, int W,
+                                                                int C, int Cout) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int pitch = C * 2 + 16;
     const int HP = CO_TH + 2, WP = CO_TW + 2;
+    const int K = 9 * C, wpitch = K * 2 + 16;                                 // bytes per weight row (odd number of 16-byte units)
     unsigned char *tile = smraw;                                             // [HP*WP][pitch]
-    float *wsm = reinterpret_cast<float *>(smraw + ((HP * WP * pitch + 15) & ~15));   // [9][C][4]
+    unsigned char *wsm = smraw + ((HP * WP * pitch + 15) & ~15);             // [8][wpitch]: B operand, row n = output channel
     const int b = blockIdx.z, ty0 = blockIdx.y * CO_TH, tx0 = blockIdx.x * CO_TW;
-    for (int e = threadIdx.x; e < 9 * C * 4; e += blockDim.x) {
-        const int co = e & 3, rest = e >> 2;
-        const int ci = rest % C, tap = rest / C;
-        wsm[e] = co < Cout ? DT<T>::to_f(w[((long long)co * C + ci) * 9 + tap]) : 0.f;
+    for (int e = threadIdx.x; e < 8 * K; e += blockDim.x) {
+        const int n = e / K, k = e - n * K;                                  // k = tap*C + ci
+        const int tap = k / C, ci = k - tap * C;
+        const T v = n < Cout ? w[((long long)n * C + ci) * 9 + tap] : DT<T>::from_f(0.f);
+        *reinterpret_cast<T *>(wsm + n * wpitch + k * 2) = v;
     }
     const int CV = C / 8;
     const bool pre = scale || shift || act != SIGE_ACT_IDENTITY;
@@ -214,27 +220,53 @@ __global__ void __launch_bounds__(CO_TH *CO_TW) conv_out_kernel(const T *__restr
         *reinterpret_cast<uint4 *>(tile + pp * pitch + cv * 16) = v;       // zero padding AFTER the pre-op
     }
     __syncthreads();
-    const int ly = threadIdx.x / CO_TW, lx = threadIdx.x % CO_TW;
-    const int hh = ty0 + ly, ww = tx0 + lx;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;            // warp = output row inside the tile
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tile), wbase = (uint32_t)__cvta_generic_to_shared(wsm);
+    const int a_row = lane & 15, a_khalf = lane >> 4;                      // ldmatrix.x4: 16 pixel rows x {k-lo, k-hi}
+    const int b_row = lane & 7, b_khalf = (lane >> 3) & 1;                 // ldmatrix.x2: 8 channel rows x {k-lo, k-hi}
     for (int tap = 0; tap < 9; ++tap) {
         const int ky = tap / 3, kx = tap - 3 * ky;
-        const unsigned char *row = tile + ((ly + ky) * WP + lx + kx) * pitch;
-        const float4 *wt = reinterpret_cast<const float4 *>(wsm + tap * C * 4);
-        for (int cv = 0; cv < CV; ++cv) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(row + cv * 16);
-            const T *el = reinterpret_cast<const T *>(&v);
+        const uint32_t arow0 = tbase + ((warp + ky) * WP + kx + a_row) * pitch + a_khalf * 16;
+        const uint32_t brow = wbase + b_row * wpitch + (tap * C) * 2 + b_khalf * 16;
+        for (int kk = 0; kk < C / 16; ++kk) {
+            uint32_t b0, b1;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(b0), "=r"(b1) : "r"(brow + kk * 32));
 #pragma unroll
-            for (int z = 0; z < 8; ++z) {
-                const float f = DT<T>::to_f(el[z]);
-                const float4 wv = wt[cv * 8 + z];
-                acc[0] = fmaf(f, wv.x, acc[0]); acc[1] = fmaf(f, wv.y, acc[1]); acc[2] = fmaf(f, wv.z, acc[2]); acc[3] = fmaf(f, wv.w, acc[3]);
+            for (int i = 0; i < 2; ++i) {
+                uint32_t a0, a1, a2, a3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                             : "r"(arow0 + i * 16 * pitch + kk * 32));
+                if (std::is_same<T, __half>::value) {
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                                 : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+                } else {
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                                 : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+                }
             }
         }
     }
-    if (hh < H && ww < W)
-        for (int co = 0; co < Cout; ++co)
-            out[(((long long)b * Cout + co) * H + hh) * W + ww] = DT<T>::from_f(acc[co] + (bias ? DT<T>::to_f(bias[co]) : 0.f));
+    // accumulator fragment: rows (pixels) lane/4 and lane/4+8, columns (channels) 2*(lane%4), +1
+    const int hh = ty0 + warp;
+    if (hh < H) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int ww = tx0 + i * 16 + (lane >> 2) + half * 8;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int co = 2 * (lane & 3) + q;
+                    if (co < Cout && ww < W)
+                        out[(((long long)b * Cout + co) * H + hh) * W + ww] =
+                            DT<T>::from_f(acc[i][half * 2 + q] + (bias ? DT<T>::to_f(bias[co]) : 0.f));
+                }
+            }
+    }
 }
 
 }  // namespace sige
@@ -252,7 +284,7 @@ int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out,
     SIGE_REQUIRE(smem <= 48 * 1024, "sige_conv_in_nhwc: weights do not fit in shared memory");
     const long long total = (long long)B * H * W * (Cout / 8);
     const long long want_blocks = (total + 255) / 256;
-    const int grid = (int)(want_blocks < 148LL * 16 ? want_blocks : 148LL * 16);
+    const int grid = (int)(want_blocks < 148LL * 2 ? want_blocks : 148LL * 2);   // persistent: the weight staging is paid once per CTA
     cudaStream_t st = (cudaStream_t)stream;
     SIGE_REQUIRE(n_aux >= 0 && n_aux <= 2 && (n_aux == 0 || aux), "sige_conv_in_nhwc: n_aux must be 0..2");
     InAux ia[2] = {{nullptr, nullptr, nullptr, 0}, {nullptr, nullptr, nullptr, 0}};
@@ -303,18 +335,18 @@ int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, i
 int sige_conv_out_nhwc(const void *x, const float *scale, const float *shift, int act, const void *w, const void *bias, void *out, int dtype,
                        int B, int H, int W, int C, int Cout, sige_stream_t stream) {
     SIGE_REQUIRE(x && w && out, "sige_conv_out_nhwc: null pointer");
-    SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && Cout >= 1 && Cout <= 4, "sige_conv_out_nhwc: needs C %% 8 == 0 and Cout <= 4");
+    SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 16 == 0 && Cout >= 1 && Cout <= 8, "sige_conv_out_nhwc: needs C %% 16 == 0 and Cout <= 8");
     SIGE_REQUIRE(act == SIGE_ACT_IDENTITY || act == SIGE_ACT_SWISH, "sige_conv_out_nhwc: unknown activation %d", act);
     SIGE_REQUIRE(((uintptr_t)x & 15) == 0, "sige_conv_out_nhwc: input not 16-byte aligned");
     const int pitch = C * 2 + 16;
-    const size_t smem = (((size_t)(CO_TH + 2) * (CO_TW + 2) * pitch + 15) & ~(size_t)15) + sizeof(float) * 9 * C * 4;
+    const size_t smem = (((size_t)(CO_TH + 2) * (CO_TW + 2) * pitch + 15) & ~(size_t)15) + (size_t)8 * (9 * C * 2 + 16);
     SIGE_REQUIRE(smem <= 227 * 1024, "sige_conv_out_nhwc: %d channels do not fit in shared memory", C);
     dim3 grid((W + CO_TW - 1) / CO_TW, (H + CO_TH - 1) / CO_TH, B);
     cudaStream_t st = (cudaStream_t)stream;
 #define SIGE_CO(T)                                                                                                        \
     do {                                                                                                                  \
         cudaFuncSetAttribute(conv_out_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
-        conv_out_kernel<T><<<grid, CO_TH * CO_TW, smem, st>>>((const T *)x, scale, shift, act, (const T *)w, (const T *)bias, (T *)out, B, H, W, \
+        conv_out_kernel<T><<<grid, CO_TH * 32, smem, st>>>((const T *)x, scale, shift, act, (const T *)w, (const T *)bias, (T *)out, B, H, W, \
                                                               C, Cout);                                                  \
     } while (0)
     switch (dtype) {

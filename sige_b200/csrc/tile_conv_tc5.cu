@@ -81,13 +81,19 @@ struct Params {
     long long *trace;          // development aid: per-CTA clock stamps (16 slots), or nullptr
 };
 
-template <int BN> struct Cfg {
-    static constexpr int NSTB = (BN == 128) ? 4 : 8;           // weight ring depth
-    static constexpr int B_STAGE_BYTES = BN * 128;
+template <int BN, int TAPS> struct Cfg {
+    // one weight-ring stage = TPS taps (a whole kernel row for the narrow 3x3 configuration): fewer barrier round
+    // trips for the single MMA-issuing thread
+    static constexpr int TPS = (TAPS == 9 && BN == 64) ? 3 : 1;
+    static constexpr int SPC = TAPS / TPS;                     // ring steps per 64-channel chunk
+    static constexpr int B_TILE_BYTES = BN * 128;              // one (tap, chunk) weight tile
+    static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES;
+    static constexpr int NSTB = (BN == 128) ? 4 : (TPS == 3 ? 3 : 8);   // weight ring depth
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = 2 * A_BUF_BYTES;
     static constexpr int OFF_BAR = OFF_B + NSTB * B_STAGE_BYTES;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;    // barriers + slack for the 1024-byte alignment
+    static constexpr int OFF_CONST = OFF_BAR + 256;            // idx[8][2] ints, then bias | aux0 scale,shift | aux1 scale,shift (BN floats each)
+    static constexpr int SMEM_BYTES = OFF_CONST + 64 + 5 * BN * 4 + 1024;    // + slack for the 1024-byte alignment
     static constexpr int EPI_PITCH = BN + EPI_PAD;             // floats
     static_assert(128 * EPI_PITCH * 4 <= 2 * A_BUF_BYTES, "epilogue staging must fit in the halo buffers");
 };
@@ -195,8 +201,8 @@ __device__ __forceinline__ long long gtime() {
 template <typename T, int BN, int TAPS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap) {
-    using C = Cfg<BN>;
-    constexpr int NSTB = C::NSTB;
+    using C = Cfg<BN, TAPS>;
+    constexpr int NSTB = C::NSTB, TPS = C::TPS, SPC = C::SPC;
     constexpr int R = (TAPS == 9) ? 6 : 4;            // halo tile extent
     constexpr int RS = R * R;
     constexpr int UNITS = TILES * RS * 8;             // 16-byte units gathered per chunk
@@ -219,10 +225,12 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     const int n0 = blockIdx.y * BN;
     const int ntile = min(TILES, p.NT - tile0);
     const int NC = p.Cin / KC;
-    const int J = NC * TAPS;
+    const int J = NC * SPC;                        // ring steps of the whole K loop (a step = TPS taps of one chunk)
     const int kr = blockIdx.z;
     const int j_begin = (int)(((long long)J * kr) / p.ksplit), j_end = (int)(((long long)J * (kr + 1)) / p.ksplit);
-    const int c_first = j_begin / TAPS, c_last = (j_end - 1) / TAPS;
+    const int c_first = j_begin / SPC, c_last = (j_end - 1) / SPC;
+    int32_t *s_idx = reinterpret_cast<int32_t *>(smem + C::OFF_CONST);          // [TILES][2] tile origins of this CTA
+    float *s_const = reinterpret_cast<float *>(smem + C::OFF_CONST + 64);       // bias | aux0 scale | aux0 shift | aux1 scale | aux1 shift
 
     if (tid == 0) SIGE_TRACE(0);
     // ---------------- one-time setup ----------------
@@ -236,6 +244,21 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
         __syncwarp();
         tmem_alloc(s32(tmem_slot), BN);     // BN fp32 accumulator columns (power of two >= 32)
+    } else if (warp == 2) {
+        // this CTA's tile origins (constant since set_masks): one global round trip here instead of one per gather thread
+        if (lane < 2 * TILES) {
+            const int t = tile0 + (lane >> 1);
+            int v = 0;
+            if (t < p.NT && p.idx) v = __ldg(p.idx + 2 * (t % p.N) + (lane & 1));
+            s_idx[lane] = v;
+        }
+    } else if (warp >= 3 && warp < 8) {
+        // per-channel epilogue constants of this CTA's BN output channels
+        const int which = warp - 3;                         // 0 bias, 1/2 aux0 scale/shift, 3/4 aux1 scale/shift
+        const float *src = which == 0 ? p.bias : (which == 1 ? p.aux[0].scale : which == 2 ? p.aux[0].shift : which == 3 ? p.aux[1].scale : p.aux[1].shift);
+        const bool on = which == 0 || (which <= 2 ? p.n_aux > 0 : p.n_aux > 1);
+        const float dflt = (which == 1 || which == 3) ? 1.f : 0.f;
+        for (int e = lane; e < BN; e += 32) s_const[which * BN + e] = (on && src && n0 + e < p.Cout) ? __ldg(src + n0 + e) : dflt;
     }
     tc_fence_before();
     __syncthreads();
@@ -251,28 +274,23 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 const int it = j - j_begin, s = it % NSTB, k = it / NSTB;
                 mbar_wait(B_EMPTY(s), (k & 1) ^ 1);
                 mbar_expect_tx(B_FULL(s), C::B_STAGE_BYTES);
-                const int c = j / TAPS, tap = j - c * TAPS;
-                tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES, &wmap, 0, (tap * NC + c) * p.Cout + n0, B_FULL(s));
+                const int c = j / SPC, tap0 = (j - c * SPC) * TPS;
+#pragma unroll
+                for (int t = 0; t < TPS; ++t)
+                    tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES + t * C::B_TILE_BYTES, &wmap, 0, ((tap0 + t) * NC + c) * p.Cout + n0,
+                                B_FULL(s));
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // the epilogue's small read-only vectors are cold in L2 on the first touch of a step: pull them in now
-        {
-            const int off = lane * 32;     // 128-byte lines of fp32
-            if (p.bias && n0 + off < p.Cout) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.bias + n0 + off));
-            for (int ax = 0; ax < p.n_aux; ++ax) {
-                if (p.aux[ax].scale && n0 + off < p.Cout) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.aux[ax].scale + n0 + off));
-                if (p.aux[ax].shift && n0 + off < p.Cout) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.aux[ax].shift + n0 + off));
-            }
-        }
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BN, p.is_bf16);
             int ab = 0, ause = 0;             // halo buffer index and how many times it has been used
             for (int j = j_begin; j < j_end; ++j) {
-                const int c = j / TAPS, tap = j - c * TAPS;
-                if (j == j_begin || tap == 0) {                       // a new chunk starts: wait for its halo buffer
+                const int c = j / SPC, st = j - c * SPC;
+                (void)c;
+                if (j == j_begin || st == 0) {                        // a new chunk starts: wait for its halo buffer
                     mbar_wait(A_FULL(ab), (ause >> 1) & 1);
                     tc_fence_after();
                     if (j == j_begin) SIGE_TRACE(5);
@@ -280,14 +298,19 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 const int it = j - j_begin, s = it % NSTB, k = it / NSTB;
                 mbar_wait(B_FULL(s), k & 1);
                 tc_fence_after();
-                const int ky = (TAPS == 9) ? tap / 3 : 0, kx = (TAPS == 9) ? tap - 3 * ky : 0;
-                const uint32_t a_addr = sbase + C::OFF_A + ab * A_BUF_BYTES + kx * A_COPY_BYTES + ky * (32 * 128);
-                const uint32_t b_addr = sbase + C::OFF_B + s * C::B_STAGE_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < KC / 16; ++kk)
-                    umma_f16(tmem_base, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), idesc, (j > j_begin || kk > 0) ? 1u : 0u);
+                for (int t = 0; t < TPS; ++t) {
+                    const int tap = st * TPS + t;
+                    const int ky = (TAPS == 9) ? tap / 3 : 0, kx = (TAPS == 9) ? tap - 3 * ky : 0;
+                    const uint32_t a_addr = sbase + C::OFF_A + ab * A_BUF_BYTES + kx * A_COPY_BYTES + ky * (32 * 128);
+                    const uint32_t b_addr = sbase + C::OFF_B + s * C::B_STAGE_BYTES + t * C::B_TILE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < KC / 16; ++kk)
+                        umma_f16(tmem_base, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), idesc,
+                                 (j > j_begin || t > 0 || kk > 0) ? 1u : 0u);
+                }
                 umma_commit(B_EMPTY(s));                              // weight stage free once these MMAs retire
-                if (tap == TAPS - 1 || j == j_end - 1) {              // chunk done: halo buffer free
+                if (st == SPC - 1 || j == j_end - 1) {                // chunk done: halo buffer free
                     umma_commit(A_EMPTY(ab));
                     ab ^= 1;
                     ++ause;
@@ -316,10 +339,10 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 g_pix[k] = -1;
                 const int t = tile0 + tl;
                 if (t < p.NT) {
-                    int n = t, b = 0;
-                    if (p.NT != p.N) { b = t / p.N; n = t - b * p.N; }      // batch > 1 only (SD); DDPM is batch 1
+                    int b = 0;
+                    if (p.NT != p.N) b = t / p.N;                          // batch > 1 only (SD); DDPM is batch 1
                     int hh = y, ww = x, img = t;
-                    if (!p.src_is_stack) { hh += __ldg(p.idx + 2 * n); ww += __ldg(p.idx + 2 * n + 1); img = b; }
+                    if (!p.src_is_stack) { hh += s_idx[2 * tl]; ww += s_idx[2 * tl + 1]; img = b; }
                     g_img[k] = img; g_ab[k] = b;
                     if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) g_pix[k] = (hh << 16) | ww;
                 }
@@ -410,9 +433,9 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     float *cst = reinterpret_cast<float *>(smem + C::OFF_A);
     // v[8] (fp32 conv result of 8 consecutive channels starting at n) -> +bias, +residual -> dst and aux destinations
     auto emit = [&](long long pixel, int n, float (&v)[8]) {
-        if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
+        const int nl = n - n0;
+        {
+            const float4 b0 = *reinterpret_cast<const float4 *>(s_const + nl), b1 = *reinterpret_cast<const float4 *>(s_const + nl + 4);
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
         if (p.residual) {
@@ -430,21 +453,11 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
         for (int ax = 0; ax < p.n_aux; ++ax) {   // extra destinations: the consumer's pre-op applied by the producer
             const AuxDst &A = p.aux[ax];
-            float w8[8];
-#pragma unroll
-            for (int z = 0; z < 8; ++z) w8[z] = v[z];
-            if (A.scale) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.scale + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.scale + n + 4));
-                w8[0] *= s0.x; w8[1] *= s0.y; w8[2] *= s0.z; w8[3] *= s0.w; w8[4] *= s1.x; w8[5] *= s1.y; w8[6] *= s1.z; w8[7] *= s1.w;
-            }
-            if (A.shift) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(A.shift + n)), s1 = __ldg(reinterpret_cast<const float4 *>(A.shift + n + 4));
-                w8[0] += s0.x; w8[1] += s0.y; w8[2] += s0.z; w8[3] += s0.w; w8[4] += s1.x; w8[5] += s1.y; w8[6] += s1.z; w8[7] += s1.w;
-            }
+            const float *sc = s_const + (1 + 2 * ax) * BN + nl, *sh = sc + BN;      // staged (scale defaults to 1, shift to 0)
             uint4 oa;
             T *ae = reinterpret_cast<T *>(&oa);
 #pragma unroll
-            for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(A.act, w8[z]));
+            for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(A.act, fmaf(v[z], sc[z], sh[z])));
             *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + pixel * A.C + A.c0 + n) = oa;
         }
     };
@@ -456,11 +469,10 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         const int t = tile0 + tl;
         int hh = oy, ww = ox, img = t;
         if (!p.dst_is_stack) {
-            int nn = t;
             img = 0;
-            if (p.NT != p.N) { img = t / p.N; nn = t - img * p.N; }
-            hh += p.offH + __ldg(p.idx + 2 * nn);
-            ww += p.offW + __ldg(p.idx + 2 * nn + 1);
+            if (p.NT != p.N) img = t / p.N;
+            hh += p.offH + s_idx[2 * tl];
+            ww += p.offW + s_idx[2 * tl + 1];
         }
         if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) return -1;
         return ((long long)img * p.dH + hh) * p.dW + ww;
@@ -586,7 +598,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 template <typename T, int BN, int TAPS> static int launch(Params &p, const void *w_packed, cudaStream_t st) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, TAPS>;
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("sige_tile_conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
@@ -617,7 +629,7 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
         }
         attr_dev = dev;
     }
-    const int J = (p.Cin / KC) * TAPS;
+    const int J = (p.Cin / KC) * C::SPC;        // ring steps
     const long long base = (long long)ceil_div(p.NT, TILES) * (p.Cout / BN);
     if (p.ksplit <= 0) {
         // one CTA per SM (214 KB smem): co-resident CTAs are 148 / 148 / 132 / 120 for cluster sizes 1 / 2 / 4 / 8
@@ -625,7 +637,7 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
         // is long: each slice should keep >= 8 (tap, chunk) steps.
         static const int kMaxCtas[9] = {0, 148, 148, 0, 132, 0, 0, 0, 120};
         int ks = 1;
-        while (ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && J / (ks * 2) >= 8) ks *= 2;
+        while (ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * C::TPS) / (ks * 2) >= 8) ks *= 2;
         p.ksplit = ks;
     }
     if (p.ksplit > J) p.ksplit = 1;

@@ -29,7 +29,7 @@ def test_group_norm_fold_and_conv_out(dtype, tol):
     from sige_b200 import ops
 
     torch.manual_seed(1)
-    for (B, C, G, H, W, Cout) in [(1, 128, 32, 256, 256, 3), (2, 64, 32, 24, 40, 3), (1, 256, 32, 16, 16, 4), (1, 32, 32, 7, 9, 1)]:
+    for (B, C, G, H, W, Cout) in [(1, 128, 32, 256, 256, 3), (2, 64, 32, 24, 40, 3), (1, 256, 32, 16, 16, 4), (1, 32, 32, 7, 9, 1), (1, 64, 32, 40, 70, 8)]:
         x = (torch.randn(B, C, H, W, device=DEV) * 1.5 + 0.3).to(dtype).contiguous(memory_format=torch.channels_last)
         gamma = (1 + 0.1 * torch.randn(C, device=DEV)).to(dtype)
         beta = (0.1 * torch.randn(C, device=DEV)).to(dtype)
