@@ -29,6 +29,28 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def profiled_traffic():
+    """DRAM traffic of the dominant kernel from the committed ncu capture (profiles/r01e_tileconv_dram_traffic_step.csv:
+    dram__bytes_read.sum + dram__bytes_write.sum of every fused tile-conv launch of one step), as average bytes per
+    launch; None if the capture is absent."""
+    import csv
+
+    path = os.path.join(_REPO, "profiles", "r01e_tileconv_dram_traffic_step.csv")
+    try:
+        rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+        hdr = rows[0]
+        vi, ui, mi, ii = hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Metric Name"), hdr.index("ID")
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total, ids = 0.0, set()
+        for r in rows[1:]:
+            if r[mi] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and r[ui] in mult:
+                total += float(r[vi].replace(",", "")) * mult[r[ui]]
+                ids.add(r[ii])
+        return total / max(1, len(ids)) if ids else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def conv_layers_of_step(model, x, t):
     """One sparse forward with hooks: [(module, input stack shape)] for every tensor-core tile conv."""
     seen = []
@@ -133,8 +155,9 @@ def measure_engine(engine, flush, reps: int = 5):
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
     slow = sorted(per, key=lambda r: -r[1])[:5]
     return {
-        "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
-        "kernel": "sige::tile_conv_mma_kernel (all %d fused gather-conv-scatter launches of one step)" % len(per),
+        "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+        "traffic": profiled_traffic(), "algorithmic_bytes_per_launch": tot_bytes / max(1, len(per)),
+        "kernel": "sige::tc5::tile_conv_tc5_kernel / sige::tile_conv_mma_kernel (all %d fused gather-conv-scatter launches of one step)" % len(per),
         "avg_launch_us": 1e3 * tot_ms / max(1, len(per)), "algorithmic_bytes_per_step": tot_bytes, "peak_source": pk["source"],
         "tensor": {"achieved_tflops": tot_flops / (tot_ms * 1e-3) / 1e12, "peak_tflops": pk["bf16_tflops"],
                    "frac": tot_flops / (tot_ms * 1e-3) / 1e12 / pk["bf16_tflops"]},
