@@ -45,10 +45,10 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, c
     float *bsm = wsm + OV * pitch;
     for (int e = threadIdx.x; e < Cout; e += blockDim.x) bsm[e] = bias ? DT<T>::to_f(bias[e]) : 0.f;
     __syncthreads();
-    const long long total = (long long)B * H * W * OV;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int total = B * H * W * OV;      // < 2^31 (checked on the host): 32-bit index math, 64-bit division is slow
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ov = i % OV;
-        long long pix = i / OV;
+        int pix = i / OV;
         const int ww = pix % W; pix /= W;
         const int hh = pix % H;
         const int b = pix / H;
@@ -75,19 +75,23 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, c
         T *oe = reinterpret_cast<T *>(&o);
 #pragma unroll
         for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(acc[z]);
-        *reinterpret_cast<uint4 *>(out + i * 8) = o;
+        *reinterpret_cast<uint4 *>(out + (long long)i * 8) = o;
         for (int ax = 0; ax < n_aux; ++ax) {   // the consumers' GroupNorm affine + SiLU, applied once here
             const InAux &A = ax == 0 ? a0 : a1;
             uint4 oa;
             T *ae = reinterpret_cast<T *>(&oa);
-#pragma unroll
-            for (int z = 0; z < 8; ++z) {
-                float f = acc[z];
-                if (A.scale) f *= __ldg(A.scale + ov * 8 + z);
-                if (A.shift) f += __ldg(A.shift + ov * 8 + z);
-                ae[z] = DT<T>::from_f(activate<true>(A.act, f));
+            float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (A.scale) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(A.scale + ov * 8)), c = __ldg(reinterpret_cast<const float4 *>(A.scale + ov * 8 + 4));
+                sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = c.x; sc[5] = c.y; sc[6] = c.z; sc[7] = c.w;
             }
-            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + i * 8) = oa;
+            if (A.shift) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(A.shift + ov * 8)), c = __ldg(reinterpret_cast<const float4 *>(A.shift + ov * 8 + 4));
+                sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w; sh[4] = c.x; sh[5] = c.y; sh[6] = c.z; sh[7] = c.w;
+            }
+#pragma unroll
+            for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(A.act, fmaf(acc[z], sc[z], sh[z])));
+            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + (long long)i * 8) = oa;
         }
     }
 }
@@ -283,6 +287,7 @@ int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out,
     const size_t smem = sizeof(float) * ((size_t)(Cout / 8) * conv_in_pitch(Cin) + Cout);
     SIGE_REQUIRE(smem <= 48 * 1024, "sige_conv_in_nhwc: weights do not fit in shared memory");
     const long long total = (long long)B * H * W * (Cout / 8);
+    SIGE_REQUIRE(total < 2147483647LL, "sige_conv_in_nhwc: tensor too large");
     const long long want_blocks = (total + 255) / 256;
     const int grid = (int)(want_blocks < 148LL * 2 ? want_blocks : 148LL * 2);   // persistent: the weight staging is paid once per CTA
     cudaStream_t st = (cudaStream_t)stream;
