@@ -115,7 +115,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:

@@ -637,7 +637,7 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
         // (ncu 'Max Active Clusters': 74 x2, 15 x8); never spill into a second wave.  Splitting only pays when the K loop
         // is long: each slice should keep >= 8 (tap, chunk) steps.
         static const int kMaxCtas[9] = {0, 148, 148, 0, 132, 0, 0, 0, 120};
-        static int min_taps = getenv("SIGE_TC5_MIN_TAPS") ? atoi(getenv("SIGE_TC5_MIN_TAPS")) : 8;   // tuning knob (taps per K slice)
+        static int min_taps = getenv("SIGE_TC5_MIN_TAPS") ? atoi(getenv("SIGE_TC5_MIN_TAPS")) : 3;   // tuning knob (taps per K slice)
         int ks = 1;
         while (ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * C::TPS) / (ks * 2) >= min_taps) ks *= 2;
         p.ksplit = ks;

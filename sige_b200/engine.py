@@ -70,7 +70,11 @@ class FusedConv:
         self.out_elems = out_elems
 
     def launch(self, stream: int) -> None:
+        if FusedConv.trace_hook is not None:      # development aid (tools/trace_engine.py)
+            FusedConv.trace_hook(self)
         ops.launch_tile_conv(self.desc, stream)
+
+    trace_hook = None
 
     def can_aux(self) -> bool:
         return self.desc.n_aux < 2

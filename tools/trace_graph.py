@@ -1,0 +1,57 @@
+"""In-graph timeline of the DDPM step engine: every tcgen05 fused launch stamps globaltimer into its own trace
+buffer (pointer captured with the kernel parameters), the CUDA graph is replayed, and the start/end of each kernel
+plus the gaps between consecutive kernels are printed.  Development aid, GPU only."""
+import ctypes, os, sys, warnings
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sige_b200 import _cabi
+from sige_b200.engine import DDPMStepEngine, FusedConv
+from sige_b200.masks import downsample_mask
+from sige_b200.workloads.ddpm import DDPMConfig, SIGEDDPMUNet, init_deterministic, synthetic_inputs
+
+dev = torch.device("cuda", 0)
+cfg = DDPMConfig()
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    model = init_deterministic(SIGEDDPMUNet(cfg), seed=0).eval().to(dev).half().to(memory_format=torch.channels_last)
+x0, x1, mask, t = synthetic_inputs(cfg, 0.012, seed=0)
+cl = lambda a: a.to(dev).half().contiguous(memory_format=torch.channels_last)
+with torch.no_grad():
+    model.set_mode("full"); model(cl(x0), t.to(dev))
+    model.set_masks(downsample_mask(mask.to(dev), min_res=8)); model.set_mode("sparse")
+lib = _cabi.lib()
+lib.sige_debug_set_trace.argtypes = [ctypes.c_void_p]
+SLOT = 256 * 16
+buf = torch.zeros(200 * SLOT, dtype=torch.int64, device=dev)
+order = {}
+def hook(fc):
+    i = order.setdefault(id(fc), len(order))
+    lib.sige_debug_set_trace(buf.data_ptr() + i * SLOT * 8)
+FusedConv.trace_hook = hook
+eng = DDPMStepEngine(model, cl(x1), use_graph=True, tc5=True, pdl="--no-pdl" not in sys.argv, branches="--no-branches" not in sys.argv)
+FusedConv.trace_hook = None
+lib.sige_debug_set_trace(None)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for _ in range(3):
+    flush.fill_(1); eng.replay()
+buf.zero_(); flush.fill_(2); torch.cuda.synchronize()
+eng.replay(); torch.cuda.synchronize()
+names = {order[id(f)]: f.name for f in eng.fused if id(f) in order}
+tt = buf.view(200, 256, 16).cpu()
+rows = []
+for i in sorted(names):
+    t_ = tt[i]; t_ = t_[t_[:, 0] > 0]
+    if t_.shape[0] == 0:
+        continue
+    st, en = int(t_[:, 0].min()), int(t_[:, 11][t_[:, 11] > 0].max()) if (t_[:, 11] > 0).any() else int(t_.max())
+    gather_done = float(torch.median(t_[:, 4][t_[:, 4] > 0].float())) if (t_[:, 4] > 0).any() else 0
+    rows.append((st, en, names[i], t_.shape[0], gather_done))
+rows.sort()
+t0 = rows[0][0]
+prev_end = t0
+busy = 0
+for st, en, name, n, gd in rows:
+    print("%-28s ctas %3d start %8.2f dur %6.2f gap-from-prev-end %6.2f" % (name, n, (st - t0) / 1e3, (en - st) / 1e3, (st - prev_end) / 1e3))
+    busy += en - st
+    prev_end = max(prev_end, en)
+print("first start -> last end: %.1f us; sum of kernel durations %.1f us over %d traced launches" % ((prev_end - t0) / 1e3, busy / 1e3, len(rows)))
