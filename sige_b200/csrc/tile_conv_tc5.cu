@@ -89,13 +89,19 @@ template <int BN, int TAPS> struct Cfg {
     static constexpr int SPC = TAPS / TPS;                     // ring steps per 64-channel chunk
     static constexpr int B_TILE_BYTES = BN * 128;              // one (tap, chunk) weight tile
     static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES;
-    static constexpr int NSTB = (BN == 128) ? 4 : (TPS == 3 ? 3 : 8);   // weight ring depth
+    static constexpr int NSTB = (BN == 128) ? 4 : (TPS == 3 ? 2 : 4);   // weight ring depth (48 / 32 / 64 KB in flight per CTA)
+    static constexpr int EPI_PITCH = BN + EPI_PAD;             // floats
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = 2 * A_BUF_BYTES;
-    static constexpr int OFF_BAR = OFF_B + NSTB * B_STAGE_BYTES;
+    // split-K (BN = 64 only): partial-tile rows pushed by the other ranks of the cluster land here — a region that no
+    // mainloop touches, so a fast rank may push while this CTA is still multiplying.  <= 7 remote ranks x 16 rows.
+    static constexpr int OFF_SLOT = OFF_B + NSTB * B_STAGE_BYTES;
+    static constexpr int SLOT_BYTES = (BN == 64) ? 112 * EPI_PITCH * 4 : 0;
+    static constexpr bool kSplitOk = (BN == 64);
+    static constexpr int OFF_BAR = OFF_SLOT + SLOT_BYTES;
     static constexpr int OFF_CONST = OFF_BAR + 256;            // idx[8][2] ints, then bias | aux0 scale,shift | aux1 scale,shift (BN floats each)
     static constexpr int SMEM_BYTES = OFF_CONST + 64 + 5 * BN * 4 + 1024;    // + slack for the 1024-byte alignment
-    static constexpr int EPI_PITCH = BN + EPI_PAD;             // floats
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
     static_assert(128 * EPI_PITCH * 4 <= 2 * A_BUF_BYTES, "epilogue staging must fit in the halo buffers");
 };
 
@@ -265,6 +271,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.ksplit > 1) cg::this_cluster().barrier_arrive();   // every thread; matched by barrier_wait() before the first remote store
     if (tid == 0) SIGE_TRACE(1);
     if (p.pdl) asm volatile("griddepcontrol.launch_dependents;\n" ::);   // the next layer may start prefetching ITS weights
 
@@ -480,10 +487,10 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     };
 
     if (p.ksplit == 1) {
-        // ---- no split-K: TMEM -> registers -> global, one thread per output pixel (its BN channels are one
-        //      contiguous BN*2-byte run in NHWC), no shared-memory staging and no CTA-wide barrier on the way out
-        if (warp >= 2 && warp < 6) {
-            const int quarter = warp & 3;
+        // ---- no split-K: TMEM -> registers -> global.  Two warps per TMEM lane quarter (warp w and w+4 may both touch
+        //      lanes 32*(w%4)..+31) split the BN columns; a thread's share of its pixel is one contiguous run in NHWC.
+        if (warp >= 2) {
+            const int quarter = warp & 3, halfsel = (warp - 2) >> 2;
             const int m = quarter * 32 + lane;
             const long long pixel = pixel_of(m);
             if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -491,7 +498,8 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             tc_fence_after();
             if (tid == 64) SIGE_TRACE(7);
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int cc = 0; cc < BN / 2; cc += 32) {
+                const int c0 = halfsel * (BN / 2) + cc;
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);   // warp-collective: every lane takes part
                 if (pixel >= 0) {
@@ -513,19 +521,31 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         return;
     }
 
-    // ---- split-K: stage the partial tile in shared memory, reduce across the cluster through DSMEM
-    if (warp >= 2 && warp < 6) {
-        // four warps cover the 128 TMEM lanes; warp w may only touch lanes 32*(w%4)..+31
+    // ---- split-K: every CTA PUSHES the rows of its partial tile straight from TMEM into the shared memory of the
+    //      rank that owns them (distributed shared memory stores), one cluster barrier, then each rank sums the ks
+    //      slots it received (local reads, fixed order -> deterministic) and stores.  Slot layout at the owner:
+    //      [source rank][row within the owner's share][EPI_PITCH].  Nobody reads remote memory after the barrier, so
+    //      no exit barrier is needed.
+    cg::cluster_group cluster = cg::this_cluster();
+    const int per = 128 / p.ksplit;
+    cluster.barrier_wait();                // (arrived during setup) every CTA of the cluster is running: remote stores are legal
+    if (warp >= 2) {
+        const int quarter = warp & 3, halfsel = (warp - 2) >> 2;
+        const int m = quarter * 32 + lane;
+        const int owner = m / per, lr = m - owner * per;
+        // own rows: this CTA's halo buffers are free once ITS accumulator is complete; remote rows: the owner's slot region
+        float *rslot = reinterpret_cast<float *>(smem + C::OFF_SLOT);
+        float *slot = owner == kr ? cst + lr * C::EPI_PITCH
+                                  : cluster.map_shared_rank(rslot, owner) + ((kr < owner ? kr : kr - 1) * per + lr) * C::EPI_PITCH;
         mbar_wait(ACC_FULL, 0);
         tc_fence_after();
         if (tid == 64) SIGE_TRACE(7);
-        const int quarter = warp & 3;
-        const int m = quarter * 32 + lane;
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int cc = 0; cc < BN / 2; cc += 32) {
+            const int c0 = halfsel * (BN / 2) + cc;
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
-            float4 *dstv = reinterpret_cast<float4 *>(cst + m * C::EPI_PITCH + c0);
+            float4 *dstv = reinterpret_cast<float4 *>(slot + c0);
 #pragma unroll
             for (int z = 0; z < 8; ++z)
                 dstv[z] = make_float4(__uint_as_float(r[4 * z]), __uint_as_float(r[4 * z + 1]), __uint_as_float(r[4 * z + 2]),
@@ -533,47 +553,31 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
         tc_fence_before();
     }
-    __syncthreads();
-    if (tid == 0) SIGE_TRACE(8);
-    if (warp == 0) tmem_dealloc(tmem_base, BN);
-
     if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();
-    const int per = 128 / p.ksplit;
-    const int m_lo = kr * per, m_hi = m_lo + per;
-    const float *part[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) part[r] = r < p.ksplit ? cluster.map_shared_rank(cst, r) : cst;
-    if (tid == 0) SIGE_TRACE(9);
-    for (int q = tid + m_lo * (BN / 8); q < m_hi * (BN / 8); q += NTHREADS) {
-        const int m = q / (BN / 8), nv = q - m * (BN / 8);
+    cluster.sync();                        // all partial rows have landed in their owners' slots
+    if (tid == 0) { SIGE_TRACE(8); SIGE_TRACE(9); }
+    if (warp == 0) tmem_dealloc(tmem_base, BN);
+    for (int q = tid; q < per * (BN / 8); q += NTHREADS) {
+        const int lr = q / (BN / 8), nv = q - lr * (BN / 8);
         const int n = n0 + nv * 8;
         if (n >= p.Cout) continue;
-        const long long pixel = pixel_of(m);
+        const long long pixel = pixel_of(kr * per + lr);
         if (pixel < 0) continue;
-        float4 c0[8], c1[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {             // all remote loads in flight before the first add
-            if (r < p.ksplit) {
-                const float *cs = part[r] + m * C::EPI_PITCH + nv * 8;
-                c0[r] = *reinterpret_cast<const float4 *>(cs);
-                c1[r] = *reinterpret_cast<const float4 *>(cs + 4);
-            }
-        }
         float v[8];
 #pragma unroll
         for (int z = 0; z < 8; ++z) v[z] = 0.f;
+        const float *rslot = reinterpret_cast<const float *>(smem + C::OFF_SLOT);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < 8; ++r) {       // fixed rank order: bitwise-deterministic sum
             if (r < p.ksplit) {
-                v[0] += c0[r].x; v[1] += c0[r].y; v[2] += c0[r].z; v[3] += c0[r].w; v[4] += c1[r].x; v[5] += c1[r].y; v[6] += c1[r].z; v[7] += c1[r].w;
+                const float *cs = (r == kr ? cst + lr * C::EPI_PITCH : rslot + ((r < kr ? r : r - 1) * per + lr) * C::EPI_PITCH) + nv * 8;
+                const float4 c0 = *reinterpret_cast<const float4 *>(cs), c1 = *reinterpret_cast<const float4 *>(cs + 4);
+                v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
             }
         }
         emit(pixel, n, v);
     }
     if (tid == 0) SIGE_TRACE(10);
-    cluster.sync();   // nobody leaves while a peer still reads its partial tile
     if (tid == 0) SIGE_TRACE(11);
 }
 
@@ -639,10 +643,10 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
         static const int kMaxCtas[9] = {0, 148, 148, 0, 132, 0, 0, 0, 120};
         static int min_taps = getenv("SIGE_TC5_MIN_TAPS") ? atoi(getenv("SIGE_TC5_MIN_TAPS")) : 3;   // tuning knob (taps per K slice)
         int ks = 1;
-        while (ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * C::TPS) / (ks * 2) >= min_taps) ks *= 2;
+        while (C::kSplitOk && ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * C::TPS) / (ks * 2) >= min_taps) ks *= 2;
         p.ksplit = ks;
     }
-    if (p.ksplit > J) p.ksplit = 1;
+    if (p.ksplit > J || !C::kSplitOk) p.ksplit = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ceil_div(p.NT, TILES), p.Cout / BN, p.ksplit);
     cfg.blockDim = dim3(NTHREADS);

@@ -54,4 +54,16 @@ for st, en, name, n, gd in rows:
     print("%-28s ctas %3d start %8.2f dur %6.2f gap-from-prev-end %6.2f" % (name, n, (st - t0) / 1e3, (en - st) / 1e3, (st - prev_end) / 1e3))
     busy += en - st
     prev_end = max(prev_end, en)
+stage_names = ["start", "setup", "idx", "ldg", "store", "mmaA", "mmaEnd", "accRdy", "tmemLd", "clSync", "stored", "end"]
+print("--- in-graph stage medians (us after the kernel's own first CTA start) for selected layers")
+for i in sorted(names):
+    nm = names[i]
+    if not any(k in nm for k in ("down.0.block.1", "mid.block_1", "up.4.block.1", "up.0.block.1", "up.4.attn.1")):
+        continue
+    t_ = tt[i]; t_ = t_[t_[:, 0] > 0]
+    if t_.shape[0] == 0:
+        continue
+    rel = (t_ - t_[:, 0].min()).float(); rel[t_ == 0] = float("nan")
+    med = [float(torch.nanmedian(rel[:, k])) / 1e3 for k in range(12)]
+    print("%-28s " % nm + " ".join("%s %.1f" % (a, b) for a, b in zip(stage_names[1:], med[1:])))
 print("first start -> last end: %.1f us; sum of kernel durations %.1f us over %d traced launches" % ((prev_end - t0) / 1e3, busy / 1e3, len(rows)))
