@@ -200,6 +200,17 @@ typedef struct {
     /* ---- optional extra destinations ---- */
     int n_aux;              /* 0, 1 or 2 */
     sige_conv_aux_t aux[2];
+    /* ---- optional fused 1x1 shortcut (tcgen05 path, 3x3 main conv only) ----
+     * out += conv1x1(src2) + bias2 on the main tiles whose sc_flags byte is non-zero (sc_flags == NULL: all); on the
+     * other tiles `residual` (the CACHED shortcut output) is added instead.  This is the reference's
+     * ScatterWithBlockResidual (sige/cuda/scatter_kernel.cu:46-74,119-146) folded into conv2's launch: the shortcut's
+     * own active tiles are a subset of the main conv's. */
+    int n_src2;             /* 0, 1 or 2 channel-concatenated raw sources (same B/H/W as src) */
+    sige_conv_src_t src2[2];
+    int Cin2;               /* channels of the shortcut input (multiple of 64) */
+    const void *w2_packed;  /* sige_pack_conv_weight of the 1x1 weights */
+    const float *bias2;     /* fp32 [Cout] or NULL */
+    const uint8_t *sc_flags;/* [N] per main tile, or NULL */
 } sige_tile_conv_t;
 
 /* Launch with programmatic dependent launch: the kernel prefetches its weights while the previous kernel

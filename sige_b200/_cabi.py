@@ -67,6 +67,7 @@ class TileConv(Structure):
         ("rC", c_int), ("res_c0", c_int),
         ("ksplit", c_int), ("flags", c_int),
         ("n_aux", c_int), ("aux", ConvAux * 2),
+        ("n_src2", c_int), ("src2", ConvSrc * 2), ("Cin2", c_int), ("w2_packed", c_void_p), ("bias2", c_void_p), ("sc_flags", c_void_p),
     ]
 
 

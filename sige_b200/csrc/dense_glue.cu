@@ -29,13 +29,15 @@ struct InAux {
     int act;
 };
 
+// One thread = 4 horizontally adjacent pixels x 8 output channels: each weight octet read from shared memory is used
+// four times (the weight reads were the bottleneck of the one-pixel version: 54 LDS.128 per pixel), each input value
+// up to three times.  Requires W % 4 == 0.
 template <typename T>
 __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *__restrict__ bias,
                                                       T *__restrict__ out, int B, int H, int W, int Cin, int Cout, int n_aux, InAux a0,
                                                       InAux a1) {
     extern __shared__ float wsm[];   // [Cout/8][pitch] (rows of 9*Cin*8 weights, padded) + bias [Cout]
     const int K = 9 * Cin, OV = Cout / 8;
-    // lanes of a warp hold different channel octets: rows 16 bytes * odd apart keep their 128-bit reads conflict-free
     const int pitch = conv_in_pitch(Cin);
     for (int e = threadIdx.x; e < Cout * K; e += blockDim.x) {
         const int co = e / K, k = e - co * K;              // k = ci*9 + tap in OIHW
@@ -45,53 +47,74 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, c
     float *bsm = wsm + OV * pitch;
     for (int e = threadIdx.x; e < Cout; e += blockDim.x) bsm[e] = bias ? DT<T>::to_f(bias[e]) : 0.f;
     __syncthreads();
-    const int total = B * H * W * OV;      // < 2^31 (checked on the host): 32-bit index math, 64-bit division is slow
+    const int WQ = W / 4;
+    const int total = B * H * WQ * OV;      // < 2^31 (checked on the host)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ov = i % OV;
-        int pix = i / OV;
-        const int ww = pix % W; pix /= W;
-        const int hh = pix % H;
-        const int b = pix / H;
-        float acc[8];
+        int q = i / OV;
+        const int wq = q % WQ; q /= WQ;
+        const int hh = q % H;
+        const int b = q / H;
+        const int w0 = wq * 4;
+        float acc[4][8];
 #pragma unroll
-        for (int z = 0; z < 8; ++z) acc[z] = bsm[ov * 8 + z];
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int z = 0; z < 8; ++z) acc[px][z] = bsm[ov * 8 + z];
         const float *wv = wsm + ov * pitch;
         for (int ky = 0; ky < 3; ++ky) {
             const int y = hh + ky - 1;
             if (y < 0 || y >= H) continue;
-            for (int kx = 0; kx < 3; ++kx) {
-                const int xx = ww + kx - 1;
-                if (xx < 0 || xx >= W) continue;
-                const T *px = x + (((long long)b * H + y) * W + xx) * Cin;
-                const float *wt = wv + (ky * 3 + kx) * Cin * 8;
-                for (int ci = 0; ci < Cin; ++ci) {
-                    const float v = DT<T>::to_f(px[ci]);
+            const T *row = x + ((long long)b * H + y) * W * Cin;
+            for (int ci = 0; ci < Cin; ++ci) {
+                float in[6];                                  // columns w0-1 .. w0+4
 #pragma unroll
-                    for (int z = 0; z < 8; ++z) acc[z] = fmaf(v, wt[ci * 8 + z], acc[z]);
+                for (int c = 0; c < 6; ++c) {
+                    const int xx = w0 - 1 + c;
+                    in[c] = (xx >= 0 && xx < W) ? DT<T>::to_f(row[(long long)xx * Cin + ci]) : 0.f;
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 wa = *reinterpret_cast<const float4 *>(wv + ((ky * 3 + kx) * Cin + ci) * 8);
+                    const float4 wb = *reinterpret_cast<const float4 *>(wv + ((ky * 3 + kx) * Cin + ci) * 8 + 4);
+                    const float wz[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int px = 0; px < 4; ++px)
+#pragma unroll
+                        for (int z = 0; z < 8; ++z) acc[px][z] = fmaf(in[px + kx], wz[z], acc[px][z]);
                 }
             }
         }
-        uint4 o;
-        T *oe = reinterpret_cast<T *>(&o);
+        float sc0[8], sh0[8], sc1[8], sh1[8];
 #pragma unroll
-        for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(acc[z]);
-        *reinterpret_cast<uint4 *>(out + (long long)i * 8) = o;
-        for (int ax = 0; ax < n_aux; ++ax) {   // the consumers' GroupNorm affine + SiLU, applied once here
-            const InAux &A = ax == 0 ? a0 : a1;
-            uint4 oa;
-            T *ae = reinterpret_cast<T *>(&oa);
-            float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (A.scale) {
-                const float4 a = __ldg(reinterpret_cast<const float4 *>(A.scale + ov * 8)), c = __ldg(reinterpret_cast<const float4 *>(A.scale + ov * 8 + 4));
-                sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = c.x; sc[5] = c.y; sc[6] = c.z; sc[7] = c.w;
-            }
-            if (A.shift) {
-                const float4 a = __ldg(reinterpret_cast<const float4 *>(A.shift + ov * 8)), c = __ldg(reinterpret_cast<const float4 *>(A.shift + ov * 8 + 4));
-                sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w; sh[4] = c.x; sh[5] = c.y; sh[6] = c.z; sh[7] = c.w;
-            }
+        for (int z = 0; z < 8; ++z) {
+            sc0[z] = (n_aux > 0 && a0.scale) ? __ldg(a0.scale + ov * 8 + z) : 1.f;
+            sh0[z] = (n_aux > 0 && a0.shift) ? __ldg(a0.shift + ov * 8 + z) : 0.f;
+            sc1[z] = (n_aux > 1 && a1.scale) ? __ldg(a1.scale + ov * 8 + z) : 1.f;
+            sh1[z] = (n_aux > 1 && a1.shift) ? __ldg(a1.shift + ov * 8 + z) : 0.f;
+        }
 #pragma unroll
-            for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(A.act, fmaf(acc[z], sc[z], sh[z])));
-            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + (long long)i * 8) = oa;
+        for (int px = 0; px < 4; ++px) {
+            const long long o8 = ((((long long)b * H + hh) * W + w0 + px) * OV + ov) * 8;
+            uint4 o;
+            T *oe = reinterpret_cast<T *>(&o);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(acc[px][z]);
+            *reinterpret_cast<uint4 *>(out + o8) = o;
+            if (n_aux > 0) {   // the consumers' GroupNorm affine + SiLU, applied once here
+                uint4 oa;
+                T *ae = reinterpret_cast<T *>(&oa);
+#pragma unroll
+                for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(a0.act, fmaf(acc[px][z], sc0[z], sh0[z])));
+                *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(a0.ptr) + o8) = oa;
+            }
+            if (n_aux > 1) {
+                uint4 oa;
+                T *ae = reinterpret_cast<T *>(&oa);
+#pragma unroll
+                for (int z = 0; z < 8; ++z) ae[z] = DT<T>::from_f(activate<true>(a1.act, fmaf(acc[px][z], sc1[z], sh1[z])));
+                *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(a1.ptr) + o8) = oa;
+            }
         }
     }
 }
@@ -282,12 +305,12 @@ extern "C" {
 int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out, int dtype, int B, int H, int W, int Cin, int Cout,
                       int n_aux, const sige_conv_aux_t *aux, sige_stream_t stream) {
     SIGE_REQUIRE(x && w && out, "sige_conv_in_nhwc: null pointer");
-    SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 4 && Cout > 0 && Cout % 8 == 0, "sige_conv_in_nhwc: needs Cin <= 4 and Cout %% 8 == 0");
+    SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && W % 4 == 0 && Cin >= 1 && Cin <= 4 && Cout > 0 && Cout % 8 == 0, "sige_conv_in_nhwc: needs W %% 4 == 0, Cin <= 4 and Cout %% 8 == 0");
     SIGE_REQUIRE(((uintptr_t)out & 15) == 0, "sige_conv_in_nhwc: output not 16-byte aligned");
     const size_t smem = sizeof(float) * ((size_t)(Cout / 8) * conv_in_pitch(Cin) + Cout);
     SIGE_REQUIRE(smem <= 48 * 1024, "sige_conv_in_nhwc: weights do not fit in shared memory");
-    const long long total = (long long)B * H * W * (Cout / 8);
-    SIGE_REQUIRE(total < 2147483647LL, "sige_conv_in_nhwc: tensor too large");
+    const long long total = (long long)B * H * (W / 4) * (Cout / 8);
+    SIGE_REQUIRE(total * 4 < 2147483647LL, "sige_conv_in_nhwc: tensor too large");
     const long long want_blocks = (total + 255) / 256;
     const int grid = (int)(want_blocks < 148LL * 2 ? want_blocks : 148LL * 2);   // persistent: the weight staging is paid once per CTA
     cudaStream_t st = (cudaStream_t)stream;

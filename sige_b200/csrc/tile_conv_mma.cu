@@ -553,6 +553,18 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
         SIGE_REQUIRE(x.act == SIGE_ACT_IDENTITY || x.act == SIGE_ACT_SWISH, "sige_tile_conv: aux %d unknown activation", i);
     }
 
+    SIGE_REQUIRE(a->n_src2 >= 0 && a->n_src2 <= 2, "sige_tile_conv: n_src2 must be 0, 1 or 2");
+    if (a->n_src2 > 0) {
+        int c2 = 0;
+        for (int s2 = 0; s2 < a->n_src2; ++s2) {
+            SIGE_REQUIRE(a->src2[s2].ptr && a->src2[s2].C > 0 && a->src2[s2].C % KC == 0 && ((uintptr_t)a->src2[s2].ptr & 15) == 0, "sige_tile_conv: bad shortcut source %d", s2);
+            c2 += a->src2[s2].C;
+        }
+        SIGE_REQUIRE(c2 == a->Cin2 && a->w2_packed && ((uintptr_t)a->w2_packed & 15) == 0, "sige_tile_conv: shortcut channels/weights mismatch");
+        SIGE_REQUIRE(!a->src_is_stack && !a->dst_is_stack, "sige_tile_conv: the fused shortcut needs full-tensor source and destination");
+        SIGE_REQUIRE((a->flags & SIGE_CONV_TC5) && tc5_supported(a), "sige_tile_conv: the fused shortcut is implemented by the tcgen05 kernel only (3x3 stride-1 on 6x6 tiles, SIGE_CONV_TC5)");
+        SIGE_REQUIRE(a->sc_flags == nullptr || a->residual != nullptr, "sige_tile_conv: sc_flags given without the cached shortcut (residual)");
+    }
     // Blackwell-native path (tcgen05 + TMEM + TMA, tile_conv_tc5.cu) when requested and the geometry fits
     if ((a->flags & SIGE_CONV_TC5) && tc5_supported(a)) return tc5_launch(a, (cudaStream_t)stream);
 

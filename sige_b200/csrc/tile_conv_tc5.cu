@@ -76,6 +76,11 @@ struct Params {
     int rC, res_c0;
     int n_aux;
     AuxDst aux[2];
+    // optional second operand set: out += conv1x1(seg2) on tiles with sc_flags != 0 (the ResNet shortcut), see sige_tile_conv_t
+    Seg seg2[2];
+    int C0_2, Cin2;
+    const float *bias2;
+    const unsigned char *sc_flags;
     int ksplit;
     int pdl;
     int is_bf16;
@@ -99,8 +104,8 @@ template <int BN, int TAPS> struct Cfg {
     static constexpr int SLOT_BYTES = (BN == 64) ? 112 * EPI_PITCH * 4 : 0;
     static constexpr bool kSplitOk = (BN == 64);
     static constexpr int OFF_BAR = OFF_SLOT + SLOT_BYTES;
-    static constexpr int OFF_CONST = OFF_BAR + 256;            // idx[8][2] ints, then bias | aux0 scale,shift | aux1 scale,shift (BN floats each)
-    static constexpr int SMEM_BYTES = OFF_CONST + 64 + 5 * BN * 4 + 1024;    // + slack for the 1024-byte alignment
+    static constexpr int OFF_CONST = OFF_BAR + 256;            // idx[8][2] ints + 8 shortcut flags, then bias | aux0 scale,shift | aux1 scale,shift | bias2
+    static constexpr int SMEM_BYTES = OFF_CONST + 80 + 6 * BN * 4 + 1024;    // + slack for the 1024-byte alignment
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
     static_assert(128 * EPI_PITCH * 4 <= 2 * A_BUF_BYTES, "epilogue staging must fit in the halo buffers");
 };
@@ -207,7 +212,8 @@ __device__ __forceinline__ long long gtime() {
 
 template <typename T, int BN, int TAPS>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap) {
+tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap,
+                     const __grid_constant__ CUtensorMap wmap2) {
     using C = Cfg<BN, TAPS>;
     constexpr int NSTB = C::NSTB, TPS = C::TPS, SPC = C::SPC;
     constexpr int R = (TAPS == 9) ? 6 : 4;            // halo tile extent
@@ -232,12 +238,17 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     const int n0 = blockIdx.y * BN;
     const int ntile = min(TILES, p.NT - tile0);
     const int NC = p.Cin / KC;
-    const int J = NC * SPC;                        // ring steps of the whole K loop (a step = TPS taps of one chunk)
+    const int J_main = NC * SPC;                   // ring steps of the main conv (a step = TPS taps of one 64-channel chunk)
+    const int NC2 = (TAPS == 9) ? p.Cin2 / KC : 0;  // fused 1x1 shortcut: one step (the centre tap) per chunk of ITS input
+    const int J = J_main + NC2;
     const int kr = blockIdx.z;
     const int j_begin = (int)(((long long)J * kr) / p.ksplit), j_end = (int)(((long long)J * (kr + 1)) / p.ksplit);
-    const int c_first = j_begin / SPC, c_last = (j_end - 1) / SPC;
+    // halo-buffer chunks in processing order: main chunks 0..NC-1, then shortcut chunks NC..NC+NC2-1
+    auto chunk_of = [&](int j) { return j < J_main ? j / SPC : NC + (j - J_main); };
+    const int c_first = chunk_of(j_begin), c_last = chunk_of(j_end - 1);
     int32_t *s_idx = reinterpret_cast<int32_t *>(smem + C::OFF_CONST);          // [TILES][2] tile origins of this CTA
-    float *s_const = reinterpret_cast<float *>(smem + C::OFF_CONST + 64);       // bias | aux0 scale | aux0 shift | aux1 scale | aux1 shift
+    unsigned char *s_flags = smem + C::OFF_CONST + 64;                          // [TILES] 1 = evaluate the fused shortcut on this tile
+    float *s_const = reinterpret_cast<float *>(smem + C::OFF_CONST + 80);       // bias | aux0 scale | aux0 shift | aux1 scale | aux1 shift | bias2
 
     if (tid == 0) SIGE_TRACE(0);
     // ---------------- one-time setup ----------------
@@ -258,12 +269,15 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             int v = 0;
             if (t < p.NT && p.idx) v = __ldg(p.idx + 2 * (t % p.N) + (lane & 1));
             s_idx[lane] = v;
+        } else if (lane < 2 * TILES + TILES) {
+            const int tl = lane - 2 * TILES, t = tile0 + tl;
+            s_flags[tl] = (p.Cin2 > 0 && t < p.NT && (p.sc_flags == nullptr || __ldg(p.sc_flags + (t % p.N)))) ? 1 : 0;
         }
-    } else if (warp >= 3 && warp < 8) {
+    } else if (warp >= 3 && warp < 9) {
         // per-channel epilogue constants of this CTA's BN output channels
-        const int which = warp - 3;                         // 0 bias, 1/2 aux0 scale/shift, 3/4 aux1 scale/shift
-        const float *src = which == 0 ? p.bias : (which == 1 ? p.aux[0].scale : which == 2 ? p.aux[0].shift : which == 3 ? p.aux[1].scale : p.aux[1].shift);
-        const bool on = which == 0 || (which <= 2 ? p.n_aux > 0 : p.n_aux > 1);
+        const int which = warp - 3;                         // 0 bias, 1/2 aux0 scale/shift, 3/4 aux1 scale/shift, 5 bias2
+        const float *src = which == 0 ? p.bias : (which == 1 ? p.aux[0].scale : which == 2 ? p.aux[0].shift : which == 3 ? p.aux[1].scale : which == 4 ? p.aux[1].shift : p.bias2);
+        const bool on = which == 0 || which == 5 || (which <= 2 ? p.n_aux > 0 : p.n_aux > 1);
         const float dflt = (which == 1 || which == 3) ? 1.f : 0.f;
         for (int e = lane; e < BN; e += 32) s_const[which * BN + e] = (on && src && n0 + e < p.Cout) ? __ldg(src + n0 + e) : dflt;
     }
@@ -281,12 +295,17 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             for (int j = j_begin; j < j_end; ++j) {
                 const int it = j - j_begin, s = it % NSTB, k = it / NSTB;
                 mbar_wait(B_EMPTY(s), (k & 1) ^ 1);
-                mbar_expect_tx(B_FULL(s), C::B_STAGE_BYTES);
-                const int c = j / SPC, tap0 = (j - c * SPC) * TPS;
+                if (j < J_main) {
+                    mbar_expect_tx(B_FULL(s), C::B_STAGE_BYTES);
+                    const int c = j / SPC, tap0 = (j - c * SPC) * TPS;
 #pragma unroll
-                for (int t = 0; t < TPS; ++t)
-                    tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES + t * C::B_TILE_BYTES, &wmap, 0, ((tap0 + t) * NC + c) * p.Cout + n0,
-                                B_FULL(s));
+                    for (int t = 0; t < TPS; ++t)
+                        tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES + t * C::B_TILE_BYTES, &wmap, 0, ((tap0 + t) * NC + c) * p.Cout + n0,
+                                    B_FULL(s));
+                } else {                                               // shortcut weights [Cin2/64][Cout][64]
+                    mbar_expect_tx(B_FULL(s), C::B_TILE_BYTES);
+                    tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES, &wmap2, 0, (j - J_main) * p.Cout + n0, B_FULL(s));
+                }
             }
         }
         __syncwarp();
@@ -296,8 +315,8 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             const uint32_t idesc = make_idesc(BN, p.is_bf16);
             int ab = 0, ause = 0;             // halo buffer index and how many times it has been used
             for (int j = j_begin; j < j_end; ++j) {
-                const int c = j / SPC, st = j - c * SPC;
-                (void)c;
+                const bool is_sc = j >= J_main;
+                const int st = is_sc ? 0 : j % SPC;
                 if (j == j_begin || st == 0) {                        // a new chunk starts: wait for its halo buffer
                     mbar_wait(A_FULL(ab), (ause >> 1) & 1);
                     tc_fence_after();
@@ -308,7 +327,8 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 tc_fence_after();
 #pragma unroll
                 for (int t = 0; t < TPS; ++t) {
-                    const int tap = st * TPS + t;
+                    if (is_sc && t > 0) break;                        // the shortcut is a single tap: the centre of the 3x3 frame
+                    const int tap = is_sc ? 4 : st * TPS + t;
                     const int ky = (TAPS == 9) ? tap / 3 : 0, kx = (TAPS == 9) ? tap - 3 * ky : 0;
                     const uint32_t a_addr = sbase + C::OFF_A + ab * A_BUF_BYTES + kx * A_COPY_BYTES + ky * (32 * 128);
                     const uint32_t b_addr = sbase + C::OFF_B + s * C::B_STAGE_BYTES + t * C::B_TILE_BYTES;
@@ -318,7 +338,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                                  (j > j_begin || t > 0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(B_EMPTY(s));                              // weight stage free once these MMAs retire
-                if (st == SPC - 1 || j == j_end - 1) {                // chunk done: halo buffer free
+                if (is_sc || st == SPC - 1 || j == j_end - 1) {       // chunk done: halo buffer free
                     umma_commit(A_EMPTY(ab));
                     ab ^= 1;
                     ++ause;
@@ -421,17 +441,57 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 }
             }
         };
+        // fused shortcut chunks: only the 4x4 centre of each halo tile is needed (tap (1,1)), from the RAW block input,
+        // into copy kx = 1 at rows y*32 + tile*4 + (x-1); tiles whose shortcut is not active contribute zeros
+        constexpr int LOADS2 = (TILES * 16 * 8 + NPROD - 1) / NPROD;
+        auto issue2 = [&](int c2) {
+            const int cbase = c2 * KC;
+            const int sg = cbase >= p.C0_2 ? 1 : 0;
+            const Seg &seg = p.seg2[sg];
+            const int cl = cbase - (sg ? p.C0_2 : 0);
+            const int Hs = p.H >> seg.up, Ws = p.W >> seg.up;
+#pragma unroll
+            for (int k = 0; k < LOADS2; ++k) {
+                const int q = ptid + k * NPROD;
+                regs[k] = make_uint4(0, 0, 0, 0);
+                const int pix = q >> 3, u = q & 7;
+                const int tl = pix >> 4, rem = pix & 15;
+                const int y = 1 + (rem >> 2), xx = 1 + (rem & 3);
+                const int t = tile0 + tl;
+                if (q < TILES * 16 * 8 && t < p.NT && s_flags[tl]) {
+                    int b = 0;
+                    if (p.NT != p.N) b = t / p.N;
+                    const int hh = y + s_idx[2 * tl], ww = xx + s_idx[2 * tl + 1];
+                    if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) {
+                        const T *src = reinterpret_cast<const T *>(seg.ptr) + (((long long)b * Hs + (hh >> seg.up)) * Ws + (ww >> seg.up)) * seg.C + cl + u * 8;
+                        regs[k] = __ldg(reinterpret_cast<const uint4 *>(src));
+                    }
+                }
+            }
+        };
+        auto store2 = [&](unsigned char *abuf) {
+#pragma unroll
+            for (int k = 0; k < LOADS2; ++k) {
+                const int q = ptid + k * NPROD;
+                if (q >= TILES * 16 * 8) continue;
+                const int pix = q >> 3, u = q & 7;
+                const int tl = pix >> 4, rem = pix & 15;
+                const int row = (1 + (rem >> 2)) * 32 + tl * 4 + (rem & 3);
+                *reinterpret_cast<uint4 *>(abuf + A_COPY_BYTES + row * 128 + ((u ^ (row & 7)) << 4)) = regs[k];
+            }
+        };
+        auto issue_any = [&](int c) { if (c < NC) issue(c); else issue2(c - NC); };
         if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");   // activations of the previous layer are complete
-        issue(c_first);
+        issue_any(c_first);
         int ab = 0, ause = 0;
         for (int c = c_first; c <= c_last; ++c) {
             mbar_wait(A_EMPTY(ab), ((ause >> 1) & 1) ^ 1);            // the MMAs that read this buffer have retired
             if (ptid == 0 && c == c_first) SIGE_TRACE(3);
-            store(c, smem + C::OFF_A + ab * A_BUF_BYTES);
+            if (c < NC) store(c, smem + C::OFF_A + ab * A_BUF_BYTES); else store2(smem + C::OFF_A + ab * A_BUF_BYTES);
             if (ptid == 0 && c == c_first) SIGE_TRACE(4);
             fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core
             mbar_arrive(A_FULL(ab));
-            if (c < c_last) issue(c + 1);
+            if (c < c_last) issue_any(c + 1);
             ab ^= 1;
             ++ause;
         }
@@ -440,13 +500,17 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     // ---------------- epilogue ----------------
     float *cst = reinterpret_cast<float *>(smem + C::OFF_A);
     // v[8] (fp32 conv result of 8 consecutive channels starting at n) -> +bias, +residual -> dst and aux destinations
-    auto emit = [&](long long pixel, int n, float (&v)[8]) {
+    auto emit = [&](long long pixel, int tl, int n, float (&v)[8]) {
         const int nl = n - n0;
         {
             const float4 b0 = *reinterpret_cast<const float4 *>(s_const + nl), b1 = *reinterpret_cast<const float4 *>(s_const + nl + 4);
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
-        if (p.residual) {
+        const bool fresh_sc = s_flags[tl] != 0;       // the fused 1x1 shortcut was evaluated on this tile
+        if (fresh_sc) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(s_const + 5 * BN + nl), b1 = *reinterpret_cast<const float4 *>(s_const + 5 * BN + nl + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        } else if (p.residual) {                       // plain residual, or the CACHED shortcut where the fused one is inactive
             const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(p.residual) + pixel * p.rC + p.res_c0 + n));
             const T *re = reinterpret_cast<const T *>(&rr);
 #pragma unroll
@@ -469,6 +533,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + pixel * A.C + A.c0 + n) = oa;
         }
     };
+    auto tl_of = [&](int m) { return TAPS == 9 ? (m >> 2) & 7 : m >> 4; };
     // GEMM row m -> destination pixel index, or -1 (row of a tile that does not exist / outside the image)
     auto pixel_of = [&](int m) -> long long {
         int tl, oy, ox;
@@ -508,7 +573,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                         float v[8];
 #pragma unroll
                         for (int z = 0; z < 8; ++z) v[z] = __uint_as_float(r[8 * g + z]);
-                        if (n0 + c0 + 8 * g < p.Cout) emit(pixel, n0 + c0 + 8 * g, v);
+                        if (n0 + c0 + 8 * g < p.Cout) emit(pixel, tl_of(m), n0 + c0 + 8 * g, v);
                     }
                 }
             }
@@ -575,7 +640,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
             }
         }
-        emit(pixel, n, v);
+        emit(pixel, tl_of(kr * per + lr), n, v);
     }
     if (tid == 0) SIGE_TRACE(10);
     if (tid == 0) SIGE_TRACE(11);
@@ -602,7 +667,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <typename T, int BN, int TAPS> static int launch(Params &p, const void *w_packed, cudaStream_t st) {
+template <typename T, int BN, int TAPS> static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaStream_t st) {
     using C = Cfg<BN, TAPS>;
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
@@ -622,6 +687,16 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
         set_error("sige_tile_conv(tcgen05): cuTensorMapEncodeTiled failed with %d", (int)r);
         return 2;
     }
+    CUtensorMap wmap2 = wmap;
+    if (p.Cin2 > 0) {
+        const cuuint64_t gdim2[2] = {(cuuint64_t)KC, (cuuint64_t)(p.Cin2 / KC) * p.Cout};
+        r = enc(&wmap2, p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w2_packed), gdim2, gstr, box,
+                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("sige_tile_conv(tcgen05): cuTensorMapEncodeTiled (shortcut weights) failed with %d", (int)r);
+            return 2;
+        }
+    }
     auto kern = tile_conv_tc5_kernel<T, BN, TAPS>;
     static int attr_dev = -1;
     int dev = 0;
@@ -634,7 +709,7 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
         }
         attr_dev = dev;
     }
-    const int J = (p.Cin / KC) * C::SPC;        // ring steps
+    const int J = (p.Cin / KC) * C::SPC + (TAPS == 9 ? p.Cin2 / KC : 0);        // ring steps
     const long long base = (long long)ceil_div(p.NT, TILES) * (p.Cout / BN);
     if (p.ksplit <= 0) {
         // one CTA per SM (214 KB smem): co-resident CTAs are 148 / 148 / 132 / 120 for cluster sizes 1 / 2 / 4 / 8
@@ -668,7 +743,7 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
     }
     cfg.attrs = attrs;
     cfg.numAttrs = na;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, wmap);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, wmap, wmap2);
     if (e != cudaSuccess) {
         set_error("sige_tile_conv(tcgen05): launch failed (grid %d x %d x %d): %s", cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z,
                   cudaGetErrorString(e));
@@ -687,6 +762,7 @@ extern "C" void sige_debug_set_trace(void *buf) { g_trace = reinterpret_cast<lon
 bool tc5_supported(const sige_tile_conv_t *a) {
     const bool g3 = a->kH == 3 && a->kW == 3 && a->stride == 1 && a->R == 6 && a->S == 6;
     const bool g1 = a->kH == 1 && a->kW == 1 && a->stride == 1 && a->R == 4 && a->S == 4;
+    if (a->n_src2 > 0 && !g3) return false;
     return (g3 || g1) && a->Cout % 64 == 0 && a->Cin % 64 == 0 && (a->ksplit == 0 || a->ksplit == 1 || a->ksplit == 2 || a->ksplit == 4 || a->ksplit == 8);
 }
 
@@ -713,6 +789,12 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.residual = a->residual; p.rC = a->rC; p.res_c0 = a->res_c0;
     p.n_aux = a->n_aux;
     for (int i = 0; i < a->n_aux; ++i) p.aux[i] = tc5::AuxDst{a->aux[i].ptr, a->aux[i].C, a->aux[i].c0, a->aux[i].scale, a->aux[i].shift, a->aux[i].act};
+    p.seg2[0] = a->n_src2 > 0 ? tc5::Seg{a->src2[0].ptr, a->src2[0].C, a->src2[0].up} : p.seg[0];
+    p.seg2[1] = a->n_src2 == 2 ? tc5::Seg{a->src2[1].ptr, a->src2[1].C, a->src2[1].up} : p.seg2[0];
+    p.C0_2 = a->n_src2 > 0 ? a->src2[0].C : 0;
+    p.Cin2 = a->n_src2 > 0 ? a->Cin2 : 0;
+    p.bias2 = a->n_src2 > 0 ? a->bias2 : nullptr;
+    p.sc_flags = a->n_src2 > 0 ? a->sc_flags : nullptr;
     p.ksplit = a->ksplit;
     p.pdl = (a->flags & SIGE_CONV_PDL) ? 1 : 0;
     p.is_bf16 = a->dtype == SIGE_BF16;
@@ -722,8 +804,8 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     const bool wide = (a->Cout % 128 == 0) && (m_blocks * (a->Cout / 128) >= 148);
     const bool three = p.taps == 9;
 #define SIGE_TC5(T)                                                                              \
-    (wide ? (three ? tc5::launch<T, 128, 9>(p, a->w_packed, st) : tc5::launch<T, 128, 1>(p, a->w_packed, st)) \
-          : (three ? tc5::launch<T, 64, 9>(p, a->w_packed, st) : tc5::launch<T, 64, 1>(p, a->w_packed, st)))
+    (wide ? (three ? tc5::launch<T, 128, 9>(p, a->w_packed, a->w2_packed, st) : tc5::launch<T, 128, 1>(p, a->w_packed, a->w2_packed, st)) \
+          : (three ? tc5::launch<T, 64, 9>(p, a->w_packed, a->w2_packed, st) : tc5::launch<T, 64, 1>(p, a->w_packed, a->w2_packed, st)))
     if (a->dtype == SIGE_F16) return SIGE_TC5(__half);
     return SIGE_TC5(__nv_bfloat16);
 #undef SIGE_TC5

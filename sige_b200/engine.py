@@ -115,7 +115,7 @@ class ConvInRec:
 
 class DDPMStepEngine:
     def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True, pdl: bool = False, ksplit: int = 0,
-                 tc5: bool = False, producer_preop: bool = True, branches: bool = True):
+                 tc5: bool = False, producer_preop: bool = True, branches: bool = True, fuse_shortcut: bool = True):
         if model.mode != "sparse":
             raise RuntimeError("DDPMStepEngine: run the dense pass, set_masks() and set_mode('sparse') first")
         p = next(model.parameters())
@@ -125,6 +125,7 @@ class DDPMStepEngine:
         self.x = x_static
         self.pdl, self.ksplit, self.tc5, self.producer_preop, self.branches = pdl, ksplit, tc5, producer_preop, branches
         self.side_stream = torch.cuda.Stream(device=p.device)
+        self.fuse_shortcut = fuse_shortcut
         assert x_static.is_cuda and x_static.dtype == self.dtype and x_static.is_contiguous(memory_format=torch.channels_last)
         self.steps: List = []          # callables taking the stream handle
         self.fused: List[FusedConv] = []
@@ -205,7 +206,7 @@ class DDPMStepEngine:
         return ops.pack_conv_weight(w.contiguous(), self.dtype), (None if b is None else b.contiguous())
 
     def conv(self, name: str, srcs: Sequence[Src], hw: Tuple[int, int], idx: torch.Tensor, block: int, conv, stride: int, off: int,
-             dst: Buf, residual: Optional[Buf] = None, packed=None, side: bool = False) -> Optional[FusedConv]:
+             dst: Buf, residual: Optional[Buf] = None, packed=None, side: bool = False, shortcut=None) -> Optional[FusedConv]:
         """Emit one fused gather->conv->scatter launch.  Each source is (buffer, upsample flag, affine); an affine
         source is read from the pre-transformed view its producer maintains, else the gather applies the pre-op."""
         n = int(idx.shape[0])
@@ -263,11 +264,30 @@ class DDPMStepEngine:
         d.ksplit = self.ksplit
         d.flags = _cabi_flags(self.pdl, self.tc5)
         d.n_aux = 0
+        sc_keep = None
+        if shortcut is not None:    # fused 1x1 shortcut: (raw source tensors, packed weights, fp32 bias, per-tile flags or None)
+            sc_tensors, sc_w, sc_b, sc_flags = shortcut
+            d.n_src2 = len(sc_tensors)
+            c2 = 0
+            for i, t in enumerate(sc_tensors):
+                assert t.is_contiguous(memory_format=torch.channels_last) and tuple(t.shape[2:]) == tuple(hw)
+                d.src2[i].ptr, d.src2[i].C, d.src2[i].up = t.data_ptr(), t.shape[1], 0
+                c2 += t.shape[1]
+            d.Cin2 = c2
+            d.w2_packed = sc_w.data_ptr()
+            d.bias2 = None if sc_b is None else sc_b.data_ptr()
+            d.sc_flags = None if sc_flags is None else sc_flags.data_ptr()
+            sc_keep = (sc_tensors, sc_w, sc_b, sc_flags)
+        else:
+            d.n_src2 = 0
         ro = (block - k) // stride + 1
         out_elems = n * cout * ro * ro
         nbytes = 2 * (n * cin * block * block + taps * cout * cin + out_elems * ((1 if dst.raw is not None else 0) + (1 if residual is not None else 0)))
         flops = 2 * n * ro * ro * cout * cin * taps
-        fc = FusedConv(d, [idx, sc, sh, wp, b32, dst, residual, tensors], name, nbytes, flops, n, out_elems)
+        if shortcut is not None:
+            nbytes += 2 * (n * d.Cin2 * 16 + cout * d.Cin2)
+            flops += 2 * n * ro * ro * cout * d.Cin2
+        fc = FusedConv(d, [idx, sc, sh, wp, b32, dst, residual, tensors, sc_keep], name, nbytes, flops, n, out_elems)
         dst.producers.append(fc)
         self.fused.append(fc)
         self.steps.append(("side" if side else "main", fc.launch))
@@ -296,7 +316,24 @@ class DDPMStepEngine:
             c = buf.shape[0]
             segs.append((buf, up, (s1[c0:c0 + c], b1[c0:c0 + c], "swish")))
             c0 += c
-        if blk.in_channels != blk.out_channels:
+        fuse_sc = (blk.in_channels != blk.out_channels and self.fuse_shortcut and self.tc5 and self.producer_preop and bs == 6
+                   and all(b.raw is not None and up == 0 for (b, up) in ins))
+        shortcut = None
+        if fuse_sc:
+            # the 1x1 shortcut rides in conv2's launch as extra K chunks (reference ScatterWithBlockResidual): fresh on the
+            # main tiles where the shortcut's own tile is active, the cached shortcut output elsewhere
+            w2, b2 = self._pack(blk.nin_shortcut)
+            if blk.shortcut_sparse:
+                sg = blk.shortcut_gather
+                skip = self.cached(blk.scatter.original_residuals[cid])
+                width = 1 << 16
+                main_key = (idx[:, 0].long() + off) * width + (idx[:, 1].long() + off)        # output-tile origin of each main tile
+                sc_key = (sg.active_indices[:, 0].long() + sg.offset[0]) * width + (sg.active_indices[:, 1].long() + sg.offset[1])
+                flags = torch.isin(main_key, sc_key).to(torch.uint8).contiguous()
+            else:
+                skip, flags = None, None
+            shortcut = ([b.raw for (b, _) in ins], w2, b2, flags)
+        elif blk.in_channels != blk.out_channels:
             if blk.shortcut_sparse:
                 sg = blk.shortcut_gather
                 sidx, sbs, soff = sg.active_indices, sg.block_size[0], sg.offset[0]
@@ -316,7 +353,7 @@ class DDPMStepEngine:
         if joined:
             self.steps.append(("join", None))
         self.conv(name + ".conv2", [(t1, 0, (blk.scale2s[cid].reshape(-1), blk.shift2s[cid].reshape(-1), "swish"))], hw, idx, bs, blk.conv2, 1,
-                  off, t2, residual=skip)
+                  off, t2, residual=skip, shortcut=shortcut)
         return t2
 
     def _attn(self, name: str, blk: AttnBlock, x: Buf, hw: Tuple[int, int]) -> Buf:

@@ -28,9 +28,9 @@ def _prepared(cfg, ratio, dtype):
     return model, cl(x1), t.to(DEV)
 
 
-@pytest.mark.parametrize("tc5,producer_preop,pdl,branches", [(False, False, False, True), (False, True, False, False), (True, True, False, True), (True, True, True, True), (True, True, True, False)])
+@pytest.mark.parametrize("tc5,producer_preop,pdl,branches,fuse", [(False, False, False, True, False), (False, True, False, False, False), (True, True, False, True, False), (True, True, True, True, True), (True, True, True, False, True), (True, True, False, True, True)])
 @pytest.mark.parametrize("tag", ["ddpm_small", "ddpm256"])
-def test_engine_matches_modules_and_reference(tag, tc5, producer_preop, pdl, branches):
+def test_engine_matches_modules_and_reference(tag, tc5, producer_preop, pdl, branches, fuse):
     from sige_b200.engine import DDPMStepEngine
     from sige_b200.parallel import cache_tensors
     from sige_b200.workloads.ddpm import DDPMConfig
@@ -42,7 +42,7 @@ def test_engine_matches_modules_and_reference(tag, tc5, producer_preop, pdl, bra
     pristine = [(n, v.clone()) for n, v in cache_tensors(model)]
     with torch.no_grad():
         via_modules = model(x1, t).float()
-    eng = DDPMStepEngine(model, x1.clone(memory_format=torch.channels_last), tc5=tc5, producer_preop=producer_preop, pdl=pdl, branches=branches)
+    eng = DDPMStepEngine(model, x1.clone(memory_format=torch.channels_last), tc5=tc5, producer_preop=producer_preop, pdl=pdl, branches=branches, fuse_shortcut=fuse)
     out1 = eng.replay().clone()
     out2 = eng.replay().clone()
     torch.cuda.synchronize()
