@@ -60,3 +60,20 @@ def test_engine_matches_modules_and_reference(tag, tc5, producer_preop, pdl, bra
           (tag, e_mod, e_ref, m_ref, len(eng.fused)))
     assert e_mod <= 2e-2 and e_ref <= 2e-2
     assert eng.launches_per_step >= len(eng.fused) > 0
+
+
+@pytest.mark.parametrize("ratio", [0.05, 0.3])
+def test_engine_matches_modules_at_larger_edits(ratio):
+    """Edit-ratio sweep of BASELINE.json configs[4]: more tiles exercise the wide-grid heuristics (BN, split-K off)."""
+    from sige_b200.engine import DDPMStepEngine
+    from sige_b200.workloads.ddpm import DDPMConfig
+
+    cfg = DDPMConfig()
+    model, x1, t = _prepared(cfg, ratio, torch.float16)
+    with torch.no_grad():
+        via_modules = model(x1, t).float()
+    eng = DDPMStepEngine(model, x1.clone(memory_format=torch.channels_last), tc5=True, pdl=True)
+    out = eng.replay().float()
+    torch.cuda.synchronize()
+    scale = float(via_modules.abs().max())
+    assert float((out - via_modules).abs().max()) / scale <= 2e-2
