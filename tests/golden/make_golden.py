@@ -19,6 +19,7 @@ committed fixtures:
     example_golden.npz    reference example.py flow (16->32 ch 3x3, 256x256, assets/mask.npy)
     ddpm_small_golden.npz DDPM U-Net miniature (64x64): full-pass and sparse-pass outputs
     ddpm256_golden.npz    DDPM 256x256 @1.2 % edit: sparse-pass output + tile counts
+    ddpm256_r30_golden.npz  same at a 30 % edit (1296 tiles at 256x256)
 """
 from __future__ import annotations
 
@@ -227,6 +228,7 @@ def main():
 
     run_ddpm(DDPMConfig.small(), 0.05, "ddpm_small", keep_full=True)
     run_ddpm(DDPMConfig(), 0.012, "ddpm256", keep_full=False)
+    run_ddpm(DDPMConfig(), 0.30, "ddpm256_r30", keep_full=False)      # BASELINE.json configs[4]: the large end of the edit sweep
 
 
 if __name__ == "__main__":

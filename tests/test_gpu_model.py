@@ -125,6 +125,18 @@ def test_ddpm256_sparse_step_fp32_matches_reference():
     assert err <= 1e-4, err
 
 
+def test_ddpm256_30pct_edit_fp32_matches_reference():
+    """Large end of the edit sweep (1296 tiles at 256x256) in exact fp32 arithmetic vs the reference's output."""
+    from sige_b200.workloads.ddpm import DDPMConfig
+
+    G = golden("ddpm256_r30_golden.npz")
+    cfg = DDPMConfig()
+    out = _sparse_step(_ddpm(cfg, torch.float32, False), cfg, float(G["ratio"][0]), torch.float32, False)
+    ref = G["sparse_out"]
+    err = float(np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max())
+    assert err <= 2e-4, err
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-2), (torch.bfloat16, 1e-1)])
 def test_ddpm256_sparse_step_half_channels_last(dtype, tol):
     """fp16/bf16 storage through ~60 stacked layers: per-layer error is <= 1e-3 (test_gpu_conv.py);
