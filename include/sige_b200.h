@@ -250,6 +250,14 @@ int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, i
 int sige_conv_out_nhwc(const void *x, const float *scale, const float *shift, int act, const void *w,
                        const void *bias, void *out, int dtype, int B, int H, int W, int C, int Cout,
                        sige_stream_t stream);
+/* Dense single-head attention core of the DDPM AttnBlock (reference diffusion/models/ddpm/sige_fused_unet.py:196-212,
+ * the torch bmm / softmax / bmm between the qkv and proj_out 1x1 convolutions) on NHWC tokens:
+ *   qkv [B][N][3C] = per pixel [q | k | v], q ALREADY multiplied by C^-0.5;  out [B][N][C] = softmax(q k^T) v.
+ * N in {64, 128, 256} tokens, C in {256, 512}, f16 / bf16 (sige_attention_tokens_supported() tells).
+ * flags: SIGE_CONV_PDL = programmatic dependent launch, as for sige_tile_conv. */
+int sige_attention_tokens_supported(int N, int C, int dtype);
+int sige_attention_tokens(const void *qkv, void *out, int B, int N, int C, int dtype, int flags,
+                          sige_stream_t stream);
 
 #ifdef __cplusplus
 }

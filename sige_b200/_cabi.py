@@ -95,6 +95,8 @@ PROTOTYPES = {
     "sige_group_norm_fold_workspace": (_I, [_I, _I]),
     "sige_group_norm_fold": (_I, [_P, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P, _P, _I, _P]),
     "sige_conv_out_nhwc": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "sige_attention_tokens_supported": (_I, [_I, _I, _I]),
+    "sige_attention_tokens": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -115,7 +115,8 @@ class ConvInRec:
 
 class DDPMStepEngine:
     def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True, pdl: bool = False, ksplit: int = 0,
-                 tc5: bool = False, producer_preop: bool = True, branches: bool = True, fuse_shortcut: bool = True):
+                 tc5: bool = False, producer_preop: bool = True, branches: bool = True, fuse_shortcut: bool = True,
+                 fused_attention: bool = True):
         if model.mode != "sparse":
             raise RuntimeError("DDPMStepEngine: run the dense pass, set_masks() and set_mode('sparse') first")
         p = next(model.parameters())
@@ -126,6 +127,7 @@ class DDPMStepEngine:
         self.pdl, self.ksplit, self.tc5, self.producer_preop, self.branches = pdl, ksplit, tc5, producer_preop, branches
         self.side_stream = torch.cuda.Stream(device=p.device)
         self.fuse_shortcut = fuse_shortcut
+        self.fused_attention = fused_attention
         assert x_static.is_cuda and x_static.dtype == self.dtype and x_static.is_contiguous(memory_format=torch.channels_last)
         self.steps: List = []          # callables taking the stream handle
         self.fused: List[FusedConv] = []
@@ -375,9 +377,16 @@ class DDPMStepEngine:
         q, k, v = tok[:, :c], tok[:, c:2 * c], tok[:, 2 * c:]
         o_tok = att_out.raw.permute(0, 2, 3, 1).reshape(h * w, c)
 
-        def attention(_stream):
-            att = torch.softmax(torch.matmul(q, k.t()), dim=-1)
-            torch.matmul(att, v, out=o_tok)
+        if self.fused_attention and ops.attention_tokens_supported(h * w, c, self.dtype):
+            tok3, o3 = tok.unsqueeze(0), o_tok.unsqueeze(0)
+            att_flags = _cabi_flags(self.pdl, False)
+
+            def attention(_stream):
+                ops.attention_tokens(tok3, out=o3, flags=att_flags)
+        else:
+            def attention(_stream):
+                att = torch.softmax(torch.matmul(q, k.t()), dim=-1)
+                torch.matmul(att, v, out=o_tok)
 
         self.steps.append(("main", attention))
         out = self.fresh(c, h, w)

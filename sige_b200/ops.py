@@ -460,3 +460,25 @@ def conv_out_nhwc(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optiona
                                                   H, W, C, Cout, _stream(x)), "sige_conv_out_nhwc")
     _bump()
     return out
+
+
+def attention_tokens_supported(n_tokens: int, channels: int, dtype: torch.dtype) -> bool:
+    code = {torch.float16: _cabi.F16, torch.bfloat16: _cabi.BF16}.get(dtype)
+    return code is not None and bool(_cabi.lib().sige_attention_tokens_supported(int(n_tokens), int(channels), code))
+
+
+def attention_tokens(qkv: torch.Tensor, out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+    """softmax(q k^T) v on tokens: qkv [B, N, 3C] contiguous = per token [q | k | v] with q pre-scaled by C^-0.5
+    (reference sige_fused_unet.py:196-212); returns [B, N, C]."""
+    _require_cuda(qkv, out)
+    assert qkv.dim() == 3 and qkv.is_contiguous() and qkv.shape[2] % 3 == 0
+    B, N, C3 = qkv.shape
+    C = C3 // 3
+    if out is None:
+        out = torch.empty((B, N, C), dtype=qkv.dtype, device=qkv.device)
+    assert out.is_contiguous() and out.shape == (B, N, C) and out.dtype == qkv.dtype
+    with torch.cuda.device(qkv.device):
+        _cabi.check(_cabi.lib().sige_attention_tokens(qkv.data_ptr(), out.data_ptr(), B, N, C, _dt(qkv), int(flags), _stream(qkv)),
+                    "sige_attention_tokens")
+    _bump()
+    return out

@@ -48,3 +48,36 @@ def test_group_norm_fold_and_conv_out(dtype, tol):
         plain = ops.conv_out_nhwc(x, None, None, "identity", w, None)
         want2 = F.conv2d(x.float(), w.float(), None, 1, 1)
         assert float((plain.float() - want2).abs().max() / want2.abs().max()) <= tol
+
+
+@pytest.mark.parametrize("N,C", [(256, 512), (64, 512), (128, 512), (128, 256), (256, 256), (64, 256)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attention_tokens_matches_fp32_softmax(N, C, dtype):
+    """The fused attention core (reference sige_fused_unet.py:196-212: bmm, softmax, bmm) vs plain fp32 torch on the same
+    16-bit inputs.  Logit scale ~ N(0, 2) gives a peaked softmax, so the cluster's flash-style combine is exercised."""
+    from sige_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(N * 7 + C)
+    qkv = torch.randn(2, N, 3 * C, generator=g)
+    qkv[:, :, :C] *= 2.0 * C ** -0.5           # q carries the c^-0.5 attention scale
+    qkv = qkv.to(DEV, dtype)
+    out = ops.attention_tokens(qkv)
+    q, k, v = (t.float() for t in qkv.split(C, dim=2))
+    ref = torch.softmax(q @ k.transpose(1, 2), dim=-1) @ v
+    err = float((out.float() - ref).abs().max()) / float(ref.abs().max())
+    assert err <= (4e-3 if dtype == torch.float16 else 2e-2), err
+    # programmatic-dependent-launch flavour of the same launch, back to back on one stream
+    out2 = torch.empty_like(out)
+    for _ in range(3):
+        ops.attention_tokens(qkv, out=out2, flags=1)
+    assert torch.equal(out, out2)
+
+
+def test_attention_tokens_rejects_unsupported_shapes():
+    from sige_b200 import ops
+
+    assert not ops.attention_tokens_supported(100, 512, torch.float16)
+    assert not ops.attention_tokens_supported(256, 192, torch.float16)
+    assert not ops.attention_tokens_supported(256, 512, torch.float32)
+    with pytest.raises(RuntimeError):
+        ops.attention_tokens(torch.zeros(1, 96, 3 * 512, device=DEV, dtype=torch.float16))

@@ -28,7 +28,8 @@ def hook(fc):
     i = order.setdefault(id(fc), len(order))
     lib.sige_debug_set_trace(buf.data_ptr() + i * SLOT * 8)
 FusedConv.trace_hook = hook
-eng = DDPMStepEngine(model, cl(x1), use_graph=True, tc5=True, pdl="--no-pdl" not in sys.argv, branches="--no-branches" not in sys.argv)
+eng = DDPMStepEngine(model, cl(x1), use_graph=True, tc5=True, pdl="--no-pdl" not in sys.argv, branches="--no-branches" not in sys.argv,
+                     fused_attention="--no-fused-attention" not in sys.argv)
 FusedConv.trace_hook = None
 lib.sige_debug_set_trace(None)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -66,4 +67,21 @@ for i in sorted(names):
     rel = (t_ - t_[:, 0].min()).float(); rel[t_ == 0] = float("nan")
     med = [float(torch.nanmedian(rel[:, k])) / 1e3 for k in range(12)]
     print("%-28s " % nm + " ".join("%s %.1f" % (a, b) for a, b in zip(stage_names[1:], med[1:])))
+if "--detail" in sys.argv:
+    print("--- absolute in-graph stamps (us after the first kernel start): start(min) | wait released+loads issued | halo stored | MMA issued | acc ready | cluster sync | stored(max) | end(max)")
+    det = []
+    for i in sorted(names):
+        t_ = tt[i]; t_ = t_[t_[:, 0] > 0]
+        if t_.shape[0] == 0:
+            continue
+        def med(k):
+            v = t_[:, k][t_[:, k] > 0]
+            return (float(torch.median((v - t0).double())) / 1e3) if v.numel() else float("nan")
+        def mx(k):
+            v = t_[:, k][t_[:, k] > 0]
+            return (float((v - t0).double().max()) / 1e3) if v.numel() else float("nan")
+        det.append((int(t_[:, 0].min()), "%-28s n%3d | %8.2f | %8.2f %8.2f %8.2f %8.2f %8.2f | %8.2f %8.2f" %
+                    (names[i], t_.shape[0], (int(t_[:, 0].min()) - t0) / 1e3, med(3), med(4), med(6), med(7), med(8), mx(10), mx(11))))
+    for _, line in sorted(det):
+        print(line)
 print("first start -> last end: %.1f us; sum of kernel durations %.1f us over %d traced launches" % ((prev_end - t0) / 1e3, busy / 1e3, len(rows)))
