@@ -87,17 +87,23 @@ struct Params {
     long long *trace;          // development aid: per-CTA clock stamps (16 slots), or nullptr
 };
 
-template <int BN, int TAPS> struct Cfg {
+template <int BN, int TAPS, bool DEEP = false> struct Cfg {
+    // DEEP (split-K launches of the narrow 3x3 configuration: small, latency-bound problems whose K slices rarely span
+    // more than one or two chunks): ONE halo buffer, and the other 72 KB go to the weight ring — 5 stages = 120 KB in
+    // flight, so a slice's weights are on their way before the previous layer has finished, instead of one L2/HBM
+    // round trip per two ring steps.
+    static_assert(!DEEP || (BN == 64 && TAPS == 9), "deep ring: narrow 3x3 only");
+    static constexpr int NAB = DEEP ? 1 : 2;
     // one weight-ring stage = TPS taps (a whole kernel row for the narrow 3x3 configuration): fewer barrier round
     // trips for the single MMA-issuing thread
     static constexpr int TPS = (TAPS == 9 && BN == 64) ? 3 : 1;
     static constexpr int SPC = TAPS / TPS;                     // ring steps per 64-channel chunk
     static constexpr int B_TILE_BYTES = BN * 128;              // one (tap, chunk) weight tile
     static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES;
-    static constexpr int NSTB = (BN == 128) ? 4 : (TPS == 3 ? 2 : 4);   // weight ring depth (48 / 32 / 64 KB in flight per CTA)
+    static constexpr int NSTB = DEEP ? 5 : ((BN == 128) ? 4 : (TPS == 3 ? 2 : 4));   // weight ring depth (120 / 48 / 32 / 64 KB in flight per CTA)
     static constexpr int EPI_PITCH = BN + EPI_PAD;             // floats
     static constexpr int OFF_A = 0;
-    static constexpr int OFF_B = 2 * A_BUF_BYTES;
+    static constexpr int OFF_B = NAB * A_BUF_BYTES;
     // split-K (BN = 64 only): partial-tile rows pushed by the other ranks of the cluster land here — a region that no
     // mainloop touches, so a fast rank may push while this CTA is still multiplying.  <= 7 remote ranks x 16 rows.
     static constexpr int OFF_SLOT = OFF_B + NSTB * B_STAGE_BYTES;
@@ -107,7 +113,7 @@ template <int BN, int TAPS> struct Cfg {
     static constexpr int OFF_CONST = OFF_BAR + 256;            // idx[8][2] ints + 8 shortcut flags, then bias | aux0 scale,shift | aux1 scale,shift | bias2
     static constexpr int SMEM_BYTES = OFF_CONST + 80 + 6 * BN * 4 + 1024;    // + slack for the 1024-byte alignment
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
-    static_assert(128 * EPI_PITCH * 4 <= 2 * A_BUF_BYTES, "epilogue staging must fit in the halo buffers");
+    static_assert(128 * EPI_PITCH * 4 <= NAB * A_BUF_BYTES, "epilogue staging must fit in the halo buffers");
 };
 
 // ------------------------------------------------------------------------------------------
@@ -165,6 +171,36 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same instruction with the descriptors given as (lo, hi) words: the single issuing thread is the critical path of a
+// latency-bound layer, so per-MMA descriptor arithmetic is reduced to one 32-bit add on the low word (start address
+// in 16-byte units; every operand base is below 256 KB, so the 14-bit field never overflows into its neighbours).
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// true in exactly one (converged) lane of the warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);      // see make_desc
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
@@ -210,12 +246,12 @@ __device__ __forceinline__ long long gtime() {
         if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); \
     } while (0)
 
-template <typename T, int BN, int TAPS>
+template <typename T, int BN, int TAPS, bool DEEP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap,
                      const __grid_constant__ CUtensorMap wmap2) {
-    using C = Cfg<BN, TAPS>;
-    constexpr int NSTB = C::NSTB, TPS = C::TPS, SPC = C::SPC;
+    using C = Cfg<BN, TAPS, DEEP>;
+    constexpr int NSTB = C::NSTB, TPS = C::TPS, SPC = C::SPC, NAB = C::NAB;
     constexpr int R = (TAPS == 9) ? 6 : 4;            // halo tile extent
     constexpr int RS = R * R;
     constexpr int UNITS = TILES * RS * 8;             // 16-byte units gathered per chunk
@@ -292,60 +328,76 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     if (warp == 0) {
         // ================= TMA producer: weights =================
         if (lane == 0) {
+            int s = 0, k = 0;                                          // ring stage and lap
+            int c = j_begin < J_main ? j_begin / SPC : 0, st = j_begin < J_main ? j_begin - c * SPC : 0;
             for (int j = j_begin; j < j_end; ++j) {
-                const int it = j - j_begin, s = it % NSTB, k = it / NSTB;
                 mbar_wait(B_EMPTY(s), (k & 1) ^ 1);
+                const uint32_t dst = sbase + C::OFF_B + s * C::B_STAGE_BYTES;
                 if (j < J_main) {
                     mbar_expect_tx(B_FULL(s), C::B_STAGE_BYTES);
-                    const int c = j / SPC, tap0 = (j - c * SPC) * TPS;
+                    const int row0 = (st * TPS * NC + c) * p.Cout + n0;      // weight rows of tap st*TPS, chunk c
 #pragma unroll
-                    for (int t = 0; t < TPS; ++t)
-                        tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES + t * C::B_TILE_BYTES, &wmap, 0, ((tap0 + t) * NC + c) * p.Cout + n0,
-                                    B_FULL(s));
+                    for (int t = 0; t < TPS; ++t) tma_load_2d(dst + t * C::B_TILE_BYTES, &wmap, 0, row0 + t * NC * p.Cout, B_FULL(s));
+                    if (++st == SPC) { st = 0; ++c; }
                 } else {                                               // shortcut weights [Cin2/64][Cout][64]
                     mbar_expect_tx(B_FULL(s), C::B_TILE_BYTES);
-                    tma_load_2d(sbase + C::OFF_B + s * C::B_STAGE_BYTES, &wmap2, 0, (j - J_main) * p.Cout + n0, B_FULL(s));
+                    tma_load_2d(dst, &wmap2, 0, (j - J_main) * p.Cout + n0, B_FULL(s));
                 }
+                if (++s == NSTB) { s = 0; ++k; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // One thread issues everything, and in a latency-bound layer its instruction stream IS the critical path (the
+        // first version spent ~17 dependent uniform-datapath instructions per MMA rebuilding both descriptors: ~140
+        // cycles per 128x64x16 MMA against a 32-cycle tensor-core floor).  Descriptor low words are now advanced by
+        // compile-time constants from per-step bases.
+        // The whole warp walks the loop converged; an elected lane issues.
+        const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+        {
             const uint32_t idesc = make_idesc(BN, p.is_bf16);
+            const uint32_t a_lo0 = desc_lo(sbase + C::OFF_A), b_lo0 = desc_lo(sbase + C::OFF_B);
+            uint32_t accum = 0;
             int ab = 0, ause = 0;             // halo buffer index and how many times it has been used
+            int st = (j_begin < J_main) ? j_begin % SPC : 0, s = 0, k = 0;
             for (int j = j_begin; j < j_end; ++j) {
                 const bool is_sc = j >= J_main;
-                const int st = is_sc ? 0 : j % SPC;
+                if (is_sc) st = 0;
                 if (j == j_begin || st == 0) {                        // a new chunk starts: wait for its halo buffer
-                    mbar_wait(A_FULL(ab), (ause >> 1) & 1);
-                    tc_fence_after();
-                    if (j == j_begin) SIGE_TRACE(5);
+                    mbar_wait(A_FULL(ab), (ause / NAB) & 1);
+                    if (j == j_begin && lane == 0) SIGE_TRACE(5);
                 }
-                const int it = j - j_begin, s = it % NSTB, k = it / NSTB;
                 mbar_wait(B_FULL(s), k & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int t = 0; t < TPS; ++t) {
-                    if (is_sc && t > 0) break;                        // the shortcut is a single tap: the centre of the 3x3 frame
-                    const int tap = is_sc ? 4 : st * TPS + t;
-                    const int ky = (TAPS == 9) ? tap / 3 : 0, kx = (TAPS == 9) ? tap - 3 * ky : 0;
-                    const uint32_t a_addr = sbase + C::OFF_A + ab * A_BUF_BYTES + kx * A_COPY_BYTES + ky * (32 * 128);
-                    const uint32_t b_addr = sbase + C::OFF_B + s * C::B_STAGE_BYTES + t * C::B_TILE_BYTES;
-#pragma unroll
-                    for (int kk = 0; kk < KC / 16; ++kk)
-                        umma_f16(tmem_base, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), idesc,
-                                 (j > j_begin || t > 0 || kk > 0) ? 1u : 0u);
+                const uint32_t b_step = b_lo0 + s * (C::B_STAGE_BYTES >> 4);
+                uint32_t a_step = a_lo0 + ab * (A_BUF_BYTES >> 4);
+                if (TAPS == 9) {
+                    if (is_sc) a_step += (A_COPY_BYTES + 32 * 128) >> 4;                           // tap (1,1)
+                    else if (TPS == 3) a_step += st * ((32 * 128) >> 4);                           // ky = st, kx = t
+                    else { const int ky = st / 3; a_step += ky * ((32 * 128) >> 4) + (st - 3 * ky) * (A_COPY_BYTES >> 4); }
                 }
-                umma_commit(B_EMPTY(s));                              // weight stage free once these MMAs retire
-                if (is_sc || st == SPC - 1 || j == j_end - 1) {       // chunk done: halo buffer free
-                    umma_commit(A_EMPTY(ab));
-                    ab ^= 1;
-                    ++ause;
+                const bool chunk_done = is_sc || st == SPC - 1 || j == j_end - 1;
+                if (elect_one()) {
+#pragma unroll
+                    for (int t = 0; t < TPS; ++t) {
+                        if (is_sc && t > 0) break;                    // the shortcut is a single tap: the centre of the 3x3 frame
+#pragma unroll
+                        for (int kk = 0; kk < KC / 16; ++kk)
+                            umma_f16_lohi(d_tmem, a_step + t * (A_COPY_BYTES >> 4) + kk * 2, b_step + t * (C::B_TILE_BYTES >> 4) + kk * 2, DESC_HI, idesc,
+                                          (accum | t | kk) ? 1u : 0u);
+                    }
+                    umma_commit(B_EMPTY(s));                          // weight stage free once these MMAs retire
+                    if (chunk_done) umma_commit(A_EMPTY(ab));         // halo buffer free
+                    if (j == j_end - 1) umma_commit(ACC_FULL);
                 }
+                __syncwarp();
+                accum = 1;
+                if (chunk_done) { ++ause; ab = ause % NAB; }
+                if (++st == SPC) st = 0;
+                if (++s == NSTB) { s = 0; ++k; }
             }
-            umma_commit(ACC_FULL);
-            SIGE_TRACE(6);
+            if (lane == 0) SIGE_TRACE(6);
         }
         __syncwarp();
     } else {
@@ -485,15 +537,15 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         issue_any(c_first);
         int ab = 0, ause = 0;
         for (int c = c_first; c <= c_last; ++c) {
-            mbar_wait(A_EMPTY(ab), ((ause >> 1) & 1) ^ 1);            // the MMAs that read this buffer have retired
+            mbar_wait(A_EMPTY(ab), ((ause / NAB) & 1) ^ 1);           // the MMAs that read this buffer have retired
             if (ptid == 0 && c == c_first) SIGE_TRACE(3);
             if (c < NC) store(c, smem + C::OFF_A + ab * A_BUF_BYTES); else store2(smem + C::OFF_A + ab * A_BUF_BYTES);
             if (ptid == 0 && c == c_first) SIGE_TRACE(4);
             fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core
             mbar_arrive(A_FULL(ab));
             if (c < c_last) issue_any(c + 1);
-            ab ^= 1;
             ++ause;
+            ab = ause % NAB;
         }
     }
 
@@ -667,8 +719,26 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <typename T, int BN, int TAPS> static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaStream_t st) {
-    using C = Cfg<BN, TAPS>;
+template <typename T, int BN, int TAPS, bool DEEP = false>
+static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaStream_t st) {
+    using C = Cfg<BN, TAPS, DEEP>;
+    const int J = (p.Cin / KC) * C::SPC + (TAPS == 9 ? p.Cin2 / KC : 0);        // ring steps
+    const long long base = (long long)ceil_div(p.NT, TILES) * (p.Cout / BN);
+    if (p.ksplit <= 0) {
+        // one CTA per SM (214 KB smem): co-resident CTAs are 148 / 148 / 132 / 120 for cluster sizes 1 / 2 / 4 / 8
+        // (ncu 'Max Active Clusters': 74 x2, 15 x8); never spill into a second wave.  Splitting only pays when the K loop
+        // is long: each slice should keep >= 8 (tap, chunk) steps.
+        static const int kMaxCtas[9] = {0, 148, 148, 0, 132, 0, 0, 0, 120};
+        static int min_taps = getenv("SIGE_TC5_MIN_TAPS") ? atoi(getenv("SIGE_TC5_MIN_TAPS")) : 3;   // tuning knob (taps per K slice)
+        int ks = 1;
+        while (C::kSplitOk && ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * C::TPS) / (ks * 2) >= min_taps) ks *= 2;
+        p.ksplit = ks;
+    }
+    if (p.ksplit > J || !C::kSplitOk) p.ksplit = 1;
+    if constexpr (BN == 64 && TAPS == 9 && !DEEP) {
+        static int deep_env = getenv("SIGE_TC5_DEEP") ? atoi(getenv("SIGE_TC5_DEEP")) : 1;   // A/B knob
+        if (p.ksplit > 1 && deep_env) return launch<T, BN, TAPS, true>(p, w_packed, w2_packed, st);
+    }
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("sige_tile_conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
@@ -697,7 +767,7 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
             return 2;
         }
     }
-    auto kern = tile_conv_tc5_kernel<T, BN, TAPS>;
+    auto kern = tile_conv_tc5_kernel<T, BN, TAPS, DEEP>;
     static int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -709,19 +779,6 @@ template <typename T, int BN, int TAPS> static int launch(Params &p, const void 
         }
         attr_dev = dev;
     }
-    const int J = (p.Cin / KC) * C::SPC + (TAPS == 9 ? p.Cin2 / KC : 0);        // ring steps
-    const long long base = (long long)ceil_div(p.NT, TILES) * (p.Cout / BN);
-    if (p.ksplit <= 0) {
-        // one CTA per SM (214 KB smem): co-resident CTAs are 148 / 148 / 132 / 120 for cluster sizes 1 / 2 / 4 / 8
-        // (ncu 'Max Active Clusters': 74 x2, 15 x8); never spill into a second wave.  Splitting only pays when the K loop
-        // is long: each slice should keep >= 8 (tap, chunk) steps.
-        static const int kMaxCtas[9] = {0, 148, 148, 0, 132, 0, 0, 0, 120};
-        static int min_taps = getenv("SIGE_TC5_MIN_TAPS") ? atoi(getenv("SIGE_TC5_MIN_TAPS")) : 3;   // tuning knob (taps per K slice)
-        int ks = 1;
-        while (C::kSplitOk && ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * C::TPS) / (ks * 2) >= min_taps) ks *= 2;
-        p.ksplit = ks;
-    }
-    if (p.ksplit > J || !C::kSplitOk) p.ksplit = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ceil_div(p.NT, TILES), p.Cout / BN, p.ksplit);
     cfg.blockDim = dim3(NTHREADS);
