@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--_cpu-child", dest="_cpu_child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-tc5", action="store_true", help="engine: use the mma.sync kernel everywhere (default: tcgen05/TMEM/TMA kernel where the geometry allows)")
     ap.add_argument("--no-producer-preop", action="store_true", help="engine: apply GroupNorm affine + SiLU in every gather (reference order) instead of once in the producer's epilogue")
+    ap.add_argument("--dense-stem", action="store_true", help="engine: evaluate conv_in on the whole image even when only the active tiles are read")
     ap.add_argument("--no-fused-attention", action="store_true", help="engine: torch matmul/softmax instead of the fused attention-core kernel")
     ap.add_argument("--no-fuse-shortcut", action="store_true", help="engine: keep the 1x1 shortcut convs as separate launches")
     ap.add_argument("--no-branches", action="store_true", help="engine: keep the 1x1 shortcut convs on the main stream (no parallel graph branch)")
@@ -294,7 +295,7 @@ def run_ours(args):
     if path == "engine":
         from sige_b200.engine import DDPMStepEngine
 
-        runner = DDPMStepEngine(model, x_dev, use_graph=not (args.no_graph or args.ncu), pdl=not args.no_pdl, ksplit=args.ksplit, tc5=not args.no_tc5, producer_preop=not args.no_producer_preop, branches=not args.no_branches, fuse_shortcut=not args.no_fuse_shortcut, fused_attention=not args.no_fused_attention)
+        runner = DDPMStepEngine(model, x_dev, use_graph=not (args.no_graph or args.ncu), pdl=not args.no_pdl, ksplit=args.ksplit, tc5=not args.no_tc5, producer_preop=not args.no_producer_preop, branches=not args.no_branches, fuse_shortcut=not args.no_fuse_shortcut, fused_attention=not args.no_fused_attention, sparse_stem=not args.dense_stem)
     else:
         from sige_b200.graphs import GraphedStep
 

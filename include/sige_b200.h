@@ -240,6 +240,12 @@ int sige_tile_conv_generic(const void *x, const void *w, const void *bias, void 
 int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out, int dtype, int B,
                       int H, int W, int Cin, int Cout, int n_aux, const sige_conv_aux_t *aux,
                       sige_stream_t stream);
+/* The same stem evaluated only inside a list of R x S pixel tiles (tile t = rows idx[2t] .. +R-1, columns idx[2t+1] ..
+ * +S-1; the same index list for every image of the batch; pixels outside the image are skipped).  When every consumer
+ * of the stem reads it through Gather with one index set (reference sige/nn/gather.py:76-89), nothing else is read. */
+int sige_conv_in_nhwc_tiles(const void *x, const void *w, const void *bias, void *out, int dtype, int B,
+                            int H, int W, int Cin, int Cout, const int32_t *idx, int n_tiles, int R, int S,
+                            int n_aux, const sige_conv_aux_t *aux, sige_stream_t stream);
 /* GroupNorm statistics folded to per-channel fp32 (scale, shift) [B, C]: GroupNorm(x) == x*scale + shift.
  * Deterministic two-stage reduction; `workspace` holds sige_group_norm_fold_workspace(B, C) floats. */
 int sige_group_norm_fold_workspace(int B, int C);

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "sige_tile_conv": (_I, [POINTER(TileConv), _P]),
     "sige_tile_conv_generic": (_I, [_P, _P, _P, _P] + [_I] * 14 + [_P]),
     "sige_conv_in_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "sige_conv_in_nhwc_tiles": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
     "sige_group_norm_fold_workspace": (_I, [_I, _I]),
     "sige_group_norm_fold": (_I, [_P, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P, _P, _I, _P]),
     "sige_conv_out_nhwc": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -13,6 +13,28 @@
 
 namespace sige {
 
+// Programmatic dependent launch for the glue kernels: each one releases its successor right away
+// (griddepcontrol.launch_dependents: the successor's launch latency and constant staging overlap this kernel) and
+// waits for its predecessor's results just before the first dependent read (griddepcontrol.wait; a no-op when the
+// launch carries no programmatic edge).  Always on: both instructions are harmless in an ordinary stream.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;\n" ::); }
+__device__ __forceinline__ void pdl_acquire() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through check_launch()
+}
+
 // ------------------------------------------------------------------------------------------
 // conv_in: Cin <= 4, Cout % 8 == 0.  One thread = one pixel x 8 output channels (one 16-byte store);
 // the 9*Cin inputs come through L1, the 9*Cin*8 weights of the thread's channel octet from shared.
@@ -46,7 +68,9 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, c
     }
     float *bsm = wsm + OV * pitch;
     for (int e = threadIdx.x; e < Cout; e += blockDim.x) bsm[e] = bias ? DT<T>::to_f(bias[e]) : 0.f;
+    pdl_release();
     __syncthreads();
+    pdl_acquire();
     const int WQ = W / 4;
     const int total = B * H * WQ * OV;      // < 2^31 (checked on the host)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -119,6 +143,78 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, c
     }
 }
 
+// conv_in restricted to a list of R x S pixel tiles (tile t covers rows idx[2t] .. +R-1, columns idx[2t+1] .. +S-1 of
+// image b = t / n_tiles; pixels outside the image are skipped).  At a small edit every later layer reads the stem's
+// output only inside the active halo tiles, so this is all of it that has to exist.  One thread = one pixel x 8 output
+// channels.  Overlapping tiles recompute the shared pixels and store identical values.
+template <typename T>
+__global__ void __launch_bounds__(256) conv_in_tiles_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *__restrict__ bias,
+                                                            T *__restrict__ out, int H, int W, int Cin, int Cout,
+                                                            const int32_t *__restrict__ idx, int n_tiles, int NT, int R, int S, int n_aux,
+                                                            InAux a0, InAux a1) {
+    extern __shared__ float wsm[];   // same layout as conv_in_kernel
+    const int K = 9 * Cin, OV = Cout / 8;
+    const int pitch = conv_in_pitch(Cin);
+    for (int e = threadIdx.x; e < Cout * K; e += blockDim.x) {
+        const int co = e / K, k = e - co * K;
+        const int ci = k / 9, tap = k - ci * 9;
+        wsm[(co >> 3) * pitch + (tap * Cin + ci) * 8 + (co & 7)] = DT<T>::to_f(w[e]);
+    }
+    float *bsm = wsm + OV * pitch;
+    for (int e = threadIdx.x; e < Cout; e += blockDim.x) bsm[e] = bias ? DT<T>::to_f(bias[e]) : 0.f;
+    pdl_release();
+    __syncthreads();
+    pdl_acquire();
+    const int total = NT * R * S * OV;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ov = i % OV;
+        int q = i / OV;
+        const int xx = q % S; q /= S;
+        const int yy = q % R;
+        const int t = q / R;
+        const int b = t / n_tiles, tt = t - b * n_tiles;
+        const int hh = __ldg(idx + 2 * tt) + yy, ww = __ldg(idx + 2 * tt + 1) + xx;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        float acc[8];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) acc[z] = bsm[ov * 8 + z];
+        const float *wv = wsm + ov * pitch;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int y = hh + ky - 1;
+            if (y < 0 || y >= H) continue;
+            const T *row = x + ((long long)b * H + y) * W * Cin;
+            for (int ci = 0; ci < Cin; ++ci) {             // same accumulation order as conv_in_kernel: bit-identical results
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xc = ww + kx - 1;
+                    if (xc < 0 || xc >= W) continue;
+                    const float in = DT<T>::to_f(row[(long long)xc * Cin + ci]);
+                    const float4 wa = *reinterpret_cast<const float4 *>(wv + ((ky * 3 + kx) * Cin + ci) * 8);
+                    const float4 wb = *reinterpret_cast<const float4 *>(wv + ((ky * 3 + kx) * Cin + ci) * 8 + 4);
+                    acc[0] = fmaf(in, wa.x, acc[0]); acc[1] = fmaf(in, wa.y, acc[1]); acc[2] = fmaf(in, wa.z, acc[2]); acc[3] = fmaf(in, wa.w, acc[3]);
+                    acc[4] = fmaf(in, wb.x, acc[4]); acc[5] = fmaf(in, wb.y, acc[5]); acc[6] = fmaf(in, wb.z, acc[6]); acc[7] = fmaf(in, wb.w, acc[7]);
+                }
+            }
+        }
+        const long long o8 = ((((long long)b * H + hh) * W + ww) * OV + ov) * 8;
+        uint4 o;
+        T *oe = reinterpret_cast<T *>(&o);
+#pragma unroll
+        for (int z = 0; z < 8; ++z) oe[z] = DT<T>::from_f(acc[z]);
+        *reinterpret_cast<uint4 *>(out + o8) = o;
+        for (int ax = 0; ax < n_aux; ++ax) {   // the consumers' GroupNorm affine + SiLU, applied once here
+            const InAux &A = ax == 0 ? a0 : a1;
+            uint4 oa;
+            T *ae = reinterpret_cast<T *>(&oa);
+#pragma unroll
+            for (int z = 0; z < 8; ++z) {
+                const float sc = A.scale ? __ldg(A.scale + ov * 8 + z) : 1.f, sh = A.shift ? __ldg(A.shift + ov * 8 + z) : 0.f;
+                ae[z] = DT<T>::from_f(activate<true>(A.act, fmaf(acc[z], sc, sh)));
+            }
+            *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + o8) = oa;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // GroupNorm fold.  Stage 1: every CTA reduces a contiguous pixel range to per-channel (sum, sumsq);
 // stage 2: one CTA adds the partials in a fixed order and emits scale = gamma*rstd,
@@ -133,6 +229,8 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const T *__restrict__ x
     const int b = blockIdx.y;
     const int per = (HW + nblk - 1) / nblk;
     const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+    pdl_release();
+    pdl_acquire();
     float s[8], q[8];
 #pragma unroll
     for (int z = 0; z < 8; ++z) { s[z] = 0.f; q[z] = 0.f; }
@@ -167,6 +265,8 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float *__restri
     const int b = blockIdx.x;
     const int S = max(1, (int)blockDim.x / C);
     const int c = threadIdx.x % C, sl = threadIdx.x / C;
+    pdl_release();
+    pdl_acquire();
     if (sl < S) {
         double ss = 0.0, qq = 0.0;
         for (int k = sl; k < nblk; k += S) {
@@ -226,25 +326,53 @@ __global__ void __launch_bounds__(CO_TH * 32) conv_out_kernel(const T *__restric
     }
     const int CV = C / 8;
     const bool pre = scale || shift || act != SIGE_ACT_IDENTITY;
-    for (int e = threadIdx.x; e < HP * WP * CV; e += blockDim.x) {
-        const int cv = e % CV, pp = e / CV;
-        const int py = pp / WP, px = pp - py * WP;
-        const int hh = ty0 + py - 1, ww = tx0 + px - 1;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-            v = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)b * H + hh) * W + ww) * C + cv * 8));
-            if (pre) {
-                T *el = reinterpret_cast<T *>(&v);
+    pdl_release();
+    pdl_acquire();                 // the weights above are constants; x, scale and shift come from the preceding kernels
+    if (blockDim.x % CV == 0) {
+        // every thread keeps ONE channel octet for all its pixels: its 8 (scale, shift) pairs live in registers and the
+        // pixel walk is a fixed stride (the pre-op — 11 M SiLU evaluations per 256x256x128 step — is this kernel's cost)
+        const int cv = threadIdx.x % CV, pstep = blockDim.x / CV;
+        float sc[8], sh[8];
 #pragma unroll
-                for (int z = 0; z < 8; ++z) {
-                    const int c = cv * 8 + z;
-                    float f = DT<T>::to_f(el[z]);
-                    f = fmaf(f, scale ? scale[(long long)b * C + c] : 1.f, shift ? shift[(long long)b * C + c] : 0.f);
-                    el[z] = DT<T>::from_f(activate<true>(act, f));
+        for (int z = 0; z < 8; ++z) {
+            sc[z] = scale ? __ldg(scale + (long long)b * C + cv * 8 + z) : 1.f;
+            sh[z] = shift ? __ldg(shift + (long long)b * C + cv * 8 + z) : 0.f;
+        }
+        for (int pp = threadIdx.x / CV; pp < HP * WP; pp += pstep) {
+            const int py = pp / WP, px = pp - py * WP;
+            const int hh = ty0 + py - 1, ww = tx0 + px - 1;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                v = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)b * H + hh) * W + ww) * C + cv * 8));
+                if (pre) {
+                    T *el = reinterpret_cast<T *>(&v);
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) el[z] = DT<T>::from_f(activate<true>(act, fmaf(DT<T>::to_f(el[z]), sc[z], sh[z])));
                 }
             }
+            *reinterpret_cast<uint4 *>(tile + pp * pitch + cv * 16) = v;   // zero padding AFTER the pre-op
         }
-        *reinterpret_cast<uint4 *>(tile + pp * pitch + cv * 16) = v;       // zero padding AFTER the pre-op
+    } else {
+        for (int e = threadIdx.x; e < HP * WP * CV; e += blockDim.x) {
+            const int cv = e % CV, pp = e / CV;
+            const int py = pp / WP, px = pp - py * WP;
+            const int hh = ty0 + py - 1, ww = tx0 + px - 1;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                v = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)b * H + hh) * W + ww) * C + cv * 8));
+                if (pre) {
+                    T *el = reinterpret_cast<T *>(&v);
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) {
+                        const int c = cv * 8 + z;
+                        float f = DT<T>::to_f(el[z]);
+                        f = fmaf(f, scale ? scale[(long long)b * C + c] : 1.f, shift ? shift[(long long)b * C + c] : 0.f);
+                        el[z] = DT<T>::from_f(activate<true>(act, f));
+                    }
+                }
+            }
+            *reinterpret_cast<uint4 *>(tile + pp * pitch + cv * 16) = v;   // zero padding AFTER the pre-op
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;            // warp = output row inside the tile
@@ -321,11 +449,39 @@ int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out,
         ia[i] = InAux{aux[i].ptr, aux[i].scale, aux[i].shift, aux[i].act};
     }
     switch (dtype) {
-        case SIGE_F16: conv_in_kernel<__half><<<grid, 256, smem, st>>>((const __half *)x, (const __half *)w, (const __half *)bias, (__half *)out, B, H, W, Cin, Cout, n_aux, ia[0], ia[1]); break;
-        case SIGE_BF16: conv_in_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)w, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)out, B, H, W, Cin, Cout, n_aux, ia[0], ia[1]); break;
+        case SIGE_F16: launch_pdl(conv_in_kernel<__half>, dim3(grid), dim3(256), smem, st, (const __half *)x, (const __half *)w, (const __half *)bias, (__half *)out, B, H, W, Cin, Cout, n_aux, ia[0], ia[1]); break;
+        case SIGE_BF16: launch_pdl(conv_in_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)w, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)out, B, H, W, Cin, Cout, n_aux, ia[0], ia[1]); break;
         default: set_error("sige_conv_in_nhwc: dtype must be f16/bf16"); return 1;
     }
     return check_launch("sige_conv_in_nhwc");
+}
+
+int sige_conv_in_nhwc_tiles(const void *x, const void *w, const void *bias, void *out, int dtype, int B, int H, int W, int Cin, int Cout,
+                            const int32_t *idx, int n_tiles, int R, int S, int n_aux, const sige_conv_aux_t *aux, sige_stream_t stream) {
+    SIGE_REQUIRE(x && w && out && idx, "sige_conv_in_nhwc_tiles: null pointer");
+    SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 4 && Cout > 0 && Cout % 8 == 0, "sige_conv_in_nhwc_tiles: needs Cin <= 4 and Cout %% 8 == 0");
+    SIGE_REQUIRE(n_tiles >= 0 && R > 0 && S > 0, "sige_conv_in_nhwc_tiles: bad tile list");
+    SIGE_REQUIRE(((uintptr_t)out & 15) == 0, "sige_conv_in_nhwc_tiles: output not 16-byte aligned");
+    if (n_tiles == 0) return 0;
+    const size_t smem = sizeof(float) * ((size_t)(Cout / 8) * conv_in_pitch(Cin) + Cout);
+    SIGE_REQUIRE(smem <= 48 * 1024, "sige_conv_in_nhwc_tiles: weights do not fit in shared memory");
+    const long long total = (long long)B * n_tiles * R * S * (Cout / 8);
+    SIGE_REQUIRE(total < 2147483647LL && (long long)B * H * W * Cout < 2147483647LL * 8, "sige_conv_in_nhwc_tiles: tensor too large");
+    const long long want_blocks = (total + 255) / 256;
+    const int grid = (int)(want_blocks < 148LL * 4 ? want_blocks : 148LL * 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    SIGE_REQUIRE(n_aux >= 0 && n_aux <= 2 && (n_aux == 0 || aux), "sige_conv_in_nhwc_tiles: n_aux must be 0..2");
+    InAux ia[2] = {{nullptr, nullptr, nullptr, 0}, {nullptr, nullptr, nullptr, 0}};
+    for (int i = 0; i < n_aux; ++i) {
+        SIGE_REQUIRE(aux[i].ptr && aux[i].C == Cout && aux[i].c0 == 0 && ((uintptr_t)aux[i].ptr & 15) == 0, "sige_conv_in_nhwc_tiles: bad aux destination %d", i);
+        ia[i] = InAux{aux[i].ptr, aux[i].scale, aux[i].shift, aux[i].act};
+    }
+    switch (dtype) {
+        case SIGE_F16: launch_pdl(conv_in_tiles_kernel<__half>, dim3(grid), dim3(256), smem, st, (const __half *)x, (const __half *)w, (const __half *)bias, (__half *)out, H, W, Cin, Cout, idx, n_tiles, B * n_tiles, R, S, n_aux, ia[0], ia[1]); break;
+        case SIGE_BF16: launch_pdl(conv_in_tiles_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)w, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)out, H, W, Cin, Cout, idx, n_tiles, B * n_tiles, R, S, n_aux, ia[0], ia[1]); break;
+        default: set_error("sige_conv_in_nhwc_tiles: dtype must be f16/bf16"); return 1;
+    }
+    return check_launch("sige_conv_in_nhwc_tiles");
 }
 
 int sige_group_norm_fold_workspace(int B, int C) { return B * 296 * C * 2; }
@@ -347,9 +503,9 @@ int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, i
 #define SIGE_GN(T)                                                                                                                       \
     do {                                                                                                                                 \
         if (smem1 > 48 * 1024) cudaFuncSetAttribute(gn_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);        \
-        gn_partial_kernel<T><<<g1, 256, smem1, st>>>((const T *)x, HW, C, workspace, nblk);                                               \
-        gn_finalize_kernel<T><<<B, 1024, sizeof(double) * 2 * C * (1024 / C > 0 ? 1024 / C : 1), st>>>(workspace, nblk, HW, C, groups, eps, (const T *)gamma, \
-                                                                                      (const T *)beta, scale, shift);                   \
+        launch_pdl(gn_partial_kernel<T>, g1, dim3(256), smem1, st, (const T *)x, HW, C, workspace, nblk);                                 \
+        launch_pdl(gn_finalize_kernel<T>, dim3(B), dim3(1024), sizeof(double) * 2 * C * (1024 / C > 0 ? 1024 / C : 1), st, (const float *)workspace, nblk, HW, \
+                   C, groups, eps, (const T *)gamma, (const T *)beta, scale, shift);                                                    \
     } while (0)
     switch (dtype) {
         case SIGE_F16: SIGE_GN(__half); break;
@@ -374,8 +530,8 @@ int sige_conv_out_nhwc(const void *x, const float *scale, const float *shift, in
 #define SIGE_CO(T)                                                                                                        \
     do {                                                                                                                  \
         cudaFuncSetAttribute(conv_out_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
-        conv_out_kernel<T><<<grid, CO_TH * 32, smem, st>>>((const T *)x, scale, shift, act, (const T *)w, (const T *)bias, (T *)out, B, H, W, \
-                                                              C, Cout);                                                  \
+        launch_pdl(conv_out_kernel<T>, grid, dim3(CO_TH * 32), smem, st, (const T *)x, scale, shift, act, (const T *)w, (const T *)bias, (T *)out, B, H, \
+                   W, C, Cout);                                                                                           \
     } while (0)
     switch (dtype) {
         case SIGE_F16: SIGE_CO(__half); break;

@@ -83,6 +83,8 @@ struct Params {
     const unsigned char *sc_flags;
     int ksplit;
     int pdl;
+    int push_async;            // split-K exchange: 1 = st.async + per-owner mbarrier, 0 = plain remote stores + cluster barrier
+    int dealloc_late;          // split-K: free TMEM after the reduction instead of before it
     int is_bf16;
     long long *trace;          // development aid: per-CTA clock stamps (16 slots), or nullptr
 };
@@ -142,6 +144,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
+}
+// wait with cluster-scope acquire: the phase is completed by remote st.async complete_tx operations
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_LOOP:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAITC_DONE;\n"
+        "bra WAITC_LOOP;\n"
+        "WAITC_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// shared::cta address -> the same offset in the shared memory of CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// 16-byte store into a peer's shared memory that reports its bytes to an mbarrier of that peer: the receiver learns
+// that the data has landed from its own barrier — no fence and no cluster-wide barrier on the sender's side
+__device__ __forceinline__ void st_async16(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t remote_bar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(remote_addr), "r"(a),
+                 "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+                 : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
@@ -267,7 +296,9 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     auto A_FULL = [&](int b) { return bar0 + 8 * (2 * NSTB + b); };
     auto A_EMPTY = [&](int b) { return bar0 + 8 * (2 * NSTB + 2 + b); };
     const uint32_t ACC_FULL = bar0 + 8 * (2 * NSTB + 4);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::OFF_BAR + 8 * (2 * NSTB + 5));
+    const uint32_t RED_FULL = bar0 + 8 * (2 * NSTB + 5);     // split-K: all partial rows of the other ranks have landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::OFF_BAR + 8 * (2 * NSTB + 6));
+    static_assert(8 * (2 * NSTB + 7) <= 256, "barrier block");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile0 = blockIdx.x * TILES;
@@ -294,6 +325,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             for (int s = 0; s < NSTB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
             for (int b = 0; b < 2; ++b) { mbar_init(A_FULL(b), NPROD); mbar_init(A_EMPTY(b), 1); }
             mbar_init(ACC_FULL, 1);
+            mbar_init(RED_FULL, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -321,9 +353,45 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (p.ksplit > 1) cg::this_cluster().barrier_arrive();   // every thread; matched by barrier_wait() before the first remote store
+    if (p.ksplit > 1) {
+        // the receiver's side of the split-K exchange: (ksplit - 1) peers x its share of rows x BN floats will arrive
+        if (tid == 0 && p.push_async) mbar_expect_tx(RED_FULL, (uint32_t)(p.ksplit - 1) * (128 / p.ksplit) * BN * 4);
+        cg::this_cluster().barrier_arrive();                 // every thread; matched by barrier_wait() before the first remote store
+    }
     if (tid == 0) SIGE_TRACE(1);
     if (p.pdl) asm volatile("griddepcontrol.launch_dependents;\n" ::);   // the next layer may start prefetching ITS weights
+
+    auto tl_of = [&](int m) { return TAPS == 9 ? (m >> 2) & 7 : m >> 4; };
+    // GEMM row m -> destination pixel index, or -1 (row of a tile that does not exist / outside the image)
+    auto pixel_of = [&](int m) -> long long {
+        int tl, oy, ox;
+        if (TAPS == 9) { oy = m >> 5; tl = (m >> 2) & 7; ox = m & 3; } else { tl = m >> 4; oy = (m >> 2) & 3; ox = m & 3; }
+        if (tl >= ntile) return -1;
+        const int t = tile0 + tl;
+        int hh = oy, ww = ox, img = t;
+        if (!p.dst_is_stack) {
+            img = 0;
+            if (p.NT != p.N) img = t / p.N;
+            hh += p.offH + s_idx[2 * tl];
+            ww += p.offW + s_idx[2 * tl + 1];
+        }
+        if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) return -1;
+        return ((long long)img * p.dH + hh) * p.dW + ww;
+    };
+
+    // destination pixels of this thread's share of the epilogue, resolved here in the prologue (it overlaps the previous
+    // layer): [0] = its GEMM row in the direct path; [0], [1] = its (at most two) items of the split-K reduction
+    int epix[2] = {-1, -1};          // (pixel indices fit 32 bits: checked on the host)
+    if (p.ksplit == 1) {
+        if (warp >= 2) epix[0] = (int)pixel_of((warp & 3) * 32 + lane);
+    } else {
+        const int per = 128 / p.ksplit;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int q = tid + i * NTHREADS;
+            if (q < per * (BN / 8)) epix[i] = (int)pixel_of(kr * per + q / (BN / 8));
+        }
+    }
 
     if (warp == 0) {
         // ================= TMA producer: weights =================
@@ -404,30 +472,46 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         // ================= A-operand producers: gather + pre-op + swizzled stores =================
         const int ptid = tid - 64;
         // per-thread gather list (fixed for the whole kernel)
-        int g_pix[LOADS];     // (hh << 16) | ww in the logical source image, -1 = zero fill, -2 = nothing to do
-        int g_img[LOADS], g_ab[LOADS];
-        int g_xyt[LOADS];     // x | y << 4 | tile << 8
+        int g_xyt[LOADS];     // x | y << 4 | tile << 8 of the halo pixel this load feeds
+        int g_off[LOADS];     // element offset of its 16-byte unit in the CURRENT source segment (channel-chunk offset
+                              // excluded), -1 = zero fill (outside the image / missing tile), -2 = nothing to do.  The
+                              // address arithmetic is done here, in the prologue that overlaps the previous layer, so that
+                              // after griddepcontrol.wait a load is one add away; it is redone if the K slice crosses into
+                              // the second (concatenated) source.
+        int g_sg = -1;
+        auto resolve = [&](int sg) {
+            const Seg &seg = p.seg[sg];
+            const int Hs = p.H >> seg.up, Ws = p.W >> seg.up;
 #pragma unroll
-        for (int k = 0; k < LOADS; ++k) {
-            const int q = ptid + k * NPROD;
-            g_pix[k] = -2; g_img[k] = 0; g_ab[k] = 0; g_xyt[k] = 0;
-            if (q < UNITS) {
-                const int pix = q >> 3;
-                const int tl = pix / RS, rem = pix - tl * RS;
-                const int y = rem / R, x = rem - y * R;
-                g_xyt[k] = x | (y << 4) | (tl << 8);
-                g_pix[k] = -1;
-                const int t = tile0 + tl;
-                if (t < p.NT) {
-                    int b = 0;
-                    if (p.NT != p.N) b = t / p.N;                          // batch > 1 only (SD); DDPM is batch 1
-                    int hh = y, ww = x, img = t;
-                    if (!p.src_is_stack) { hh += s_idx[2 * tl]; ww += s_idx[2 * tl + 1]; img = b; }
-                    g_img[k] = img; g_ab[k] = b;
-                    if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) g_pix[k] = (hh << 16) | ww;
+            for (int k = 0; k < LOADS; ++k) {
+                const int q = ptid + k * NPROD;
+                g_off[k] = -2;
+                if (q < UNITS) {
+                    g_off[k] = -1;
+                    const int x = g_xyt[k] & 15, y = (g_xyt[k] >> 4) & 15, tl = g_xyt[k] >> 8;
+                    const int t = tile0 + tl;
+                    if (t < p.NT) {
+                        int hh = y, ww = x, img = t;
+                        if (!p.src_is_stack) {
+                            hh += s_idx[2 * tl];
+                            ww += s_idx[2 * tl + 1];
+                            img = (p.NT != p.N) ? t / p.N : 0;          // batch > 1 only (SD); DDPM is batch 1
+                        }
+                        if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+                            g_off[k] = ((img * Hs + (hh >> seg.up)) * Ws + (ww >> seg.up)) * seg.C + (q & 7) * 8;
+                    }
                 }
             }
+            g_sg = sg;
+        };
+#pragma unroll
+        for (int k = 0; k < LOADS; ++k) {
+            const int pix = (ptid + k * NPROD) >> 3;
+            const int tl = pix / RS, rem = pix - tl * RS;
+            const int y = rem / R, x = rem - y * R;
+            g_xyt[k] = x | (y << 4) | (tl << 8);
         }
+        resolve(c_first < NC && c_first * KC >= p.C0 ? 1 : 0);
         if (ptid == 0) SIGE_TRACE(2);   // bookkeeping (idx loads) done
         uint4 regs[LOADS];
         auto issue = [&](int c) {
@@ -435,14 +519,12 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             const int sg = cbase >= p.C0 ? 1 : 0;
             const Seg &seg = p.seg[sg];
             const int cl = cbase - (sg ? p.C0 : 0);
-            const int Hs = p.H >> seg.up, Ws = p.W >> seg.up;
+            if (sg != g_sg) resolve(sg);
 #pragma unroll
             for (int k = 0; k < LOADS; ++k) {
                 regs[k] = make_uint4(0, 0, 0, 0);
-                if (g_pix[k] >= 0) {
-                    const int hh = (g_pix[k] >> 16) >> seg.up, ww = (g_pix[k] & 0xffff) >> seg.up;
-                    const int u = (ptid + k * NPROD) & 7;
-                    const T *src = reinterpret_cast<const T *>(seg.ptr) + (((long long)g_img[k] * Hs + hh) * Ws + ww) * seg.C + cl + u * 8;
+                if (g_off[k] >= 0) {
+                    const T *src = reinterpret_cast<const T *>(seg.ptr) + g_off[k] + cl;
                     regs[k] = __ldg(reinterpret_cast<const uint4 *>(src));
                 }
             }
@@ -451,22 +533,23 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         auto store = [&](int c, unsigned char *abuf) {
 #pragma unroll
             for (int k = 0; k < LOADS; ++k) {
-                if (g_pix[k] == -2) continue;
+                if (g_off[k] == -2) continue;
                 uint4 v = regs[k];
                 const int u = (ptid + k * NPROD) & 7;
-                if (pre && g_pix[k] >= 0) {
+                if (pre && g_off[k] >= 0) {
+                    const int ab_k = (p.NT != p.N) ? (tile0 + (g_xyt[k] >> 8)) / p.N : 0;      // batch index (batch > 1: SD only)
                     const int ch = c * KC + u * 8;
                     T *e = reinterpret_cast<T *>(&v);
                     float sc[8], sh[8];
 #pragma unroll
                     for (int z = 0; z < 8; ++z) { sc[z] = 1.f; sh[z] = 0.f; }
                     if (p.scale) {
-                        const float4 *s4 = reinterpret_cast<const float4 *>(p.scale + (long long)g_ab[k] * p.affine_bstride + ch);
+                        const float4 *s4 = reinterpret_cast<const float4 *>(p.scale + (long long)ab_k * p.affine_bstride + ch);
                         const float4 a = __ldg(s4), b = __ldg(s4 + 1);
                         sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
                     }
                     if (p.shift) {
-                        const float4 *s4 = reinterpret_cast<const float4 *>(p.shift + (long long)g_ab[k] * p.affine_bstride + ch);
+                        const float4 *s4 = reinterpret_cast<const float4 *>(p.shift + (long long)ab_k * p.affine_bstride + ch);
                         const float4 a = __ldg(s4), b = __ldg(s4 + 1);
                         sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w; sh[4] = b.x; sh[5] = b.y; sh[6] = b.z; sh[7] = b.w;
                     }
@@ -585,31 +668,13 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             *reinterpret_cast<uint4 *>(reinterpret_cast<T *>(A.ptr) + pixel * A.C + A.c0 + n) = oa;
         }
     };
-    auto tl_of = [&](int m) { return TAPS == 9 ? (m >> 2) & 7 : m >> 4; };
-    // GEMM row m -> destination pixel index, or -1 (row of a tile that does not exist / outside the image)
-    auto pixel_of = [&](int m) -> long long {
-        int tl, oy, ox;
-        if (TAPS == 9) { oy = m >> 5; tl = (m >> 2) & 7; ox = m & 3; } else { tl = m >> 4; oy = (m >> 2) & 3; ox = m & 3; }
-        if (tl >= ntile) return -1;
-        const int t = tile0 + tl;
-        int hh = oy, ww = ox, img = t;
-        if (!p.dst_is_stack) {
-            img = 0;
-            if (p.NT != p.N) img = t / p.N;
-            hh += p.offH + s_idx[2 * tl];
-            ww += p.offW + s_idx[2 * tl + 1];
-        }
-        if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) return -1;
-        return ((long long)img * p.dH + hh) * p.dW + ww;
-    };
-
     if (p.ksplit == 1) {
         // ---- no split-K: TMEM -> registers -> global.  Two warps per TMEM lane quarter (warp w and w+4 may both touch
         //      lanes 32*(w%4)..+31) split the BN columns; a thread's share of its pixel is one contiguous run in NHWC.
         if (warp >= 2) {
             const int quarter = warp & 3, halfsel = (warp - 2) >> 2;
             const int m = quarter * 32 + lane;
-            const long long pixel = pixel_of(m);
+            const long long pixel = epix[0];
             if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
             mbar_wait(ACC_FULL, 0);
             tc_fence_after();
@@ -662,23 +727,40 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             const int c0 = halfsel * (BN / 2) + cc;
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
-            float4 *dstv = reinterpret_cast<float4 *>(slot + c0);
+            if (p.push_async && owner != kr) {
+                // st.async: the bytes are counted by an mbarrier of the OWNER, which then waits on its own barrier only
+                const uint32_t remote = map_rank(sbase + C::OFF_SLOT + (uint32_t)(((kr < owner ? kr : kr - 1) * per + lr) * C::EPI_PITCH + c0) * 4, owner);
+                const uint32_t remote_bar = map_rank(RED_FULL, owner);
 #pragma unroll
-            for (int z = 0; z < 8; ++z)
-                dstv[z] = make_float4(__uint_as_float(r[4 * z]), __uint_as_float(r[4 * z + 1]), __uint_as_float(r[4 * z + 2]),
-                                      __uint_as_float(r[4 * z + 3]));
+                for (int z = 0; z < 8; ++z) st_async16(remote + 16 * z, r[4 * z], r[4 * z + 1], r[4 * z + 2], r[4 * z + 3], remote_bar);
+            } else {
+                float4 *dstv = reinterpret_cast<float4 *>(slot + c0);
+#pragma unroll
+                for (int z = 0; z < 8; ++z)
+                    dstv[z] = make_float4(__uint_as_float(r[4 * z]), __uint_as_float(r[4 * z + 1]), __uint_as_float(r[4 * z + 2]),
+                                          __uint_as_float(r[4 * z + 3]));
+            }
         }
         tc_fence_before();
     }
     if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
-    cluster.sync();                        // all partial rows have landed in their owners' slots
+    if (p.push_async) {
+        __syncthreads();                   // own rows staged; every tcgen05.ld of this CTA has completed
+        mbar_wait_cluster(RED_FULL, 0);    // the rows the other ranks pushed have landed
+    } else {
+        cluster.sync();                    // all partial rows have landed in their owners' slots
+    }
     if (tid == 0) { SIGE_TRACE(8); SIGE_TRACE(9); }
-    if (warp == 0) tmem_dealloc(tmem_base, BN);
-    for (int q = tid; q < per * (BN / 8); q += NTHREADS) {
+    if (warp == 0 && !p.dealloc_late) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+    static_assert(!C::kSplitOk || 64 * (BN / 8) <= 2 * NTHREADS, "at most two items per thread (ksplit >= 2: <= 64 rows per rank)");
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int q = tid + i * NTHREADS;
+        if (q >= per * (BN / 8)) break;
         const int lr = q / (BN / 8), nv = q - lr * (BN / 8);
         const int n = n0 + nv * 8;
         if (n >= p.Cout) continue;
-        const long long pixel = pixel_of(kr * per + lr);
+        const long long pixel = epix[i];
         if (pixel < 0) continue;
         float v[8];
 #pragma unroll
@@ -694,6 +776,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
         emit(pixel, tl_of(kr * per + lr), n, v);
     }
+    if (warp == 0 && p.dealloc_late) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
     if (tid == 0) SIGE_TRACE(10);
     if (tid == 0) SIGE_TRACE(11);
 }
@@ -820,6 +903,12 @@ bool tc5_supported(const sige_tile_conv_t *a) {
     const bool g3 = a->kH == 3 && a->kW == 3 && a->stride == 1 && a->R == 6 && a->S == 6;
     const bool g1 = a->kH == 1 && a->kW == 1 && a->stride == 1 && a->R == 4 && a->S == 4;
     if (a->n_src2 > 0 && !g3) return false;
+    // the kernel keeps 32-bit element offsets into its sources
+    const long long px = a->src_is_stack ? (long long)a->B * a->N * a->R * a->S : (long long)a->B * a->H * a->W;
+    long long cmax = 0;
+    for (int i = 0; i < a->n_src; ++i) cmax = a->src[i].C > cmax ? a->src[i].C : cmax;
+    if (px * cmax >= (1ll << 31)) return false;
+    if ((a->dst_is_stack ? (long long)a->B * a->N * 16 : (long long)a->B * a->dH * a->dW) >= (1ll << 31)) return false;
     return (g3 || g1) && a->Cout % 64 == 0 && a->Cin % 64 == 0 && (a->ksplit == 0 || a->ksplit == 1 || a->ksplit == 2 || a->ksplit == 4 || a->ksplit == 8);
 }
 
@@ -855,6 +944,10 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.ksplit = a->ksplit;
     p.pdl = (a->flags & SIGE_CONV_PDL) ? 1 : 0;
     p.is_bf16 = a->dtype == SIGE_BF16;
+    static int push_env = getenv("SIGE_TC5_PUSH_ASYNC") ? atoi(getenv("SIGE_TC5_PUSH_ASYNC")) : 1;      // A/B knobs
+    static int late_env = getenv("SIGE_TC5_DEALLOC_LATE") ? atoi(getenv("SIGE_TC5_DEALLOC_LATE")) : 0;
+    p.push_async = push_env;
+    p.dealloc_late = late_env;
     p.trace = g_trace;
     // BN = 128 only when that still leaves enough CTAs; small problems want more, narrower CTAs
     const long long m_blocks = ceil_div(p.NT, tc5::TILES);

@@ -56,6 +56,7 @@ class Buf:
         self.shape = tuple(shape)           # (C, H, W)
         self.cached_init = cached_init      # pristine values (fp32-convertible) when only active tiles are rewritten
         self.producers: List = []           # objects with .can_aux() / .add_aux(view, scale, shift, act)
+        self.readers: List = []             # (tile origins, tile size, upsample flag) of every fused launch that reads it
         self.views = {}
 
 
@@ -97,6 +98,8 @@ class ConvInRec:
     def __init__(self):
         self.aux = []
         self.keep = []
+        self.tiles = None        # tile origins when every reader gathers the stem through ONE index set, else None (dense)
+        self.tile_size = 6
 
     def can_aux(self) -> bool:
         return len(self.aux) < 2
@@ -116,7 +119,7 @@ class ConvInRec:
 class DDPMStepEngine:
     def __init__(self, model: SIGEDDPMUNet, x_static: torch.Tensor, use_graph: bool = True, pdl: bool = False, ksplit: int = 0,
                  tc5: bool = False, producer_preop: bool = True, branches: bool = True, fuse_shortcut: bool = True,
-                 fused_attention: bool = True):
+                 fused_attention: bool = True, sparse_stem: bool = True):
         if model.mode != "sparse":
             raise RuntimeError("DDPMStepEngine: run the dense pass, set_masks() and set_mode('sparse') first")
         p = next(model.parameters())
@@ -128,6 +131,7 @@ class DDPMStepEngine:
         self.side_stream = torch.cuda.Stream(device=p.device)
         self.fuse_shortcut = fuse_shortcut
         self.fused_attention = fused_attention
+        self.sparse_stem = sparse_stem
         assert x_static.is_cuda and x_static.dtype == self.dtype and x_static.is_contiguous(memory_format=torch.channels_last)
         self.steps: List = []          # callables taking the stream handle
         self.fused: List[FusedConv] = []
@@ -235,6 +239,10 @@ class DDPMStepEngine:
         d.dtype = ops._DTYPES[self.dtype]
         d.n_src = len(srcs)
         csum = 0
+        for (b_, up_, _) in srcs:
+            b_.readers.append((idx, block, up_))
+        if residual is not None:
+            residual.readers.append((idx, block, 0))
         for s, (t, (_, up, _)) in enumerate(zip(tensors, srcs)):
             assert t is not None and t.is_contiguous(memory_format=torch.channels_last) and t.dtype == self.dtype, name
             d.src[s].ptr, d.src[s].C, d.src[s].up = t.data_ptr(), t.shape[1], up
@@ -335,6 +343,8 @@ class DDPMStepEngine:
             else:
                 skip, flags = None, None
             shortcut = ([b.raw for (b, _) in ins], w2, b2, flags)
+            for (b, _) in ins:
+                b.readers.append((idx, bs, 0))        # the fused shortcut reads the centre 4x4 of conv2's 6x6 tiles
         elif blk.in_channels != blk.out_channels:
             if blk.shortcut_sparse:
                 sg = blk.shortcut_gather
@@ -404,7 +414,7 @@ class DDPMStepEngine:
         h0.producers.append(rec)
 
         def conv_in(_stream):
-            ops.conv_in_nhwc(self.x, w_in, b_in, out=h0.raw, aux=rec.aux)
+            ops.conv_in_nhwc(self.x, w_in, b_in, out=h0.raw, aux=rec.aux, tiles=rec.tiles, tile_size=rec.tile_size)
 
         self.steps.append(("main", conv_in))
         hs: List[Tuple[Buf, int]] = [(h0, res)]
@@ -466,6 +476,13 @@ class DDPMStepEngine:
             ops.conv_out_nhwc(h_last, gn_scale, gn_shift, "swish", w_out, b_out, out=self.output)
 
         self.steps.append(("main", tail))
+        # ---- the stem only has to exist where it is read: if every reader gathers it through one index set, restrict it
+        rd = h0.readers
+        if self.sparse_stem and rd and all(up_ == 0 and blk_ <= 6 and torch.equal(i_, rd[0][0]) for (i_, blk_, up_) in rd):
+            rec.tiles, rec.tile_size = rd[0][0].contiguous(), max(blk_ for (_, blk_, _) in rd)
+            for t_ in [h0.raw] + [v[0] for v in h0.views.values()]:
+                if t_ is not None:
+                    t_.zero_()          # never read outside the tiles; defined contents all the same
 
     # ------------------------------------------------------------------ execution
     def run_eager(self) -> torch.Tensor:

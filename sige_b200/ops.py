@@ -398,10 +398,22 @@ def tile_conv_generic(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torc
 # --------------------------------------------------------------------------------------
 # dense glue of a step (conv_in / GroupNorm fold / conv_out), NHWC f16/bf16
 # --------------------------------------------------------------------------------------
+def conv_aux(view: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], activation_name: str):
+    """Descriptor of an extra producer-side output: view = act(out*scale + shift), NHWC with the producer's channels;
+    scale / shift fp32 [C] (kept alive by the caller)."""
+    a = _cabi.ConvAux()
+    a.ptr, a.C, a.c0 = view.data_ptr(), view.shape[1], 0
+    a.scale = None if scale is None else scale.data_ptr()
+    a.shift = None if shift is None else shift.data_ptr()
+    a.act = _act(activation_name)
+    return a
+
+
 def conv_in_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
-                 aux=None) -> torch.Tensor:
-    """3x3 pad-1 conv with Cin <= 4 on a channels-last image (reference sige_fused_unet.py:395)."""
-    _require_cuda(x, weight, bias)
+                 aux=None, tiles: Optional[torch.Tensor] = None, tile_size: int = 6) -> torch.Tensor:
+    """3x3 pad-1 conv with Cin <= 4 on a channels-last image (reference sige_fused_unet.py:395).  With ``tiles`` (int32
+    [N, 2] tile origins) only the pixels inside those tile_size x tile_size tiles of ``out`` are written."""
+    _require_cuda(x, weight, bias, tiles)
     x, _ = _dense(x, NHWC)
     B, Cin, H, W = x.shape
     w = weight.detach().to(x.dtype).contiguous()
@@ -414,8 +426,14 @@ def conv_in_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
         arr = (_cabi.ConvAux * 2)()
         for i in range(n_aux):
             arr[i] = aux[i]
-        _cabi.check(_cabi.lib().sige_conv_in_nhwc(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), _dt(x), B, H, W,
-                                                 Cin, Cout, n_aux, arr, _stream(x)), "sige_conv_in_nhwc")
+        if tiles is not None:
+            assert tiles.dtype == torch.int32 and tiles.dim() == 2 and tiles.shape[1] == 2 and tiles.is_contiguous()
+            _cabi.check(_cabi.lib().sige_conv_in_nhwc_tiles(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), _dt(x),
+                                                           B, H, W, Cin, Cout, tiles.data_ptr(), int(tiles.shape[0]), int(tile_size), int(tile_size),
+                                                           n_aux, arr, _stream(x)), "sige_conv_in_nhwc_tiles")
+        else:
+            _cabi.check(_cabi.lib().sige_conv_in_nhwc(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), _dt(x), B, H, W,
+                                                     Cin, Cout, n_aux, arr, _stream(x)), "sige_conv_in_nhwc")
     _bump()
     return out
 

@@ -43,7 +43,7 @@ def test_engine_matches_modules_and_reference(tag, tc5, producer_preop, pdl, bra
     with torch.no_grad():
         via_modules = model(x1, t).float()
     eng = DDPMStepEngine(model, x1.clone(memory_format=torch.channels_last), tc5=tc5, producer_preop=producer_preop, pdl=pdl, branches=branches, fuse_shortcut=fuse,
-                         fused_attention=tc5)      # the mma.sync combinations also cover the torch attention core
+                         fused_attention=tc5, sparse_stem=tc5)      # the mma.sync combinations also cover the torch attention core and the dense stem
     out1 = eng.replay().clone()
     out2 = eng.replay().clone()
     torch.cuda.synchronize()

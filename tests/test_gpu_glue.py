@@ -81,3 +81,28 @@ def test_attention_tokens_rejects_unsupported_shapes():
     assert not ops.attention_tokens_supported(256, 512, torch.float32)
     with pytest.raises(RuntimeError):
         ops.attention_tokens(torch.zeros(1, 96, 3 * 512, device=DEV, dtype=torch.float16))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_conv_in_tiles_matches_dense_inside_the_tiles(dtype):
+    """Stem restricted to a tile list (sige_conv_in_nhwc_tiles): bit-identical to the dense stem inside the tiles,
+    untouched outside; tiles may overlap and may stick out of the image."""
+    from sige_b200 import ops
+
+    torch.manual_seed(3)
+    B, Cin, Cout, H, W = 1, 3, 128, 64, 48
+    x = torch.randn(B, Cin, H, W, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 3, 3, device=DEV) / (Cin * 9) ** 0.5).to(dtype)
+    b = torch.randn(Cout, device=DEV).to(dtype)
+    sc, sh = torch.rand(Cout, device=DEV) + 0.5, torch.randn(Cout, device=DEV)
+    dense_aux = torch.empty(B, Cout, H, W, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
+    dense = ops.conv_in_nhwc(x, w, b, aux=[ops.conv_aux(dense_aux, sc, sh, "swish")])
+    tiles = torch.tensor([[-1, -1], [3, 7], [7, 7], [59, 43], [30, 44]], dtype=torch.int32, device=DEV)
+    out = torch.full_like(dense, 7.0)
+    aux = torch.full_like(dense, 7.0)
+    ops.conv_in_nhwc(x, w, b, out=out, aux=[ops.conv_aux(aux, sc, sh, "swish")], tiles=tiles, tile_size=6)
+    inside = torch.zeros(H, W, dtype=torch.bool, device=DEV)
+    for (y0, x0) in tiles.tolist():
+        inside[max(y0, 0):max(min(y0 + 6, H), 0), max(x0, 0):max(min(x0 + 6, W), 0)] = True
+    assert torch.equal(out[:, :, inside], dense[:, :, inside]) and torch.equal(aux[:, :, inside], dense_aux[:, :, inside])
+    assert bool((out[:, :, ~inside] == 7.0).all()) and bool((aux[:, :, ~inside] == 7.0).all())
