@@ -359,7 +359,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         cg::this_cluster().barrier_arrive();                 // every thread; matched by barrier_wait() before the first remote store
     }
     if (tid == 0) SIGE_TRACE(1);
-    if (p.pdl) asm volatile("griddepcontrol.launch_dependents;\n" ::);   // the next layer may start prefetching ITS weights
+    if (p.pdl == 1) asm volatile("griddepcontrol.launch_dependents;\n" ::);   // the next layer may start prefetching ITS weights
 
     auto tl_of = [&](int m) { return TAPS == 9 ? (m >> 2) & 7 : m >> 4; };
     // GEMM row m -> destination pixel index, or -1 (row of a tile that does not exist / outside the image)
@@ -633,6 +633,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     }
 
     // ---------------- epilogue ----------------
+    if (p.pdl == 2) asm volatile("griddepcontrol.launch_dependents;\n" ::);   // (A/B) release the next layer only now
     float *cst = reinterpret_cast<float *>(smem + C::OFF_A);
     // v[8] (fp32 conv result of 8 consecutive channels starting at n) -> +bias, +residual -> dst and aux destinations
     auto emit = [&](long long pixel, int tl, int n, float (&v)[8]) {
@@ -942,7 +943,8 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.bias2 = a->n_src2 > 0 ? a->bias2 : nullptr;
     p.sc_flags = a->n_src2 > 0 ? a->sc_flags : nullptr;
     p.ksplit = a->ksplit;
-    p.pdl = (a->flags & SIGE_CONV_PDL) ? 1 : 0;
+    static int trig_env = getenv("SIGE_TC5_LATE_TRIGGER") ? atoi(getenv("SIGE_TC5_LATE_TRIGGER")) : 1;     // A/B knob
+    p.pdl = (a->flags & SIGE_CONV_PDL) ? (trig_env ? 2 : 1) : 0;
     p.is_bf16 = a->dtype == SIGE_BF16;
     static int push_env = getenv("SIGE_TC5_PUSH_ASYNC") ? atoi(getenv("SIGE_TC5_PUSH_ASYNC")) : 1;      // A/B knobs
     static int late_env = getenv("SIGE_TC5_DEALLOC_LATE") ? atoi(getenv("SIGE_TC5_DEALLOC_LATE")) : 0;
