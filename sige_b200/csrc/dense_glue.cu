@@ -61,10 +61,18 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const T *__restrict__ x, c
     extern __shared__ float wsm[];   // [Cout/8][pitch] (rows of 9*Cin*8 weights, padded) + bias [Cout]
     const int K = 9 * Cin, OV = Cout / 8;
     const int pitch = conv_in_pitch(Cin);
-    for (int e = threadIdx.x; e < Cout * K; e += blockDim.x) {
-        const int co = e / K, k = e - co * K;              // k = ci*9 + tap in OIHW
-        const int ci = k / 9, tap = k - ci * 9;
-        wsm[(co >> 3) * pitch + (tap * Cin + ci) * 8 + (co & 7)] = DT<T>::to_f(w[e]);
+    for (int e0 = threadIdx.x; e0 < Cout * K; e0 += blockDim.x * 8) {      // 8 coalesced loads in flight per thread
+        T v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int e = e0 + j * blockDim.x; v[j] = e < Cout * K ? w[e] : DT<T>::from_f(0.f); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = e0 + j * blockDim.x;
+            if (e >= Cout * K) break;
+            const int co = e / K, k = e - co * K;          // k = ci*9 + tap in OIHW
+            const int ci = k / 9, tap = k - ci * 9;
+            wsm[(co >> 3) * pitch + (tap * Cin + ci) * 8 + (co & 7)] = DT<T>::to_f(v[j]);
+        }
     }
     float *bsm = wsm + OV * pitch;
     for (int e = threadIdx.x; e < Cout; e += blockDim.x) bsm[e] = bias ? DT<T>::to_f(bias[e]) : 0.f;
@@ -155,10 +163,18 @@ __global__ void __launch_bounds__(256) conv_in_tiles_kernel(const T *__restrict_
     extern __shared__ float wsm[];   // same layout as conv_in_kernel
     const int K = 9 * Cin, OV = Cout / 8;
     const int pitch = conv_in_pitch(Cin);
-    for (int e = threadIdx.x; e < Cout * K; e += blockDim.x) {
-        const int co = e / K, k = e - co * K;
-        const int ci = k / 9, tap = k - ci * 9;
-        wsm[(co >> 3) * pitch + (tap * Cin + ci) * 8 + (co & 7)] = DT<T>::to_f(w[e]);
+    for (int e0 = threadIdx.x; e0 < Cout * K; e0 += blockDim.x * 8) {      // 8 coalesced loads in flight per thread
+        T v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int e = e0 + j * blockDim.x; v[j] = e < Cout * K ? w[e] : DT<T>::from_f(0.f); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = e0 + j * blockDim.x;
+            if (e >= Cout * K) break;
+            const int co = e / K, k = e - co * K;
+            const int ci = k / 9, tap = k - ci * 9;
+            wsm[(co >> 3) * pitch + (tap * Cin + ci) * 8 + (co & 7)] = DT<T>::to_f(v[j]);
+        }
     }
     float *bsm = wsm + OV * pitch;
     for (int e = threadIdx.x; e < Cout; e += blockDim.x) bsm[e] = bias ? DT<T>::to_f(bias[e]) : 0.f;
@@ -235,11 +251,22 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const T *__restrict__ x
 #pragma unroll
     for (int z = 0; z < 8; ++z) { s[z] = 0.f; q[z] = 0.f; }
     if (slot < slots) {
-        for (int p = p0 + slot; p < p1; p += slots) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(x + ((long long)b * HW + p) * C + cv * 8));
-            const T *e = reinterpret_cast<const T *>(&v);
+        constexpr int GB = 8;     // loads in flight per thread (same summation order as a plain loop)
+        for (int pb = p0 + slot; pb < p1; pb += slots * GB) {
+            uint4 v[GB];
 #pragma unroll
-            for (int z = 0; z < 8; ++z) { const float f = DT<T>::to_f(e[z]); s[z] += f; q[z] = fmaf(f, f, q[z]); }
+            for (int j = 0; j < GB; ++j) {
+                const int p = pb + j * slots;
+                v[j] = make_uint4(0, 0, 0, 0);
+                if (p < p1) v[j] = __ldg(reinterpret_cast<const uint4 *>(x + ((long long)b * HW + p) * C + cv * 8));
+            }
+#pragma unroll
+            for (int j = 0; j < GB; ++j) {
+                if (pb + j * slots >= p1) break;
+                const T *e = reinterpret_cast<const T *>(&v[j]);
+#pragma unroll
+                for (int z = 0; z < 8; ++z) { const float f = DT<T>::to_f(e[z]); s[z] += f; q[z] = fmaf(f, f, q[z]); }
+            }
         }
     }
     extern __shared__ float red[];   // [slots][C][2]
@@ -269,9 +296,20 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float *__restri
     pdl_acquire();
     if (sl < S) {
         double ss = 0.0, qq = 0.0;
-        for (int k = sl; k < nblk; k += S) {
-            const float *p = part + (((long long)b * nblk + k) * C + c) * 2;
-            ss += p[0]; qq += p[1];
+        constexpr int FB = 8;     // loads in flight per thread (same summation order as a plain loop)
+        for (int k0 = sl; k0 < nblk; k0 += S * FB) {
+            float2 v[FB];
+#pragma unroll
+            for (int j = 0; j < FB; ++j) {
+                const int k = k0 + j * S;
+                v[j] = make_float2(0.f, 0.f);
+                if (k < nblk) v[j] = *reinterpret_cast<const float2 *>(part + (((long long)b * nblk + k) * C + c) * 2);
+            }
+#pragma unroll
+            for (int j = 0; j < FB; ++j) {
+                if (k0 + j * S >= nblk) break;
+                ss += v[j].x; qq += v[j].y;
+            }
         }
         dsm[(sl * C + c) * 2] = ss; dsm[(sl * C + c) * 2 + 1] = qq;
     }
@@ -318,11 +356,25 @@ __global__ void __launch_bounds__(CO_TH * 32) conv_out_kernel(const T *__restric
     unsigned char *tile = smraw;                                             // [HP*WP][pitch]
     unsigned char *wsm = smraw + ((HP * WP * pitch + 15) & ~15);             // [8][wpitch]: B operand, row n = output channel
     const int b = blockIdx.z, ty0 = blockIdx.y * CO_TH, tx0 = blockIdx.x * CO_TW;
-    for (int e = threadIdx.x; e < 8 * K; e += blockDim.x) {
-        const int n = e / K, k = e - n * K;                                  // k = tap*C + ci
-        const int tap = k / C, ci = k - tap * C;
-        const T v = n < Cout ? w[((long long)n * C + ci) * 9 + tap] : DT<T>::from_f(0.f);
-        *reinterpret_cast<T *>(wsm + n * wpitch + k * 2) = v;
+    {
+        constexpr int WB = 8;     // weight elements in flight per thread (the staging is a chain of scattered 2-byte loads)
+        for (int e0 = threadIdx.x; e0 < 8 * K; e0 += blockDim.x * WB) {
+            T v[WB];
+#pragma unroll
+            for (int j = 0; j < WB; ++j) {
+                const int e = e0 + j * blockDim.x;
+                const int n = e / K, k = e - n * K;                          // k = tap*C + ci
+                const int tap = k / C, ci = k - tap * C;
+                v[j] = (e < 8 * K && n < Cout) ? w[((long long)n * C + ci) * 9 + tap] : DT<T>::from_f(0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < WB; ++j) {
+                const int e = e0 + j * blockDim.x;
+                if (e >= 8 * K) break;
+                const int n = e / K, k = e - n * K;
+                *reinterpret_cast<T *>(wsm + n * wpitch + k * 2) = v[j];
+            }
+        }
     }
     const int CV = C / 8;
     const bool pre = scale || shift || act != SIGE_ACT_IDENTITY;
@@ -338,19 +390,31 @@ __global__ void __launch_bounds__(CO_TH * 32) conv_out_kernel(const T *__restric
             sc[z] = scale ? __ldg(scale + (long long)b * C + cv * 8 + z) : 1.f;
             sh[z] = shift ? __ldg(shift + (long long)b * C + cv * 8 + z) : 0.f;
         }
-        for (int pp = threadIdx.x / CV; pp < HP * WP; pp += pstep) {
-            const int py = pp / WP, px = pp - py * WP;
-            const int hh = ty0 + py - 1, ww = tx0 + px - 1;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-                v = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)b * H + hh) * W + ww) * C + cv * 8));
-                if (pre) {
-                    T *el = reinterpret_cast<T *>(&v);
+        // loads are issued in batches of HB before any is consumed: one DRAM round trip per batch instead of per pixel
+        constexpr int HB = 8;
+        for (int pp0 = threadIdx.x / CV; pp0 < HP * WP; pp0 += pstep * HB) {
+            uint4 v[HB];
+            bool ok[HB];
+#pragma unroll
+            for (int j = 0; j < HB; ++j) {
+                const int pp = pp0 + j * pstep;
+                const int py = pp / WP, px = pp - py * WP;
+                const int hh = ty0 + py - 1, ww = tx0 + px - 1;
+                ok[j] = pp < HP * WP && hh >= 0 && hh < H && ww >= 0 && ww < W;
+                v[j] = make_uint4(0, 0, 0, 0);
+                if (ok[j]) v[j] = __ldg(reinterpret_cast<const uint4 *>(x + (((long long)b * H + hh) * W + ww) * C + cv * 8));
+            }
+#pragma unroll
+            for (int j = 0; j < HB; ++j) {
+                const int pp = pp0 + j * pstep;
+                if (pp >= HP * WP) break;
+                if (pre && ok[j]) {
+                    T *el = reinterpret_cast<T *>(&v[j]);
 #pragma unroll
                     for (int z = 0; z < 8; ++z) el[z] = DT<T>::from_f(activate<true>(act, fmaf(DT<T>::to_f(el[z]), sc[z], sh[z])));
                 }
+                *reinterpret_cast<uint4 *>(tile + pp * pitch + cv * 16) = v[j];   // zero padding AFTER the pre-op
             }
-            *reinterpret_cast<uint4 *>(tile + pp * pitch + cv * 16) = v;   // zero padding AFTER the pre-op
         }
     } else {
         for (int e = threadIdx.x; e < HP * WP * CV; e += blockDim.x) {
