@@ -286,12 +286,14 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const T *__restrict__ x
 template <typename T>
 __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float *__restrict__ part, int nblk, int HW, int C, int G, float eps,
                                                            const T *__restrict__ gamma, const T *__restrict__ beta,
-                                                           float *__restrict__ scale, float *__restrict__ shift) {
-    // grid = B, block = 1024 threads = S slices x C channels; fixed summation order -> deterministic
-    extern __shared__ double dsm[];   // [S][C][2]
-    const int b = blockIdx.x;
-    const int S = max(1, (int)blockDim.x / C);
-    const int c = threadIdx.x % C, sl = threadIdx.x / C;
+                                                           float *__restrict__ scale, float *__restrict__ shift, int CPB) {
+    // grid = (C / CPB, B): a CTA owns CPB channels (whole groups); block = 1024 threads = S slices x CPB channels;
+    // fixed summation order -> deterministic
+    extern __shared__ double dsm[];   // [S][CPB][2]
+    const int b = blockIdx.y, c0 = blockIdx.x * CPB;
+    const int S = max(1, (int)blockDim.x / CPB);
+    const int cl = threadIdx.x % CPB, sl = threadIdx.x / CPB;
+    const int c = c0 + cl;
     pdl_release();
     pdl_acquire();
     if (sl < S) {
@@ -311,19 +313,19 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float *__restri
                 ss += v[j].x; qq += v[j].y;
             }
         }
-        dsm[(sl * C + c) * 2] = ss; dsm[(sl * C + c) * 2 + 1] = qq;
+        dsm[(sl * CPB + cl) * 2] = ss; dsm[(sl * CPB + cl) * 2 + 1] = qq;
     }
     __syncthreads();
-    if (threadIdx.x < C) {
+    if (threadIdx.x < CPB) {
         double ss = 0.0, qq = 0.0;
-        for (int k = 0; k < S; ++k) { ss += dsm[(k * C + c) * 2]; qq += dsm[(k * C + c) * 2 + 1]; }
-        dsm[c * 2] = ss; dsm[c * 2 + 1] = qq;           // slice 0 row now holds the per-channel totals
+        for (int k = 0; k < S; ++k) { ss += dsm[(k * CPB + cl) * 2]; qq += dsm[(k * CPB + cl) * 2 + 1]; }
+        dsm[cl * 2] = ss; dsm[cl * 2 + 1] = qq;         // slice 0 row now holds the per-channel totals
     }
     __syncthreads();
-    if (threadIdx.x < C) {
-        const int per = C / G, g = c / per;
+    if (threadIdx.x < CPB) {
+        const int per = C / G, gl = cl / per;           // CPB is a multiple of the group size
         double ss = 0.0, qq = 0.0;
-        for (int k = 0; k < per; ++k) { ss += dsm[2 * (g * per + k)]; qq += dsm[2 * (g * per + k) + 1]; }
+        for (int k = 0; k < per; ++k) { ss += dsm[2 * (gl * per + k)]; qq += dsm[2 * (gl * per + k) + 1]; }
         const double n = (double)per * HW;
         const double mean = ss / n;
         double var = qq / n - mean * mean;
@@ -564,12 +566,15 @@ int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, i
     const size_t smem1 = sizeof(float) * (size_t)slots * C * 2;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 g1(nblk, B);
+    // finalize: 32 channels per CTA when that is a whole number of groups (4 CTAs x 32 slices for C = 128), else one CTA
+    const int per_group = C / groups;
+    const int cpb = (C % 32 == 0 && 32 % per_group == 0) ? 32 : C;
 #define SIGE_GN(T)                                                                                                                       \
     do {                                                                                                                                 \
         if (smem1 > 48 * 1024) cudaFuncSetAttribute(gn_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);        \
         launch_pdl(gn_partial_kernel<T>, g1, dim3(256), smem1, st, (const T *)x, HW, C, workspace, nblk);                                 \
-        launch_pdl(gn_finalize_kernel<T>, dim3(B), dim3(1024), sizeof(double) * 2 * C * (1024 / C > 0 ? 1024 / C : 1), st, (const float *)workspace, nblk, HW, \
-                   C, groups, eps, (const T *)gamma, (const T *)beta, scale, shift);                                                    \
+        launch_pdl(gn_finalize_kernel<T>, dim3(C / cpb, B), dim3(1024), sizeof(double) * 2 * cpb * (1024 / cpb > 0 ? 1024 / cpb : 1), st,            \
+                   (const float *)workspace, nblk, HW, C, groups, eps, (const T *)gamma, (const T *)beta, scale, shift, cpb);              \
     } while (0)
     switch (dtype) {
         case SIGE_F16: SIGE_GN(__half); break;
