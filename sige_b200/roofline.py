@@ -30,12 +30,12 @@ def peaks():
 
 
 def profiled_traffic():
-    """DRAM traffic of the dominant kernel from the committed ncu capture (profiles/r01e_tileconv_dram_traffic_step.csv:
+    """DRAM traffic of the dominant kernel from the committed ncu capture (profiles/r01j_tileconv_dram_traffic_step.csv:
     dram__bytes_read.sum + dram__bytes_write.sum of every fused tile-conv launch of one step), as average bytes per
     launch; None if the capture is absent."""
     import csv
 
-    path = os.path.join(_REPO, "profiles", "r01e_tileconv_dram_traffic_step.csv")
+    path = os.path.join(_REPO, "profiles", "r01j_tileconv_dram_traffic_step.csv")
     try:
         rows = [r for r in csv.reader(open(path)) if len(r) > 10]
         hdr = rows[0]
