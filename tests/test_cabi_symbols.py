@@ -62,3 +62,15 @@ def test_missing_library_is_loud(monkeypatch, tmp_path):
         assert "no CPU or PyTorch fallback" in str(e)
     else:
         raise AssertionError("expected SigeLibraryMissing")
+
+
+def test_attention_shape_predicate_is_pure_host_logic(cabi_lib):
+    """sige_attention_tokens_supported() never touches the device: the shapes the fused attention core takes
+    (64 keys per CTA, clusters of 1 / 2 / 4 key slices; 256 or 512 channels; 16-bit storage)."""
+    h = ctypes.CDLL(cabi_lib)
+    f = h.sige_attention_tokens_supported
+    f.restype, f.argtypes = ctypes.c_int, [ctypes.c_int] * 3
+    F32, F16, BF16 = 0, 1, 2
+    assert f(256, 512, F16) == 1 and f(64, 512, BF16) == 1 and f(128, 256, F16) == 1
+    assert f(256, 512, F32) == 0      # fp32 goes through the library path
+    assert f(100, 512, F16) == 0 and f(512, 512, F16) == 0 and f(256, 192, F16) == 0 and f(0, 512, F16) == 0
