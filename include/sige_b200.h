@@ -256,7 +256,7 @@ int sige_group_norm_fold(const void *x, int dtype, int B, int H, int W, int C, i
 int sige_conv_out_nhwc(const void *x, const float *scale, const float *shift, int act, const void *w,
                        const void *bias, void *out, int dtype, int B, int H, int W, int C, int Cout,
                        sige_stream_t stream);
-/* Dense single-head attention core of the DDPM AttnBlock (reference diffusion/models/ddpm/sige_fused_unet.py:196-212,
+/* Dense single-head attention core of the DDPM AttnBlock (reference diffusion/models/ddpm_arch/sige_fused_unet.py:185-199,
  * the torch bmm / softmax / bmm between the qkv and proj_out 1x1 convolutions) on NHWC tokens:
  *   qkv [B][N][3C] = per pixel [q | k | v], q ALREADY multiplied by C^-0.5;  out [B][N][C] = softmax(q k^T) v.
  * N in {64, 128, 256} tokens, C in {256, 512}, f16 / bf16 (sige_attention_tokens_supported() tells).

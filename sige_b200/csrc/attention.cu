@@ -1,6 +1,6 @@
 // attention.cu — single-head dense attention core of the DDPM AttnBlock on NHWC tokens, one launch.
 //
-// Replaces the reference's torch ops in diffusion/models/ddpm/sige_fused_unet.py:196-212 (q·k^T · c^-0.5 → softmax →
+// Replaces the reference's torch ops in diffusion/models/ddpm_arch/sige_fused_unet.py:185-199 (q·k^T · c^-0.5 → softmax →
 // ·v) for the DENSE attention blocks (16x16 and 8x8 resolution: the reference never runs these tile-sparse).  The
 // tokens live in the NHWC qkv buffer the fused 1x1 conv just produced: row n = pixel n, [q | k | v] of C channels
 // each, q already scaled by c^-0.5 (folded into the conv's weights by the engine).

@@ -487,7 +487,7 @@ def attention_tokens_supported(n_tokens: int, channels: int, dtype: torch.dtype)
 
 def attention_tokens(qkv: torch.Tensor, out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
     """softmax(q k^T) v on tokens: qkv [B, N, 3C] contiguous = per token [q | k | v] with q pre-scaled by C^-0.5
-    (reference sige_fused_unet.py:196-212); returns [B, N, C]."""
+    (reference sige_fused_unet.py:185-199); returns [B, N, C]."""
     _require_cuda(qkv, out)
     assert qkv.dim() == 3 and qkv.is_contiguous() and qkv.shape[2] % 3 == 0
     B, N, C3 = qkv.shape

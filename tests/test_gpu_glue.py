@@ -53,7 +53,7 @@ def test_group_norm_fold_and_conv_out(dtype, tol):
 @pytest.mark.parametrize("N,C", [(256, 512), (64, 512), (128, 512), (128, 256), (256, 256), (64, 256)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_attention_tokens_matches_fp32_softmax(N, C, dtype):
-    """The fused attention core (reference sige_fused_unet.py:196-212: bmm, softmax, bmm) vs plain fp32 torch on the same
+    """The fused attention core (reference sige_fused_unet.py:185-199: bmm, softmax, bmm) vs plain fp32 torch on the same
     16-bit inputs.  Logit scale ~ N(0, 2) gives a peaked softmax, so the cluster's flash-style combine is exercised."""
     from sige_b200 import ops
 
