@@ -235,6 +235,17 @@ int sige_tile_conv_generic(const void *x, const void *w, const void *bias, void 
 /*   reference diffusion/models/ddpm_arch/sige_fused_unet.py:395 (conv_in),    */
 /*   :431-433 (norm_out -> swish -> conv_out), models/common.py:37-57 (fold)   */
 /* ------------------------------------------------------------------------- */
+/* Launch plan sige_tile_conv would use for a descriptor: pure host logic (no pointer is dereferenced, nothing is
+ * launched) — exported so that the tile-width / split-K / ring heuristics can be tested without a GPU. */
+typedef struct {
+    int path;      /* 1 = tcgen05 kernel, 0 = mma.sync kernel (the fields below are then 0) */
+    int bn;        /* output channels per CTA (64 or 128) */
+    int ksplit;    /* K slices = thread-block cluster size (1, 2, 4, 8) */
+    int deep_ring; /* 1 = one halo buffer + five weight stages (split-K launches of the narrow 3x3 configuration) */
+    int grid_x, grid_y, grid_z;
+} sige_tile_conv_plan_t;
+int sige_tile_conv_plan(const sige_tile_conv_t *desc, sige_tile_conv_plan_t *plan);
+
 /* 3x3 / stride 1 / pad 1 convolution with Cin <= 4 (the RGB stem): x NHWC (B,H,W,Cin), w OIHW, out NHWC;
  * up to two extra outputs aux[i] = act(out*scale+shift) (NHWC, Cout channels). */
 int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out, int dtype, int B,

@@ -44,6 +44,11 @@ class ConvAux(Structure):
     _fields_ = [("ptr", c_void_p), ("C", c_int), ("c0", c_int), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int)]
 
 
+class TileConvPlan(ctypes.Structure):
+    _fields_ = [("path", ctypes.c_int), ("bn", ctypes.c_int), ("ksplit", ctypes.c_int), ("deep_ring", ctypes.c_int),
+                ("grid_x", ctypes.c_int), ("grid_y", ctypes.c_int), ("grid_z", ctypes.c_int)]
+
+
 class TileConv(Structure):
     _fields_ = [
         ("dtype", c_int),
@@ -91,6 +96,7 @@ PROTOTYPES = {
     "sige_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "sige_tile_conv": (_I, [POINTER(TileConv), _P]),
     "sige_tile_conv_generic": (_I, [_P, _P, _P, _P] + [_I] * 14 + [_P]),
+    "sige_tile_conv_plan": (_I, [_P, _P]),
     "sige_conv_in_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "sige_conv_in_nhwc_tiles": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
     "sige_group_norm_fold_workspace": (_I, [_I, _I]),

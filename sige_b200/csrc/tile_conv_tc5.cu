@@ -803,26 +803,42 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// Launch plan of one layer: tile width, K split and ring flavour.  Pure host logic (exported as sige_tile_conv_plan so
+// that it can be tested without a GPU).
+struct Plan {
+    int bn, ksplit, deep;
+};
+
+static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int ksplit_req) {
+    Plan pl;
+    const long long m_blocks = ceil_div(NT, TILES);
+    // BN = 128 only when that still leaves enough CTAs; small problems want more, narrower CTAs
+    const bool wide = (Cout % 128 == 0) && (m_blocks * (Cout / 128) >= 148);
+    pl.bn = wide ? 128 : 64;
+    const bool split_ok = pl.bn == 64;                       // Cfg::kSplitOk
+    const int tps = (taps == 9 && pl.bn == 64) ? 3 : 1;     // Cfg::TPS
+    const int J = (Cin / KC) * (taps / tps) + (taps == 9 ? Cin2 / KC : 0);        // ring steps
+    const long long base = m_blocks * (Cout / pl.bn);
+    int ks = ksplit_req;
+    if (ks <= 0) {
+        // one CTA per SM (214 KB smem): co-resident CTAs are 148 / 148 / 132 / 120 for cluster sizes 1 / 2 / 4 / 8
+        // (ncu 'Max Active Clusters': 74 x2, 15 x8); never spill into a second wave.  Splitting pays while every slice
+        // keeps >= min_taps taps (measured: 3 is best).
+        static const int kMaxCtas[9] = {0, 148, 148, 0, 132, 0, 0, 0, 120};
+        static int min_taps = getenv("SIGE_TC5_MIN_TAPS") ? atoi(getenv("SIGE_TC5_MIN_TAPS")) : 3;   // tuning knob (taps per K slice)
+        ks = 1;
+        while (split_ok && ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * tps) / (ks * 2) >= min_taps) ks *= 2;
+    }
+    if (ks > J || !split_ok) ks = 1;
+    pl.ksplit = ks;
+    static int deep_env = getenv("SIGE_TC5_DEEP") ? atoi(getenv("SIGE_TC5_DEEP")) : 1;   // A/B knob
+    pl.deep = (pl.bn == 64 && taps == 9 && ks > 1 && deep_env) ? 1 : 0;
+    return pl;
+}
+
 template <typename T, int BN, int TAPS, bool DEEP = false>
 static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaStream_t st) {
     using C = Cfg<BN, TAPS, DEEP>;
-    const int J = (p.Cin / KC) * C::SPC + (TAPS == 9 ? p.Cin2 / KC : 0);        // ring steps
-    const long long base = (long long)ceil_div(p.NT, TILES) * (p.Cout / BN);
-    if (p.ksplit <= 0) {
-        // one CTA per SM (214 KB smem): co-resident CTAs are 148 / 148 / 132 / 120 for cluster sizes 1 / 2 / 4 / 8
-        // (ncu 'Max Active Clusters': 74 x2, 15 x8); never spill into a second wave.  Splitting only pays when the K loop
-        // is long: each slice should keep >= 8 (tap, chunk) steps.
-        static const int kMaxCtas[9] = {0, 148, 148, 0, 132, 0, 0, 0, 120};
-        static int min_taps = getenv("SIGE_TC5_MIN_TAPS") ? atoi(getenv("SIGE_TC5_MIN_TAPS")) : 3;   // tuning knob (taps per K slice)
-        int ks = 1;
-        while (C::kSplitOk && ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * C::TPS) / (ks * 2) >= min_taps) ks *= 2;
-        p.ksplit = ks;
-    }
-    if (p.ksplit > J || !C::kSplitOk) p.ksplit = 1;
-    if constexpr (BN == 64 && TAPS == 9 && !DEEP) {
-        static int deep_env = getenv("SIGE_TC5_DEEP") ? atoi(getenv("SIGE_TC5_DEEP")) : 1;   // A/B knob
-        if (p.ksplit > 1 && deep_env) return launch<T, BN, TAPS, true>(p, w_packed, w2_packed, st);
-    }
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("sige_tile_conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
@@ -951,16 +967,34 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.push_async = push_env;
     p.dealloc_late = late_env;
     p.trace = g_trace;
-    // BN = 128 only when that still leaves enough CTAs; small problems want more, narrower CTAs
-    const long long m_blocks = ceil_div(p.NT, tc5::TILES);
-    const bool wide = (a->Cout % 128 == 0) && (m_blocks * (a->Cout / 128) >= 148);
-    const bool three = p.taps == 9;
+    const tc5::Plan pl = tc5::decide(p.NT, p.Cin, p.Cout, p.taps, p.Cin2, a->ksplit);
+    p.ksplit = pl.ksplit;
+    const bool wide = pl.bn == 128, three = p.taps == 9;
 #define SIGE_TC5(T)                                                                              \
     (wide ? (three ? tc5::launch<T, 128, 9>(p, a->w_packed, a->w2_packed, st) : tc5::launch<T, 128, 1>(p, a->w_packed, a->w2_packed, st)) \
-          : (three ? tc5::launch<T, 64, 9>(p, a->w_packed, a->w2_packed, st) : tc5::launch<T, 64, 1>(p, a->w_packed, a->w2_packed, st)))
+          : (three ? (pl.deep ? tc5::launch<T, 64, 9, true>(p, a->w_packed, a->w2_packed, st) : tc5::launch<T, 64, 9>(p, a->w_packed, a->w2_packed, st)) \
+                   : tc5::launch<T, 64, 1>(p, a->w_packed, a->w2_packed, st)))
     if (a->dtype == SIGE_F16) return SIGE_TC5(__half);
     return SIGE_TC5(__nv_bfloat16);
 #undef SIGE_TC5
 }
 
 }  // namespace sige
+
+// Which kernel and grid sige_tile_conv would use for this descriptor (no pointer is dereferenced, nothing is launched).
+extern "C" int sige_tile_conv_plan(const sige_tile_conv_t *a, sige_tile_conv_plan_t *out) {
+    using namespace sige;
+    SIGE_REQUIRE(a && out, "sige_tile_conv_plan: null pointer");
+    out->path = 0; out->bn = 0; out->ksplit = 0; out->deep_ring = 0; out->grid_x = out->grid_y = out->grid_z = 0;
+    if (!((a->flags & SIGE_CONV_TC5) && tc5_supported(a))) return 0;      // mma.sync / CUDA-core paths
+    const long long NT = (long long)a->B * a->N;
+    const tc5::Plan pl = tc5::decide(NT, a->Cin, a->Cout, a->kH * a->kW, a->n_src2 > 0 ? a->Cin2 : 0, a->ksplit);
+    out->path = 1;
+    out->bn = pl.bn;
+    out->ksplit = pl.ksplit;
+    out->deep_ring = pl.deep;
+    out->grid_x = ceil_div(NT, tc5::TILES);
+    out->grid_y = a->Cout / pl.bn;
+    out->grid_z = pl.ksplit;
+    return 0;
+}

@@ -74,3 +74,68 @@ def test_attention_shape_predicate_is_pure_host_logic(cabi_lib):
     assert f(256, 512, F16) == 1 and f(64, 512, BF16) == 1 and f(128, 256, F16) == 1
     assert f(256, 512, F32) == 0      # fp32 goes through the library path
     assert f(100, 512, F16) == 0 and f(512, 512, F16) == 0 and f(256, 192, F16) == 0 and f(0, 512, F16) == 0
+
+
+def _conv_desc(n_tiles, cin, cout, k, *, stride=1, cin2=0, ksplit=0, res=64):
+    from sige_b200 import _cabi
+
+    d = _cabi.TileConv()
+    d.dtype = _cabi.F16
+    d.B, d.H, d.W = 1, res, res
+    d.n_src = 1
+    d.src[0].C, d.src[0].up = cin, 0
+    d.src_is_stack = 0
+    d.N = n_tiles
+    d.R = d.S = {(3, 1): 6, (1, 1): 4, (3, 2): 5}[(k, stride)]
+    d.Cin, d.Cout, d.kH, d.kW, d.stride = cin, cout, k, k, stride
+    d.dst_is_stack, d.dH, d.dW, d.dC = 0, res // stride, res // stride, cout
+    d.ksplit = ksplit
+    d.flags = _cabi.CONV_PDL | _cabi.CONV_TC5
+    if cin2:
+        d.n_src2, d.Cin2 = 1, cin2
+        d.src2[0].C = cin2
+    return d
+
+
+def test_tile_conv_launch_plan_heuristics(cabi_lib):
+    """sige_tile_conv_plan: the host-side choice of tile width, split-K (= cluster size) and ring flavour of the tcgen05
+    kernel, on the layer shapes of a DDPM-256 step.  Invariants: one wave only (148 / 148 / 132 / 120 co-resident CTAs
+    for cluster sizes 1 / 2 / 4 / 8), every K slice non-empty, deep ring exactly for split narrow 3x3 launches."""
+    from sige_b200 import _cabi
+
+    lib = _cabi.lib()
+    cap = {1: 148, 2: 148, 4: 132, 8: 120}
+
+    def plan(d):
+        p = _cabi.TileConvPlan()
+        assert lib.sige_tile_conv_plan(ctypes.byref(d), ctypes.byref(p)) == 0
+        return p
+
+    # known points (1.2 % edit: 64 tiles at 256^2 ... 4 tiles at 8^2)
+    p = plan(_conv_desc(4, 512, 512, 3))
+    assert (p.path, p.bn, p.ksplit, p.deep_ring, p.grid_x, p.grid_y, p.grid_z) == (1, 64, 8, 1, 1, 8, 8)
+    p = plan(_conv_desc(16, 512, 512, 3))
+    assert (p.bn, p.ksplit, p.deep_ring, p.grid_x * p.grid_y * p.grid_z) == (64, 4, 1, 64)
+    p = plan(_conv_desc(64, 128, 128, 3, res=256))
+    assert (p.bn, p.ksplit, p.deep_ring) == (64, 4, 1)
+    p = plan(_conv_desc(1296, 128, 128, 3, res=256))        # 30 % edit: wide tiles, no split
+    assert (p.bn, p.ksplit, p.deep_ring, p.grid_x) == (128, 1, 0, 162)
+    p = plan(_conv_desc(16, 512, 1536, 1))                  # qkv of the 16x16 attention block
+    assert p.path == 1 and p.bn == 64 and p.ksplit in (1, 2) and p.deep_ring == 0
+    assert plan(_conv_desc(16, 256, 256, 3, stride=2)).path == 0      # stride-2 downsample: mma.sync kernel
+    assert plan(_conv_desc(16, 96, 128, 3)).path == 0                  # Cin not a multiple of 64
+    assert plan(_conv_desc(4, 512, 512, 3, ksplit=2)).ksplit == 2      # an explicit request is honoured
+    # sweep
+    for n_tiles in (1, 4, 13, 16, 32, 64, 100, 256, 1296, 4096):
+        for cin, cout in ((128, 128), (128, 256), (256, 256), (512, 512), (1024, 512), (768, 256)):
+            for k in (1, 3):
+                for cin2 in ((0, cin) if k == 3 else (0,)):
+                    p = plan(_conv_desc(n_tiles, cin, cout, k, cin2=cin2, res=256))
+                    assert p.path == 1 and p.bn in (64, 128) and p.ksplit in cap
+                    ctas = p.grid_x * p.grid_y * p.grid_z
+                    assert p.grid_x == (n_tiles + 7) // 8 and p.grid_y == cout // p.bn and p.grid_z == p.ksplit
+                    if p.ksplit > 1:
+                        assert ctas <= cap[p.ksplit] and p.bn == 64
+                    steps = (cin // 64) * (k * k // (3 if (k == 3 and p.bn == 64) else 1)) + cin2 // 64
+                    assert p.ksplit <= steps
+                    assert p.deep_ring == int(p.bn == 64 and k == 3 and p.ksplit > 1)
