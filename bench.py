@@ -206,6 +206,12 @@ def cpu_reference_subprocess(ratio: float, steps: int, warmup: int, timeout: int
     return best
 
 
+def workload_name(ratio: float) -> str:
+    """The same workload label on both arms (BASELINE.json configs[1] at the default ratio)."""
+    return ("DDPM U-Net 256x256 (ch128, mult 1-1-2-2-4-4), %.1f%% centred-square edit (%d px), sparse step, random-init weights"
+            % (100 * ratio, int(round((ratio ** 0.5) * 256))))
+
+
 def run_reference(args):
     rank = _env_int("RANK", 0)
     if rank != 0:
@@ -220,8 +226,8 @@ def run_reference(args):
         "impl": "reference", "metric": "DDPM 256x256 denoising steps/sec @1.2% edit", "value": r["value"], "unit": "steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DDPM U-Net 256x256, %.1f%% centred-square edit, sparse step, random-init weights" % (100 * args.ratio),
-                   "device": "cpu"},
+        "config": {"workload": workload_name(args.ratio), "device": "cpu",
+                   "edits_per_gpu": 0, "parallelism": "the reference's CPU flow on the host cores (rank 0 only)"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "thread_sweep")},
         "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -388,8 +394,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
             "config": {
-                "workload": "DDPM U-Net 256x256 (ch128, mult 1-1-2-2-4-4), %.1f%% centred-square edit (28 px), sparse step, random-init weights"
-                            % (100 * args.ratio),
+                "workload": workload_name(args.ratio),
                 "path": path, "edits_per_gpu": 1, "parallelism": "edits sharded 1/GPU, caches broadcast once (%d bytes), no per-step collective" % nbytes,
                 "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                 "timing": "per-step CUDA events on the launching stream, max over ranks",
