@@ -167,3 +167,44 @@ def test_oracle_against_compiled_reference(oracle, ref_cpu):
             a = oracle.scatter_gather(xs, x, bs, bs, idx, m1, sc, sh, "swish", False)
             b = ref_cpu.scatter_gather(t(xs), t(x), bs, bs, t(idx), t(m2), t(sc), t(sh), "swish", False).numpy()
             assert np.array_equal(a, b)
+
+
+def test_block_residual_and_remaining_geometries_against_compiled_reference(oracle, ref_cpu):
+    """Second differential sweep vs the reference's compiled CPU backend: scatter_with_block_residual (reference
+    sige/cpu/scatter.cpp:41-68,111-135), the identity activation, wider channel counts, the SD down-sampling geometry
+    (k3 s2 p1: 5x5 tiles, offset 1) and empty index lists."""
+    if ref_cpu is None:
+        pytest.skip("oracle/_ref not present")
+    t = torch.from_numpy
+    rng = np.random.default_rng(23)
+    for trial in range(16):
+        B, C = int(rng.integers(1, 3)), [3, 36, 64, 128][trial % 4]
+        H, W = int(rng.integers(8, 26)), int(rng.integers(8, 26))
+        # main 3x3 tiles and the 1x1 shortcut's own tiles on the same mask (a ResBlock with Cin != Cout)
+        mask = rng.random((H, W)) < (0.0 if trial == 5 else 0.06)
+        idx0 = oracle.reduce_mask(mask, 6, 4, 1)
+        idx1 = oracle.reduce_mask(mask, 4, 4, 0)
+        N0, N1 = idx0.shape[0], idx1.shape[0]
+        x0 = rng.standard_normal((B * N0, C, 4, 4)).astype(np.float32)
+        x1 = rng.standard_normal((B * N1, C, 4, 4)).astype(np.float32)
+        y0 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        y1 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        a = oracle.scatter_with_block_residual(x0, y0, x1, y1, 1, 1, 1, 1, idx0, idx1)
+        b = ref_cpu.scatter_with_block_residual(t(x0), t(y0), t(x1), t(y1), 1, 1, 1, 1, t(idx0), t(idx1)).numpy()
+        assert np.array_equal(a, b)
+        # identity activation, no affine / scale only / shift only
+        x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        sc = rng.standard_normal((1, C, 1, 1)).astype(np.float32)
+        for (s_, h_) in ((None, None), (sc, None), (None, sc)):
+            a = oracle.gather(x, 6, 6, idx0, s_, h_, "identity", False)
+            b = ref_cpu.gather(t(x), 6, 6, t(idx0), None if s_ is None else t(s_), None if h_ is None else t(h_), "identity", False).numpy()
+            assert np.array_equal(a, b)
+        # SD down-sampling geometry: k3 s2 p1 -> 5x5 tiles, tile stride 4, offset 1, 2x2 outputs
+        idx2 = oracle.reduce_mask(mask, 5, 4, 1)
+        N2 = idx2.shape[0]
+        Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        xs = rng.standard_normal((B * N2, C, 2, 2)).astype(np.float32)
+        y = rng.standard_normal((B, C, Ho, Wo)).astype(np.float32)
+        a = oracle.scatter(xs, y, 1, 1, 2, 2, idx2, None)
+        b = ref_cpu.scatter(t(xs), t(y), 1, 1, 2, 2, t(idx2), None).numpy()
+        assert np.array_equal(a, b)
