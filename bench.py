@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """bench.py — DDPM 256x256 denoising steps/sec @ 1.2 % edit (BASELINE.json metric), B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--ratio 0.012]
-                    [--path engine|modules] [--no-flush]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cuda] [--ratio 0.012]
+                    [--path fused|modules] [--no-flush]
 
 One "step" = one SPARSE forward of the DDPM U-Net on the edited latent with pre-filled caches —
 what the reference's Runner.profile times (reference diffusion/runner.py:214-245).  Workload =
@@ -18,8 +18,16 @@ stream, with an L2 flush (256 MiB write) between steps outside the event bracket
 region sits between barrier + synchronize.  e2e = the same step through the public API with
 host buffers: pinned H2D copy of x_t and D2H copy of eps inside every timed step.
 
---impl reference: the reference's CPU flow (its sige/cpu kernels via oracle/_ref + oneDNN conv,
-the same model graph) on this box's host cores, rank 0 only.
+Our arm drives the reference's UNMODIFIED model file (baseline/_ref/diffusion/models/ddpm_arch/sige_fused_unet.py, a
+verbatim copy made by baseline/build_ref.py) on this repository's `sige` package through its public call
+`model(x, t)`; in sparse mode SIGEModel runs that forward as a fused step (sige_b200.fused).  When baseline/_ref did
+not travel, the in-tree restatement of the same architecture (sige_b200.workloads.ddpm) is used and
+`config.model_file` says so.
+
+--impl reference: the reference itself — its python package, its sige.cpu OpenMP kernels + oneDNN conv — on this
+box's host cores (baseline/run_reference.py in a child process), rank 0 only.
+--impl reference-cuda: the reference itself on the SAME GPU — its python package, its sige.cuda kernels recompiled for
+sm_100a + cuDNN, fp32 — i.e. what a user of the reference gets on a B200 today.
 """
 from __future__ import annotations
 
@@ -54,11 +62,15 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--ratio", type=float, default=0.012)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
-    ap.add_argument("--path", default="auto", choices=["auto", "engine", "modules"],
-                    help="engine = fused CUDA-graph step engine; modules = sige.nn operator modules (graph-captured)")
+    ap.add_argument("--path", default="fused", choices=["fused", "modules"],
+                    help="fused = model(x, t) as a traced, fused, graph-captured step (the default behaviour of SIGEModel); "
+                         "modules = the eager sige.nn operator modules, graph-captured")
+    ap.add_argument("--model", default="auto", choices=["auto", "reference", "intree"],
+                    help="reference = the reference's unmodified model file from baseline/_ref on this repo's sige.nn; "
+                         "intree = sige_b200.workloads.ddpm (same architecture, same weights)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -69,7 +81,6 @@ def parse():
     ap.add_argument("--dense-stem", action="store_true", help="engine: evaluate conv_in on the whole image even when only the active tiles are read")
     ap.add_argument("--no-fused-attention", action="store_true", help="engine: torch matmul/softmax instead of the fused attention-core kernel")
     ap.add_argument("--no-fuse-shortcut", action="store_true", help="engine: keep the 1x1 shortcut convs as separate launches")
-    ap.add_argument("--no-branches", action="store_true", help="engine: keep the 1x1 shortcut convs on the main stream (no parallel graph branch)")
     ap.add_argument("--no-pdl", action="store_true", help="engine: plain stream order between fused layers (default: programmatic dependent launch)")
     ap.add_argument("--ksplit", type=int, default=0, help="engine: force the split-K factor (0 = auto)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -144,18 +155,35 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_reference_steps(ratio: float, steps: int, warmup: int, threads: int = 0):
-    """Times the reference's CPU flow in THIS process (call it from a process that has not touched CUDA and
-    that was started with OMP_WAIT_POLICY=PASSIVE: two OpenMP runtimes — torch's and the one the reference
-    kernels link — otherwise spin against each other on a many-core host)."""
+def _reference_child(backend: str, ratio: float, steps: int, warmup: int, threads: int, timeout: float):
+    """One run of baseline/run_reference.py (the reference's own python + native backend) in a clean child process."""
+    import subprocess
+
+    sys.path.insert(0, os.path.join(REPO, "baseline"))
+    import loader
+
+    env = loader.reference_env(threads)
+    if backend == "cpu":
+        env["CUDA_VISIBLE_DEVICES"] = ""
+        if host_cores() > 32:   # many-core host: keep torch's and the reference kernels' OpenMP runtimes from spinning against each other
+            env.update(OMP_WAIT_POLICY="PASSIVE", GOMP_SPINCOUNT="0")
+    cmd = [sys.executable, os.path.join(REPO, "baseline", "run_reference.py"), "--backend", backend, "--steps", str(steps), "--warmup", str(warmup),
+           "--ratio", str(ratio)] + (["--threads", str(threads)] if threads else [])
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError("reference child failed: %s" % out.stderr.strip().splitlines()[-1:] )
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def cpu_reference_legacy(ratio: float, steps: int, warmup: int, threads: int):
+    """Fallback when baseline/_ref did not travel: the in-tree model graph on the reference's CPU kernels (oracle/_ref)
+    or the oracle port, in THIS process (call from a process that has not touched CUDA)."""
     import torch
 
     from oracle.cpu_runtime import ddpm_cpu_sparse_step
     from sige_b200.workloads.ddpm import DDPMConfig
 
-    cores = host_cores()
-    threads = threads or cores
-    step, kind = ddpm_cpu_sparse_step(DDPMConfig(), ratio, threads=threads)
+    step, kind = ddpm_cpu_sparse_step(DDPMConfig(), ratio, threads=threads or host_cores())
     try:
         for _ in range(warmup):
             step()
@@ -165,49 +193,55 @@ def cpu_reference_steps(ratio: float, steps: int, warmup: int, threads: int = 0)
         dt = time.perf_counter() - t0
     finally:
         step.close()
-    return {"value": steps / dt, "unit": "steps/s", "cores": threads, "host_cores": cores, "kind": kind,
-            "sample": "%d sparse DDPM-256 steps @%.1f%% edit after %d warm-up, %d torch threads, fp32, oneDNN conv + %s tile kernels"
-                      % (steps, 100 * ratio, warmup, torch.get_num_threads(), "reference sige/cpu (oracle/_ref)" if kind == "reference" else "oracle C port"),
-            "ms_per_step": 1e3 * dt / steps}
+    return {"steps_per_s": steps / dt, "ms_per_step": 1e3 * dt / steps, "threads": torch.get_num_threads(), "kind": kind}
 
 
-def cpu_reference_subprocess(ratio: float, steps: int, warmup: int, timeout: int = 170):
-    """Run the CPU reference leg in a clean child process; try a few thread counts (all host cores is not
-    the fastest on a 100+-core host for this small workload) and keep the best."""
-    import subprocess
+def cpu_reference_subprocess(ratio: float, steps: int, warmup: int, timeout: int = 170, threads: int = 0):
+    """The reference's CPU flow on this box's host cores: a short thread sweep (all host cores is not the fastest on a
+    100+-core host for this small workload), then the winning count re-timed on the full `steps`."""
+    sys.path.insert(0, os.path.join(REPO, "baseline"))
+    import loader
 
     cores = host_cores()
-    cands = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True)
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
-    if cores > 32:   # many-core host: keep the two OpenMP runtimes (torch's, the reference kernels') from spinning against each other
-        env.update(OMP_WAIT_POLICY="PASSIVE", GOMP_SPINCOUNT="0")
-    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
-        env.pop(k, None)
-    best, tried = None, []
     budget = time.time() + timeout
+    if not loader.available():
+        import subprocess
+
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--_cpu-child", "--threads", str(threads or min(cores, 32)),
+                              "--steps", str(steps), "--warmup", str(warmup), "--ratio", str(ratio)], env=env, capture_output=True, text=True, timeout=timeout)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+        return {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "host_cores": cores, "kind": r["kind"] if r["kind"] == "port" else "reference",
+                "timed_steps": steps, "ms_per_step": r["ms_per_step"],
+                "sample": "%d sparse DDPM-256 steps @%.1f%% edit, in-tree model graph on %s + oneDNN conv, fp32 (baseline/_ref absent)" % (steps, 100 * ratio, r["kind"])}
+    cands = [threads] if threads else sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True)
+    tried, best_t, best_v = [], None, 0.0
     for th in cands:
-        left = budget - time.time()
-        if left < 15:
+        if len(cands) == 1:
+            best_t = th
             break
-        probe = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--_cpu-child", "--threads", str(th),
-                 "--steps", str(steps if best is None else max(3, steps // 2)), "--warmup", str(warmup), "--ratio", str(ratio)]
+        left = budget - time.time()
+        if left < 40:
+            break
         try:
-            out = subprocess.run(probe, env=env, capture_output=True, text=True, timeout=min(left, 80)).stdout
-            r = json.loads(out.strip().splitlines()[-1])
+            r = _reference_child("cpu", ratio, max(3, steps // 4), 1, th, min(left - 20, 60))
         except Exception as e:  # noqa: BLE001
             tried.append({"threads": th, "error": type(e).__name__})
             continue
-        tried.append({"threads": th, "steps_per_s": r["value"]})
-        if best is None or r["value"] > best["value"]:
-            best = r
-    if best is None:
+        tried.append({"threads": th, "steps_per_s": r["steps_per_s"]})
+        if r["steps_per_s"] > best_v:
+            best_t, best_v = th, r["steps_per_s"]
+    if best_t is None:
         raise RuntimeError("cpu reference leg failed: %r" % (tried,))
-    best["thread_sweep"] = tried
-    return best
+    r = _reference_child("cpu", ratio, steps, warmup, best_t, max(30.0, budget - time.time()))
+    return {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "host_cores": cores, "kind": "reference", "timed_steps": r["steps"],
+            "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "thread_sweep": tried,
+            "sample": "%d sparse DDPM-256 steps @%.1f%% edit after %d warm-up: the reference's own python (sige.nn, sige_fused_unet.py) + its sige.cpu "
+                      "OpenMP kernels + oneDNN conv, fp32, %d threads (best of the sweep)" % (r["steps"], 100 * ratio, r["warmup"], r["threads"])}
 
 
 def workload_name(ratio: float) -> str:
-    """The same workload label on both arms (BASELINE.json configs[1] at the default ratio)."""
+    """The same workload label on every arm (BASELINE.json configs[1] at the default ratio)."""
     return ("DDPM U-Net 256x256 (ch128, mult 1-1-2-2-4-4), %.1f%% centred-square edit (%d px), sparse step, random-init weights"
             % (100 * ratio, int(round((ratio ** 0.5) * 256))))
 
@@ -216,21 +250,45 @@ def run_reference(args):
     rank = _env_int("RANK", 0)
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 40))
-    warm = max(1, min(args.warmup, 3))
     if args._cpu_child:
-        print(json.dumps(cpu_reference_steps(args.ratio, steps, warm, args.threads)), flush=True)
+        print(json.dumps(cpu_reference_legacy(args.ratio, max(1, args.steps), max(1, args.warmup), args.threads)), flush=True)
         return
-    r = cpu_reference_subprocess(args.ratio, steps, warm)
+    steps = max(1, min(args.steps, 40))          # each step is a bounded sample: the whole arm ends within a few minutes
+    warm = max(1, min(args.warmup, 5))
+    r = cpu_reference_subprocess(args.ratio, steps, warm, threads=args.threads)
     line = {
         "impl": "reference", "metric": "DDPM 256x256 denoising steps/sec @1.2% edit", "value": r["value"], "unit": "steps/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
+        "n_gpus": args.gpus, "steps": r["timed_steps"], "warmup": r.get("warmup", warm), "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.ratio), "device": "cpu",
                    "edits_per_gpu": 0, "parallelism": "the reference's CPU flow on the host cores (rank 0 only)"},
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "thread_sweep")},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "host_cores", "kind", "sample", "thread_sweep") if k in r},
         "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_cuda(args):
+    """The reference's own CUDA path (sige.cuda for sm_100a + cuDNN, fp32, its unmodified python) on GPU 0 of this box."""
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(REPO, "baseline"))
+    import loader
+
+    if not loader.available(cuda=True):
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "baseline/_ref/sige/cuda.so absent (run baseline/build_ref.py where /root/reference exists)"}), flush=True)
+        return
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    r = _reference_child("cuda", args.ratio, steps, warm, 0, 600)
+    line = {
+        "impl": "reference-cuda", "metric": "DDPM 256x256 denoising steps/sec @1.2% edit", "value": r["steps_per_s"], "unit": "steps/s",
+        "n_gpus": 1, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "device_ms_per_step": r["device_ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cuDNN TF32 allowed: %s — torch default)" % r["tf32"], "data": "synthetic",
+        "config": {"workload": workload_name(args.ratio), "device": r["gpu"], "path": "reference sige.nn + sige.cuda (sm_100a rebuild) + cuDNN, eager, NCHW",
+                   "timing": "the reference's Runner.profile protocol: synchronize after every forward, wall clock"},
+        "e2e": {"value": r["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -238,13 +296,35 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def build_model(cfg, which: str):
+    """(model, label): the reference's unmodified model file on this repo's sige.nn when baseline/_ref is present."""
+    import warnings
+
+    from sige_b200.workloads.ddpm import SIGEDDPMUNet, init_deterministic
+
+    sys.path.insert(0, os.path.join(REPO, "baseline"))
+    import loader
+
+    use_ref = which == "reference" or (which == "auto" and loader.available())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if use_ref:
+            model = loader.reference_ddpm_on_this_repo(cfg)
+            label = "baseline/_ref/diffusion/models/ddpm_arch/sige_fused_unet.py (the reference's file, unmodified) on this repo's sige.nn"
+        else:
+            model = SIGEDDPMUNet(cfg)
+            label = "sige_b200/workloads/ddpm.py (in-tree restatement of the same architecture; baseline/_ref absent)"
+        model = init_deterministic(model, seed=0).eval()
+    return model, label
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from sige_b200 import ops
     from sige_b200.masks import downsample_mask
-    from sige_b200.workloads.ddpm import DDPMConfig, SIGEDDPMUNet, init_deterministic, synthetic_inputs
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
 
     rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -259,27 +339,16 @@ def run_ours(args):
     cfg = DDPMConfig()
     torch.backends.cudnn.benchmark = True
 
-    import warnings
-
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        model = init_deterministic(SIGEDDPMUNet(cfg), seed=0).eval().to(dev).to(dtype).to(memory_format=torch.channels_last)
+    model, model_label = build_model(cfg, args.model)
+    model = model.to(dev).to(dtype).to(memory_format=torch.channels_last)
     # every rank edits the SAME original image with its OWN edit (seed + rank)
     x0, x1, mask, t = synthetic_inputs(cfg, args.ratio, seed=0, edit_seed=rank)
     fmt = torch.channels_last
     x0d = x0.to(dev).to(dtype).contiguous(memory_format=fmt)
     td = t.to(dev)
-
     path = args.path
-    if path == "auto":
-        try:
-            from sige_b200 import engine as _engine  # noqa: F401
 
-            path = "engine" if getattr(_engine, "AVAILABLE", False) else "modules"
-        except Exception:  # noqa: BLE001
-            path = "modules"
-
-    log("model built; dense pass on the original image")
+    log("model built (%s); dense pass on the original image" % model_label)
     with torch.no_grad():
         model.set_mode("full")
         model(x0d, td)                       # every rank records shapes; rank 0's caches are authoritative
@@ -292,56 +361,70 @@ def run_ours(args):
         model.set_masks(downsample_mask(mask.to(dev), min_res=8))
         model.set_mode("sparse")
 
-    log("masks set; building the step runner (path=%s)" % path)
-    x_host = x1.to(dtype).contiguous(memory_format=fmt).pin_memory()
-    x_dev = torch.empty_like(x_host, device=dev)
-    x_dev.copy_(x_host)
+    log("masks set; building the step (path=%s)" % path)
+    x_host = x1.to(dtype).contiguous().pin_memory()
+    x_dev = x_host.to(dev)
     out_host = torch.empty((1, cfg.out_ch, cfg.image_size, cfg.image_size), dtype=dtype).pin_memory()
+    use_graph = not (args.no_graph or args.ncu)
 
-    if path == "engine":
-        from sige_b200.engine import DDPMStepEngine
+    if path == "fused":
+        model.set_fused(True, use_graph=use_graph, pdl=not args.no_pdl, ksplit=args.ksplit, tc5=not args.no_tc5, producer_preop=not args.no_producer_preop,
+                        fuse_shortcut=not args.no_fuse_shortcut, fused_attention=not args.no_fused_attention, sparse_stem=not args.dense_stem)
+        with torch.no_grad():
+            model(x_dev, td)                 # first sparse call: trace -> lower -> capture
+        runner = model.fused_step
+        if runner is None:
+            raise SystemExit("bench.py: the model did not run as a fused step")
+        log("fused step: %d fused conv launches, %d steps, eager nodes: %s" % (len(runner.fused), len(runner.steps), runner.eager_nodes or "none"))
 
-        runner = DDPMStepEngine(model, x_dev, use_graph=not (args.no_graph or args.ncu), pdl=not args.no_pdl, ksplit=args.ksplit, tc5=not args.no_tc5, producer_preop=not args.no_producer_preop, branches=not args.no_branches, fuse_shortcut=not args.no_fuse_shortcut, fused_attention=not args.no_fused_attention, sparse_stem=not args.dense_stem)
+        def step(x):
+            return model(x, td)              # the public call: copy-in, graph replay, copy-out
     else:
         from sige_b200.graphs import GraphedStep
 
-        runner = GraphedStep(model, x_dev, td, use_graph=not (args.no_graph or args.ncu))
+        model.set_fused(False)
+        runner = GraphedStep(model, x_dev, td, use_graph=use_graph)
+
+        def step(x):
+            if x is not runner.x:
+                runner.x.copy_(x, non_blocking=True)
+            return runner.replay()
     launches_per_step = runner.launches_per_step
-    out_dev = runner.output
 
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
     if args.ncu:
-        for _ in range(max(3, args.warmup)):
-            runner.replay()
-        torch.cuda.synchronize()
-        n_prof = 1          # one step is the unit of every committed capture; ncu replays each kernel ~40 times under --set full
-        torch.cuda.profiler.start()
-        for i in range(n_prof):
+        with torch.no_grad():
+            for _ in range(max(3, args.warmup)):
+                step(x_dev)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
             if flush is not None:
-                flush.fill_(i & 0xFF)
-            runner.replay()
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-        log("profiled %d eager step(s) (%d launches of our kernels per step)" % (n_prof, launches_per_step))
+                flush.fill_(1)
+            step(x_dev)                      # one step is the unit of every committed capture; ncu replays each kernel ~40 times under --set full
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        log("profiled 1 eager step (%d launches of our kernels per step)" % launches_per_step)
         return
 
     def timed_steps(k, e2e):
         total = 0.0
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
-        for i in range(k):
-            if flush is not None:
-                flush.fill_(i & 0xFF)
-            evs[i][0].record(stream)
-            if e2e:
-                x_dev.copy_(x_host, non_blocking=True)
-            out = runner.replay()
-            if e2e:
-                out_host.copy_(out, non_blocking=True)
-            evs[i][1].record(stream)
-            if e2e:
-                evs[i][1].synchronize()      # the caller consumes eps before issuing the next step
+        with torch.no_grad():
+            for i in range(k):
+                if flush is not None:
+                    flush.fill_(i & 0xFF)
+                evs[i][0].record(stream)
+                if e2e:
+                    x = x_host.to(dev, non_blocking=True)       # this step's input arrives from pinned host memory
+                    out = step(x)
+                    out_host.copy_(out, non_blocking=True)      # ... and its result goes back
+                else:
+                    out = step(x_dev)
+                evs[i][1].record(stream)
+                if e2e:
+                    evs[i][1].synchronize()      # the caller consumes eps before issuing the next step
         torch.cuda.synchronize()
         for a, b in evs:
             total += a.elapsed_time(b)
@@ -379,7 +462,7 @@ def run_ours(args):
         try:
             from sige_b200 import roofline
 
-            roof = roofline.measure_engine(runner, flush) if path == "engine" else roofline.measure_dominant_kernel(model, dtype, flush)
+            roof = roofline.measure_engine(runner, flush) if path == "fused" else roofline.measure_dominant_kernel(model, dtype, flush)
         except Exception as e:  # noqa: BLE001
             roof = {"error": repr(e)}
         log("roofline done")
@@ -394,8 +477,9 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
             "config": {
-                "workload": workload_name(args.ratio),
-                "path": path, "edits_per_gpu": 1, "parallelism": "edits sharded 1/GPU, caches broadcast once (%d bytes), no per-step collective" % nbytes,
+                "workload": workload_name(args.ratio), "model_file": model_label,
+                "path": path + (" (model(x, t) -> SIGEModel fused step: traced, lowered, CUDA graph)" if path == "fused" else ""),
+                "edits_per_gpu": 1, "parallelism": "edits sharded 1/GPU, caches broadcast once (%d bytes), no per-step collective" % nbytes,
                 "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                 "timing": "per-step CUDA events on the launching stream, max over ranks",
             },
@@ -416,6 +500,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda(args)
     else:
         run_ours(args)
 

@@ -6,7 +6,8 @@ gather -> conv -> scatter hot path behind the reference's operator surface.
     sige_b200.masks    reduce_mask / dilate_mask / compute_difference_mask / downsample_mask
                        (reference sige/utils.py)
     sige_b200.ops      torch-facing wrappers of the C-ABI (include/sige_b200.h)
-    sige_b200.engine   fused, CUDA-graph-captured DDPM step built from the same kernels
+    sige_b200.lazy     deferred execution: one forward recorded on lazy tensor handles
+    sige_b200.fused    that tape lowered to one fused launch per layer + CUDA graph (what SIGEModel runs in sparse mode)
 
 ``import sige`` (the thin alias package at the repo root) exposes the same objects under the
 reference's module paths, so unmodified model files keep working.

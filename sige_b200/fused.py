@@ -1,0 +1,1501 @@
+"""Fused step: an UNMODIFIED model forward, traced once, executed as one fused sm_100a launch per layer.
+
+``FusedStep(model, x, *more)`` runs ``model.forward`` once on lazy handles (``sige_b200.lazy``) in sparse
+mode, lowers the recorded tape to a short program of launches and captures it in a CUDA graph.  The model is
+any ``sige.nn.SIGEModel`` — the reference's own ``diffusion/models/ddpm_arch/sige_fused_unet.py`` drops in
+unmodified (tests/test_gpu_reference_model.py); nothing here looks at model classes, only at the calls the
+forward makes.
+
+What the lowering recognises (everything else runs as an eager torch node inside the same graph, so any
+traceable forward stays correct):
+
+  Gather -> SIGEConv2d / nn.Conv2d -> Scatter          one ``sige_tile_conv`` launch: gather (+GroupNorm affine,
+  (reference sige_fused_unet.py:100-131, 212-248)      +SiLU) -> tcgen05 conv -> (+bias, +residual) -> in-place
+                                                        scatter into a persistent NHWC buffer initialised from the
+                                                        module's cache (the reference's sparse_update form,
+                                                        sige/nn/scatter.py:59-60: no clone)
+  ... -> ScatterGather -> SIGEConv2d                    free: conv2 gathers from the buffer conv1 scattered into
+  ScatterWithBlockResidual                              the 1x1 shortcut rides in conv2's launch as extra K chunks
+  (sige/cuda/scatter_kernel.cu:46-74)                   (fresh where its own tile is active, cached elsewhere)
+  torch.cat / F.interpolate(nearest, x2) / F.pad        folded into the consumer's gather stage (channel segments,
+  (sige_fused_unet.py:423, :223, :244)                  half-resolution addressing, zero halo) — never materialised
+  x*scale+shift, x*sigmoid(x), F.silu                   folded into the consumer conv's pre-op (written once by the
+  (sige_fused_unet.py:112-123)                          PRODUCER's epilogue when it can, else applied in the gather)
+  nn.Conv2d on a full tensor (dense low-res blocks)     the same kernel with an all-tiles index list; `+ x` and the
+                                                        1x1 shortcut of a dense block join the conv's launch
+  split/reshape/bmm/softmax/bmm attention core          ``sige_attention_tokens`` (one launch), c^-0.5 folded into
+  (sige_fused_unet.py:185-199)                          the q rows of the qkv weights
+  conv on the <=4-channel input image                   ``sige_conv_in_nhwc`` (restricted to the active tiles when
+                                                        every reader gathers it through one index set)
+  GroupNorm -> SiLU -> conv to <=8 channels             ``sige_group_norm_fold`` + ``sige_conv_out_nhwc``
+
+Numerics: the same formulas as the operator-module path; the only reassociations are fp32 FMA for the affine, the
+1x1 shortcut evaluated on every main tile whose shortcut tile is active instead of being patched by (fresh - cached),
+and scalar / per-channel affines in front of a 1x1 conv folded exactly into its weights.
+
+The executor is injected: ``CudaExecutor`` (libsige_b200.so through ``sige_b200.ops``) is the product; tests
+inject a CPU simulator of the launch descriptors to check the lowering without a GPU.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import lazy
+from .lazy import LazyTensor, Node, TraceUnsupported
+
+
+# =====================================================================================================================
+# program objects
+# =====================================================================================================================
+class Buf:
+    """One activation of the step: an NHWC tensor (allocated on first request) plus pre-transformed views
+    act(raw*scale+shift) that its PRODUCER writes for each consumer (so that consumers gather plain bytes)."""
+
+    def __init__(self, owner: "Lowering", shape, cached_init: Optional[torch.Tensor] = None, raw: Optional[torch.Tensor] = None):
+        self.owner = owner
+        self.shape = tuple(int(s) for s in shape)            # (B, C, H, W)
+        self.cached_init = cached_init                        # pristine values when only active tiles are rewritten per step
+        self._raw = raw
+        self.producers: List = []                             # objects with .can_aux() / .add_aux(view, scale, shift, act)
+        self.readers: List = []                               # (idx, block, up) of fused launches reading it; None = a dense read
+        self.views: Dict = {}
+
+    @property
+    def raw(self) -> torch.Tensor:
+        if self._raw is None:
+            if self.cached_init is not None:
+                self._raw = self.owner.clone_cache(self.cached_init)
+            else:
+                self._raw = self.owner.empty(*self.shape)
+        return self._raw
+
+    @property
+    def has_raw(self) -> bool:
+        return self._raw is not None
+
+
+class ConvSpec:
+    """Everything one fused gather->conv->scatter launch needs, as tensors (the executor turns it into a descriptor)."""
+
+    def __init__(self):
+        self.name = ""
+        self.srcs: List[Tuple[torch.Tensor, int]] = []       # (NHWC tensor, upsample flag); or the stack when src_is_stack
+        self.src_is_stack = False
+        self.B = 1
+        self.H = self.W = 0
+        self.idx: Optional[torch.Tensor] = None
+        self.N = 0
+        self.block = 0
+        self.scale: Optional[torch.Tensor] = None            # fp32 [Cin] or [B, Cin]
+        self.shift: Optional[torch.Tensor] = None
+        self.per_sample_affine = False
+        self.act = "identity"
+        self.weight: Optional[torch.Tensor] = None           # fp32 OIHW (after exact folds)
+        self.bias: Optional[torch.Tensor] = None             # fp32 [Cout] or None
+        self.weight_key = None                               # cache key of the packed form
+        self.out_row_scale: Optional[Tuple[int, float]] = None
+        self.k = 1
+        self.stride = 1
+        self.off = 0
+        self.dst: Optional[Buf] = None
+        self.dst_stack: Optional[torch.Tensor] = None        # destination is a tile stack (B*N, Cout, Ro, So) NHWC
+        self.residual: Optional[torch.Tensor] = None
+        self.aux: List[Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], str]] = []
+        self.shortcut = None                                 # (src tensors, weight fp32 OI11, bias fp32, flags uint8 [N] or None)
+        self.pdl = False
+        self.tc5 = False
+        self.ksplit = 0
+
+    @property
+    def Cin(self) -> int:
+        return int(self.weight.shape[1])
+
+    @property
+    def Cout(self) -> int:
+        return int(self.weight.shape[0])
+
+
+class FusedConv:
+    """One prepared ``sige_tile_conv`` launch (prepared by the executor at finalize time)."""
+
+    trace_hook = None        # development aid (tools/trace_graph.py)
+
+    def __init__(self, spec: ConvSpec):
+        self.spec = spec
+        self.name = spec.name
+        self.launch_fn: Optional[Callable[[int], None]] = None
+        self.desc = None
+        self.keep: List = []
+
+    def can_aux(self) -> bool:
+        return len(self.spec.aux) < 2
+
+    def add_aux(self, view: torch.Tensor, scale, shift, act: str) -> None:
+        self.spec.aux.append((view, scale, shift, act))
+
+    def launch(self, stream: int) -> None:
+        if FusedConv.trace_hook is not None:
+            FusedConv.trace_hook(self)
+        self.launch_fn(stream)
+
+    # ---- accounting (algorithmic bytes / flops of one fused launch)
+    @property
+    def tiles(self) -> int:
+        return self.spec.B * self.spec.N
+
+    @property
+    def out_elems(self) -> int:
+        s = self.spec
+        ro = (s.block - s.k) // s.stride + 1
+        return s.B * s.N * s.Cout * ro * ro
+
+    @property
+    def bytes(self) -> int:
+        s = self.spec
+        n = s.B * s.N
+        dsts = (1 if (s.dst is not None and s.dst.has_raw) or s.dst_stack is not None else 0) + (1 if s.residual is not None else 0) + len(s.aux)
+        b = 2 * (n * s.Cin * s.block * s.block + s.k * s.k * s.Cout * s.Cin + self.out_elems * dsts)
+        if s.shortcut is not None:
+            c2 = int(s.shortcut[1].shape[1])
+            b += 2 * (n * c2 * 16 + s.Cout * c2)
+        return b
+
+    @property
+    def flops(self) -> int:
+        s = self.spec
+        ro = (s.block - s.k) // s.stride + 1
+        f = 2 * s.B * s.N * ro * ro * s.Cout * s.Cin * s.k * s.k
+        if s.shortcut is not None:
+            f += 2 * s.B * s.N * ro * ro * s.Cout * int(s.shortcut[1].shape[1])
+        return f
+
+
+class ConvInRec:
+    """conv_in launch record (<=4-channel stem) with up to two transformed extra outputs."""
+
+    def __init__(self, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Buf):
+        self.x, self.weight, self.bias, self.out = x, weight, bias, out
+        self.aux: List = []
+        self.tiles: Optional[torch.Tensor] = None   # tile origins when every reader gathers the stem through ONE index set
+        self.tile_size = 6
+
+    def can_aux(self) -> bool:
+        return len(self.aux) < 2
+
+    def add_aux(self, view, scale, shift, act) -> None:
+        self.aux.append((view, scale, shift, act))
+
+
+# =====================================================================================================================
+# executors
+# =====================================================================================================================
+_PACKED: Dict = {}       # packed weights survive re-compilation (new masks, same weights)
+
+
+class CudaExecutor:
+    """The product path: every launch goes through libsige_b200.so (sige_b200.ops).  No fallback."""
+
+    name = "cuda"
+
+    def __init__(self, device: torch.device, dtype: torch.dtype):
+        from . import ops
+
+        self.ops, self.device, self.dtype = ops, device, dtype
+
+    def _pack(self, w: torch.Tensor, key) -> torch.Tensor:
+        if key is not None and key in _PACKED:
+            return _PACKED[key]
+        wp = self.ops.pack_conv_weight(w.contiguous(), self.dtype)
+        if key is not None:
+            _PACKED[key] = wp
+        return wp
+
+    def prepare_conv(self, fc: FusedConv) -> None:
+        ops = self.ops
+        from ._cabi import CONV_PDL, CONV_TC5
+
+        s = fc.spec
+        w, b = s.weight, s.bias
+        key = s.weight_key
+        if s.out_row_scale is not None:
+            rows, f = s.out_row_scale
+            w = w.clone()
+            w[:rows] *= f
+            if b is not None:
+                b = b.clone()
+                b[:rows] *= f
+            key = None if key is None else key + (("rows", rows, f),)
+        wp = self._pack(w, key)
+        b32 = None if b is None else b.float().contiguous()
+        d = ops.tile_conv_descriptor()
+        d.dtype = ops._DTYPES[self.dtype]
+        d.n_src = len(s.srcs)
+        for i, (t, up) in enumerate(s.srcs):
+            d.src[i].ptr, d.src[i].C, d.src[i].up = t.data_ptr(), t.shape[1], up
+        d.B, d.H, d.W = s.B, s.H, s.W
+        d.src_is_stack = 1 if s.src_is_stack else 0
+        d.idx = None if s.idx is None else s.idx.data_ptr()
+        d.N = s.N
+        d.R = d.S = s.block
+        d.scale = None if s.scale is None else s.scale.data_ptr()
+        d.shift = None if s.shift is None else s.shift.data_ptr()
+        d.affine_bstride = s.Cin if s.per_sample_affine else 0
+        d.act = ops._act(s.act)
+        d.w_packed = wp.data_ptr()
+        d.bias = None if b32 is None else b32.data_ptr()
+        d.Cin, d.Cout, d.kH, d.kW, d.stride = s.Cin, s.Cout, s.k, s.k, s.stride
+        if s.dst_stack is not None:
+            d.dst, d.dst_is_stack = s.dst_stack.data_ptr(), 1
+            d.dH, d.dW, d.dC, d.dst_c0 = s.dst_stack.shape[2], s.dst_stack.shape[3], s.dst_stack.shape[1], 0
+        else:
+            need_raw = s.dst.has_raw or not s.aux
+            d.dst = s.dst.raw.data_ptr() if need_raw else None
+            d.dst_is_stack = 0
+            d.dH, d.dW, d.dC, d.dst_c0 = s.dst.shape[2], s.dst.shape[3], s.dst.shape[1], 0
+        d.offH = d.offW = s.off
+        if s.residual is not None:
+            d.residual, d.rC, d.res_c0 = s.residual.data_ptr(), s.residual.shape[1], 0
+        else:
+            d.residual, d.rC, d.res_c0 = None, 0, 0
+        d.ksplit = s.ksplit
+        d.flags = (CONV_PDL if s.pdl else 0) | (CONV_TC5 if s.tc5 else 0)
+        d.n_aux = len(s.aux)
+        keep = [wp, b32]
+        for i, (view, sc, sh, act) in enumerate(s.aux):
+            a = d.aux[i]
+            a.ptr, a.C, a.c0 = view.data_ptr(), view.shape[1], 0
+            a.scale = None if sc is None else sc.data_ptr()
+            a.shift = None if sh is None else sh.data_ptr()
+            a.act = ops._act(act)
+        d.n_src2 = 0
+        if s.shortcut is not None:
+            sc_tensors, sc_w, sc_b, sc_flags = s.shortcut
+            w2 = self._pack(sc_w, None if s.weight_key is None else s.weight_key + ("shortcut",))
+            b2 = None if sc_b is None else sc_b.float().contiguous()
+            d.n_src2 = len(sc_tensors)
+            for i, t in enumerate(sc_tensors):
+                d.src2[i].ptr, d.src2[i].C, d.src2[i].up = t.data_ptr(), t.shape[1], 0
+            d.Cin2 = int(sc_w.shape[1])
+            d.w2_packed = w2.data_ptr()
+            d.bias2 = None if b2 is None else b2.data_ptr()
+            d.sc_flags = None if sc_flags is None else sc_flags.data_ptr()
+            keep += [w2, b2]
+        fc.desc, fc.keep = d, keep
+        fc.launch_fn = lambda stream, d=d: ops.launch_tile_conv(d, stream)
+
+    def prepare_conv_in(self, rec: ConvInRec) -> Callable[[int], None]:
+        ops = self.ops
+        w = rec.weight.detach().to(self.dtype).contiguous()
+        b = None if rec.bias is None else rec.bias.detach().to(self.dtype).contiguous()
+        aux = [ops.conv_aux(v, sc, sh, act) for (v, sc, sh, act) in rec.aux]
+        out = rec.out.raw
+
+        def run(_stream):
+            ops.conv_in_nhwc(rec.x, w, b, out=out, aux=aux, tiles=rec.tiles, tile_size=rec.tile_size)
+
+        return run
+
+    def prepare_tail(self, x: torch.Tensor, groups: int, eps: float, gamma, beta, act: str, weight, bias, out: torch.Tensor):
+        ops = self.ops
+        dt = self.dtype
+        B, C = x.shape[0], x.shape[1]
+        g = None if gamma is None else gamma.detach().to(dt).contiguous()
+        bt = None if beta is None else beta.detach().to(dt).contiguous()
+        w = weight.detach().to(dt).contiguous()
+        b = None if bias is None else bias.detach().to(dt).contiguous()
+        scale = torch.empty((B, C), dtype=torch.float32, device=x.device)
+        shift = torch.empty((B, C), dtype=torch.float32, device=x.device)
+        ws = torch.empty((ops._cabi.lib().sige_group_norm_fold_workspace(B, C),), dtype=torch.float32, device=x.device)
+
+        def run(_stream):
+            ops.group_norm_fold(x, groups, eps, g, bt, scale=scale, shift=shift, workspace=ws)
+            ops.conv_out_nhwc(x, scale, shift, act, w, b, out=out)
+
+        return run
+
+    def attention_supported(self, n_tokens: int, channels: int) -> bool:
+        return self.ops.attention_tokens_supported(n_tokens, channels, self.dtype)
+
+    def prepare_attention(self, qkv_tokens: torch.Tensor, out_tokens: torch.Tensor, pdl: bool):
+        ops = self.ops
+        from ._cabi import CONV_PDL
+
+        flags = CONV_PDL if pdl else 0
+
+        def run(_stream):
+            ops.attention_tokens(qkv_tokens, out=out_tokens, flags=flags)
+
+        return run
+
+    def gather(self, x, block, idx, scale, shift, act, act_first):
+        return self.ops.gather(x, block[0], block[1], idx, scale, shift, act, act_first)
+
+    def launch_counter(self) -> int:
+        return self.ops.launch_count
+
+
+# =====================================================================================================================
+# symbolic values of the lowering
+# =====================================================================================================================
+class Pre:
+    """Pending per-channel pointwise op act(x*scale+shift); scale/shift are fp32 [C] or [B, C] tensors or None."""
+
+    def __init__(self, scale=None, shift=None, act: Optional[str] = None):
+        self.scale, self.shift, self.act = scale, shift, act
+
+    def copy(self) -> "Pre":
+        return Pre(self.scale, self.shift, self.act)
+
+
+class Full:
+    """A (B, C, H, W) activation: channel concat of (Buf, upsample flag) segments + pending pointwise op + pending pad."""
+
+    def __init__(self, segs: List[Tuple[Buf, int]], pre: Optional[Pre] = None, pad: Optional[Tuple[int, int, int, int]] = None):
+        self.segs, self.pre, self.pad = segs, pre, pad
+
+    @property
+    def plain(self) -> bool:
+        return self.pre is None and self.pad is None
+
+    @property
+    def single(self) -> Optional[Buf]:
+        return self.segs[0][0] if (self.plain and len(self.segs) == 1 and self.segs[0][1] == 0) else None
+
+    @property
+    def C(self) -> int:
+        return sum(b.shape[1] for b, _ in self.segs)
+
+    @property
+    def B(self) -> int:
+        return self.segs[0][0].shape[0]
+
+    @property
+    def HW(self) -> Tuple[int, int]:
+        b, up = self.segs[0]
+        return (b.shape[2] << up, b.shape[3] << up)
+
+
+class Stack:
+    """Lazy Gather: halo tiles of `src` (a plain Full) cut by `gather` with the fused pre-op."""
+
+    def __init__(self, src: Full, gather, scale, shift):
+        self.src, self.gather, self.scale, self.shift = src, gather, scale, shift
+
+
+class RealStack:
+    """A materialised tile stack (B*N, C, R, S) produced by an eager node."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+
+
+class ConvOut:
+    """A conv whose launch has not been emitted yet (its consumer decides destination / residual / shortcut)."""
+
+    def __init__(self, node: Node, src, weight, bias, k: int, stride: int, padding: int):
+        self.node, self.src, self.weight, self.bias, self.k, self.stride, self.padding = node, src, weight, bias, k, stride, padding
+
+    @property
+    def on_tiles(self) -> bool:
+        return isinstance(self.src, (Stack, RealStack))
+
+
+class RealT:
+    """A real tensor at a stable address (static inputs, outputs of eager nodes)."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+
+
+class Sig:
+    def __init__(self, of: LazyTensor):
+        self.of = of
+
+
+class GNVal:
+    def __init__(self, src: Buf, groups: int, weight, bias, eps: float, act: Optional[str] = None):
+        self.src, self.groups, self.weight, self.bias, self.eps, self.act = src, groups, weight, bias, eps, act
+
+
+class ChanSlice:
+    def __init__(self, buf: Buf, c0: int, c1: int):
+        self.buf, self.c0, self.c1 = buf, c0, c1
+
+
+class Tok:
+    def __init__(self, sl: ChanSlice, layout: str):
+        self.sl, self.layout = sl, layout            # 'bcn' or 'bnc'
+
+
+class Scores:
+    def __init__(self, q: ChanSlice, k: ChanSlice, scale: float = 1.0):
+        self.q, self.k, self.scale = q, k, scale
+
+
+class Probs:
+    def __init__(self, s: Scores, transposed: bool = False):
+        self.s, self.transposed = s, transposed
+
+
+class AttnOut:
+    def __init__(self, s: Scores, v: ChanSlice):
+        self.s, self.v = s, v
+
+
+_MATERIAL = (Full, Stack, RealStack, ConvOut, RealT)
+
+
+def _is_const(o) -> bool:
+    return isinstance(o, torch.Tensor) and not isinstance(o, LazyTensor)
+
+
+def _pair(v) -> Tuple[int, int]:
+    if isinstance(v, (tuple, list)):
+        return (int(v[0]), int(v[-1]))
+    return (int(v), int(v))
+
+
+# =====================================================================================================================
+# lowering
+# =====================================================================================================================
+class Lowering:
+    def __init__(self, tape: lazy.Tape, outputs, static_inputs: Sequence[torch.Tensor], executor, dtype: torch.dtype, device,
+                 pdl: bool = True, tc5: bool = True, producer_preop: bool = True, fuse_shortcut: bool = True,
+                 fused_attention: bool = True, sparse_stem: bool = True, ksplit: int = 0, module_names: Optional[Dict[int, str]] = None):
+        self.tape, self.ex, self.dtype, self.dev = tape, executor, dtype, device
+        self.module_names = module_names or {}
+        self.pdl, self.tc5, self.producer_preop, self.fuse_shortcut = pdl, tc5, producer_preop, fuse_shortcut
+        self.fused_attention, self.sparse_stem, self.ksplit = fused_attention, sparse_stem, ksplit
+        self.steps: List[Tuple[str, Callable[[int], None]]] = []
+        self.fused: List[FusedConv] = []
+        self.conv_ins: List[ConvInRec] = []
+        self.eager_nodes: List[str] = []
+        self._all_idx: Dict = {}
+        self._vecs: Dict = {}
+        self._pending_prepare: List[Callable[[], None]] = []
+        self.env: Dict[int, Any] = {}
+        self.uses: Dict[int, int] = {}
+        self._keepalive: List = []
+        for lt, t in zip(tape.inputs, static_inputs):
+            self.env[id(lt)] = RealT(t)
+        self._count_uses(outputs)
+        for node in tape.nodes:
+            self._lower(node)
+        self.outputs = lazy._tree_map(lambda o: self._output(o) if isinstance(o, LazyTensor) else o, outputs)
+        self._post()
+
+    # ------------------------------------------------------------------ helpers: memory
+    def empty(self, b: int, c: int, h: int, w: int) -> torch.Tensor:
+        return torch.empty((b, c, h, w), dtype=self.dtype, device=self.dev, memory_format=torch.channels_last)
+
+    def clone_cache(self, cache: torch.Tensor) -> torch.Tensor:
+        return cache.detach().to(self.dtype).clone(memory_format=torch.channels_last)
+
+    def fresh(self, b: int, c: int, h: int, w: int) -> Buf:
+        """A buffer that is completely rewritten every step (dense layers)."""
+        return Buf(self, (b, c, h, w))
+
+    def cached(self, cache: torch.Tensor) -> Buf:
+        """A buffer initialised from a module cache; only active tiles are rewritten per step.  The program owns a
+        copy (the module's cache stays pristine)."""
+        return Buf(self, cache.shape, cached_init=cache.detach())
+
+    def vec(self, v: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """fp32 contiguous copy of a per-channel vector (kept alive; one copy per distinct source)."""
+        if v is None:
+            return None
+        key = (v.data_ptr(), v.numel(), v._version, tuple(v.shape), tuple(v.stride()))
+        if key not in self._vecs:
+            self._vecs[key] = (v.detach().to(self.dev).reshape(-1).float().contiguous(), v)
+        return self._vecs[key][0]
+
+    def all_tiles(self, h: int, w: int, off: int) -> torch.Tensor:
+        """Index list covering the whole image with stride-4 tiles (dense layers as 'everything active')."""
+        key = (h, w, off)
+        if key not in self._all_idx:
+            ii, jj = torch.meshgrid(torch.arange(0, h, 4), torch.arange(0, w, 4), indexing="ij")
+            idx = torch.stack([ii.reshape(-1), jj.reshape(-1)], 1) - off
+            self._all_idx[key] = idx.to(torch.int32).to(self.dev).contiguous()
+        return self._all_idx[key]
+
+    # ------------------------------------------------------------------ use counts
+    def _count_uses(self, outputs) -> None:
+        def bump(o):
+            if isinstance(o, LazyTensor):
+                self.uses[id(o)] = self.uses.get(id(o), 0) + 1
+            return o
+
+        for node in self.tape.nodes:
+            lazy._tree_map(bump, node.args)
+            lazy._tree_map(bump, node.kwargs)
+        lazy._tree_map(bump, outputs)
+
+    def n_uses(self, lt: LazyTensor) -> int:
+        return self.uses.get(id(lt), 0)
+
+    # ------------------------------------------------------------------ views (producer-side pre-op)
+    def view(self, buf: Buf, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], act: str) -> Optional[torch.Tensor]:
+        """Tensor holding act(buf*scale+shift), kept up to date by buf's producer(s); None if not possible.
+        scale / shift: fp32 [C] vectors (slices allowed)."""
+        if not self.producer_preop or not buf.producers:
+            return None
+        key = (None if scale is None else (scale.data_ptr(), scale.numel()), None if shift is None else (shift.data_ptr(), shift.numel()), act)
+        if key in buf.views:
+            return buf.views[key][0]
+        if not all(pr.can_aux() for pr in buf.producers):
+            return None
+        b, c, h, w = buf.shape
+        sc = None if scale is None else scale.contiguous()
+        sh = None if shift is None else shift.contiguous()
+        v = self.empty(b, c, h, w)
+        if buf.cached_init is not None:
+            z = buf.cached_init.to(self.dev).float()
+            if sc is not None:
+                z = z * sc.view(1, -1, 1, 1)
+            if sh is not None:
+                z = z + sh.view(1, -1, 1, 1)
+            if act == "swish":
+                z = z * torch.sigmoid(z)
+            v.copy_(z)
+        else:
+            v.zero_()
+        for pr in buf.producers:
+            pr.add_aux(v, sc, sh, act)
+        buf.views[key] = (v, sc, sh)
+        return v
+
+    # ------------------------------------------------------------------ emission of one fused launch
+    def emit_conv(self, name: str, segs: Sequence[Tuple[Buf, int]], pre: Optional[Pre], hw: Tuple[int, int], idx: torch.Tensor, block: int,
+                  weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, off: int, dst: Optional[Buf], residual: Optional[Buf] = None,
+                  shortcut=None, stack_src: Optional[torch.Tensor] = None, dst_stack: Optional[torch.Tensor] = None,
+                  weight_fold: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Optional[FusedConv]:
+        """Each source is (buffer, upsample flag); `pre` spans the concatenated channels.  An affine source is read from the
+        pre-transformed view its producer maintains, else the gather stage applies the pre-op."""
+        if stack_src is not None:            # rows are b*N + i (reference sige/cuda/gather_kernel.cu:30)
+            B = dst.shape[0] if (dst is not None and idx is not None) else 1
+            n = int(stack_src.shape[0]) // B
+            assert idx is None or int(idx.shape[0]) == n, name
+        else:
+            B, n = segs[0][0].shape[0], int(idx.shape[0])
+        s = ConvSpec()
+        s.name = name
+        w32 = weight.detach().float()
+        b32 = None if bias is None else bias.detach().float()
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape), self.dtype, str(self.dev))
+        if weight_fold is not None:        # exact fold of a per-input-channel affine (no activation) into a 1x1 conv
+            f_scale, f_shift = weight_fold
+            assert w32.shape[2] == 1 and w32.shape[3] == 1
+            if f_shift is not None:
+                b32 = (torch.zeros(w32.shape[0], device=w32.device) if b32 is None else b32) + (w32[:, :, 0, 0] @ f_shift.to(w32.device))
+            if f_scale is not None:
+                w32 = w32 * f_scale.to(w32.device).view(1, -1, 1, 1)
+            key = key + ("fold", None if f_scale is None else (f_scale.data_ptr(), f_scale._version), None if f_shift is None else (f_shift.data_ptr(), f_shift._version))
+            self._keepalive.append(weight_fold)
+        s.weight, s.bias, s.weight_key = w32, b32, key
+        s.k, s.stride, s.off, s.block = int(weight.shape[2]), stride, off, block
+        s.B, s.H, s.W = B, hw[0], hw[1]
+        s.idx, s.N = idx, n
+        s.pdl, s.tc5, s.ksplit = self.pdl, self.tc5, self.ksplit
+        if stack_src is not None:
+            s.src_is_stack = True
+            s.srcs = [(stack_src, 0)]
+            s.H, s.W = block, block
+        else:
+            tensors: List[torch.Tensor] = []
+            gather_side = False
+            if pre is not None and (pre.scale is not None or pre.shift is not None or pre.act):
+                per_sample = (pre.scale is not None and pre.scale.dim() == 2) or (pre.shift is not None and pre.shift.dim() == 2)
+                views, c0 = [], 0
+                if not per_sample:
+                    for (b_, up_) in segs:
+                        c = b_.shape[1]
+                        sc = None if pre.scale is None else pre.scale[c0:c0 + c]
+                        sh = None if pre.shift is None else pre.shift[c0:c0 + c]
+                        views.append(self.view(b_, sc, sh, pre.act or "identity"))
+                        c0 += c
+                if per_sample or any(v is None for v in views):
+                    gather_side = True
+                    tensors = [b_.raw for (b_, _) in segs]
+                    s.scale = None if pre.scale is None else pre.scale.contiguous()
+                    s.shift = None if pre.shift is None else pre.shift.contiguous()
+                    s.per_sample_affine = per_sample
+                    s.act = pre.act or "identity"
+                else:
+                    tensors = views
+            else:
+                tensors = [b_.raw for (b_, _) in segs]
+            for (b_, up_) in segs:
+                b_.readers.append((idx, block, up_))
+            s.srcs = [(t, up) for t, (_, up) in zip(tensors, segs)]
+            del gather_side
+        if residual is not None:
+            residual.readers.append((idx, block, 0))
+            s.residual = residual.raw
+        s.dst, s.dst_stack = dst, dst_stack
+        if shortcut is not None:
+            sc_bufs, sc_w, sc_b, sc_flags = shortcut
+            for b_ in sc_bufs:
+                b_.readers.append((idx, block, 0))      # the fused shortcut reads the centre 4x4 of conv2's 6x6 tiles
+            s.shortcut = ([b_.raw for b_ in sc_bufs], sc_w.detach().float(), None if sc_b is None else sc_b.detach().float(), sc_flags)
+        fc = FusedConv(s)
+        if n == 0:
+            return None
+        if dst is not None:
+            dst.producers.append(fc)
+        self.fused.append(fc)
+        self.steps.append(("conv", fc.launch))
+        return fc
+
+    # ------------------------------------------------------------------ forcing / materialising values
+    def sym(self, lt) -> Any:
+        return self.env.get(id(lt))
+
+    def as_full(self, lt: LazyTensor) -> Optional[Full]:
+        """The value as a Full (emitting a pending conv / evaluating an un-lowered producer eagerly and wrapping its
+        result); None if it is not a (B, C, H, W) activation."""
+        v = self.sym(lt)
+        if isinstance(v, Full):
+            return v
+        if isinstance(v, ConvOut) and not v.on_tiles:
+            buf = self.force_dense(v)
+            f = Full([(buf, 0)])
+            self.env[id(lt)] = f
+            return f
+        if isinstance(v, (Stack, RealStack, ConvOut)) or lt.dim() != 4 or lt.shape[1] % 8 != 0:
+            return None
+        if not isinstance(v, RealT):
+            if lt.node is None:
+                return None
+            self.eager(lt.node)            # an island the lowering does not know: its result feeds the fused layers again
+            v = self.sym(lt)
+        if isinstance(v, RealT) and v.tensor.is_contiguous(memory_format=torch.channels_last):
+            f = Full([(Buf(self, v.tensor.shape, raw=v.tensor), 0)])
+            self.env[id(lt)] = f
+            return f
+        return None
+
+    def plain_buf(self, lt: LazyTensor) -> Optional[Buf]:
+        """The value as ONE raw buffer (materialising pending cat / upsample / pre-op through an eager node if needed)."""
+        f = self.as_full(lt)
+        if f is None:
+            return None
+        if f.single is not None:
+            return f.single
+        t = self.materialize_full(lt, f)
+        return self.sym(lt).single if isinstance(self.sym(lt), Full) else Buf(self, t.shape, raw=t)
+
+    def force_dense(self, co: ConvOut, residual: Optional[Buf] = None, shortcut=None) -> Buf:
+        """Emit a dense (all-tiles) conv into a fresh buffer."""
+        f: Full = co.src
+        h, w = f.HW
+        B = f.B
+        cout = int(co.weight.shape[0])
+        name = "n%d.conv%dx%d" % (co.node.index, co.k, co.k)
+        if co.k == 3 and co.stride == 1:
+            idx, block, off, dh, dw = self.all_tiles(h, w, 1), 6, 1, h, w
+        elif co.k == 1:
+            idx, block, off, dh, dw = self.all_tiles(h, w, 0), 4, 0, h, w
+        else:       # 3x3 stride 2 on the (0,1,0,1)-padded input: 5x5 tiles overhang the far edges, where the halo is zero
+            idx, block, off, dh, dw = self.all_tiles(h, w, 0), 5, 0, h // 2, w // 2
+        dst = self.fresh(B, cout, dh, dw)
+        pre, fold = f.pre, None
+        if pre is not None and co.k == 1 and not pre.act and not self._per_sample(pre):
+            fold, pre = (pre.scale, pre.shift), None          # exact: no halo in a 1x1 conv
+        self.emit_conv(name, f.segs, pre, (h, w), idx, block, co.weight, co.bias, co.stride, off, dst, residual=residual, shortcut=shortcut,
+                       weight_fold=fold)
+        return dst
+
+    @staticmethod
+    def _per_sample(pre: Pre) -> bool:
+        return (pre.scale is not None and pre.scale.dim() == 2) or (pre.shift is not None and pre.shift.dim() == 2)
+
+    def tile_conv_args(self, co: ConvOut):
+        """(segs, pre, hw, idx, block, off, stack_src) of a conv on tiles."""
+        st = co.src
+        if isinstance(st, RealStack):
+            t = st.tensor
+            return None, None, (t.shape[2], t.shape[3]), None, int(t.shape[2]), 0, t
+        g = st.gather
+        pre = None
+        if st.scale is not None or st.shift is not None or g.activation_name != "identity":
+            pre = Pre(self._chan_vec(st.scale, st.src), self._chan_vec(st.shift, st.src), None if g.activation_name == "identity" else g.activation_name)
+        return st.src.segs, pre, st.src.HW, g.active_indices.to(self.dev), int(g.block_size[0]), int(g.offset[0]), None
+
+    def _chan_vec(self, t: Optional[torch.Tensor], f: Full) -> Optional[torch.Tensor]:
+        """(1|B, C, 1, 1) broadcast operand -> fp32 [C] (or [B, C]) vector."""
+        if t is None:
+            return None
+        C = f.C
+        if t.numel() == 1:
+            return self.vec(t).expand(C).contiguous()
+        if t.dim() == 4 and t.shape[2] == 1 and t.shape[3] == 1 and t.shape[1] == C:
+            if t.shape[0] == 1:
+                return self.vec(t)
+            return self.vec(t).view(t.shape[0], C)
+        raise TraceUnsupported("unsupported affine operand shape %s" % (tuple(t.shape),))
+
+    # ---- eager fallback ------------------------------------------------------------------------------------------
+    def runtime_tensor(self, lt: LazyTensor) -> Optional[torch.Tensor]:
+        """A real tensor, at a stable address, that holds the value when the program reaches this point."""
+        v = self.sym(lt)
+        if isinstance(v, RealT):
+            return v.tensor
+        if isinstance(v, RealStack):
+            return v.tensor
+        if isinstance(v, Full):
+            if v.single is not None:
+                v.single.readers.append(None)
+                return v.single.raw
+            return self.materialize_full(lt, v)
+        if isinstance(v, ConvOut):
+            if v.on_tiles:
+                return self.force_stack(lt, v)
+            buf = self.force_dense(v)
+            self.env[id(lt)] = Full([(buf, 0)])
+            buf.readers.append(None)
+            return buf.raw
+        if isinstance(v, Stack):
+            return self.materialize_stack(lt, v)
+        # speculative symbolic kinds (or nothing yet): evaluate the producing node eagerly
+        if lt.node is None:
+            raise TraceUnsupported("input without a binding")
+        self.eager(lt.node)
+        return self.runtime_tensor(lt)
+
+    def materialize_full(self, lt: LazyTensor, f: Full) -> torch.Tensor:
+        B, C = f.B, f.C
+        h, w = f.HW
+        if f.pad is not None:
+            l, r, t_, b_ = f.pad
+            out = self.empty(B, C, h + t_ + b_, w + l + r)
+        else:
+            out = self.empty(B, C, h, w)
+        raws = []
+        for buf, up in f.segs:
+            buf.readers.append(None)
+            raws.append((buf.raw, up))
+        pre, pad = f.pre, f.pad
+        dtype = self.dtype
+
+        def run(_stream):
+            parts = [F.interpolate(t, scale_factor=2.0, mode="nearest") if up else t for (t, up) in raws]
+            z = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+            if pre is not None:
+                zf = z.float()
+                if pre.scale is not None:
+                    zf = zf * (pre.scale.view(1, -1, 1, 1) if pre.scale.dim() == 1 else pre.scale.view(pre.scale.shape[0], -1, 1, 1))
+                if pre.shift is not None:
+                    zf = zf + (pre.shift.view(1, -1, 1, 1) if pre.shift.dim() == 1 else pre.shift.view(pre.shift.shape[0], -1, 1, 1))
+                if pre.act == "swish":
+                    zf = zf * torch.sigmoid(zf)
+                z = zf.to(dtype)
+            if pad is not None:
+                z = F.pad(z, pad)
+            out.copy_(z)
+
+        self.steps.append(("eager", run))
+        self.eager_nodes.append("materialize(%s)" % (lt.node.name if lt.node is not None else "input"))
+        self.env[id(lt)] = Full([(Buf(self, out.shape, raw=out), 0)])
+        return out
+
+    def materialize_stack(self, lt: LazyTensor, st: Stack) -> torch.Tensor:
+        src = self.plain_of_full(st.src)
+        g = st.gather
+        src.readers.append(None)
+        x = src.raw
+        idx = g.active_indices.to(self.dev)
+        n = int(idx.shape[0])
+        out = torch.empty((x.shape[0] * n, x.shape[1], g.block_size[0], g.block_size[1]), dtype=self.dtype, device=self.dev, memory_format=torch.channels_last)
+        ex, scale, shift = self.ex, st.scale, st.shift
+
+        def run(_stream):
+            out.copy_(ex.gather(x, g.block_size, idx, scale, shift, g.activation_name, g.activation_first))
+
+        self.steps.append(("eager", run))
+        self.eager_nodes.append("gather(n%d)" % lt.node.index)
+        self.env[id(lt)] = RealStack(out)
+        return out
+
+    def plain_of_full(self, f: Full) -> Buf:
+        if f.single is not None:
+            return f.single
+        raise TraceUnsupported("gather of a concatenated / upsampled tensor outside a fused conv")
+
+    def force_stack(self, lt: LazyTensor, co: ConvOut) -> torch.Tensor:
+        """Emit a conv on tiles whose result stays a stack (a foreign op consumes it)."""
+        segs, pre, hw, idx, block, off, stack_src = self.tile_conv_args(co)
+        n = int(idx.shape[0]) if idx is not None else int(stack_src.shape[0])
+        B = 1 if stack_src is not None else segs[0][0].shape[0]
+        ro = (block - co.k) // co.stride + 1
+        out = torch.empty((B * n, int(co.weight.shape[0]), ro, ro), dtype=self.dtype, device=self.dev, memory_format=torch.channels_last)
+        self.emit_conv("n%d.conv_stack" % co.node.index, segs, pre, hw, idx, block, co.weight, co.bias, co.stride, off, None, stack_src=stack_src, dst_stack=out)
+        self.env[id(lt)] = RealStack(out)
+        return out
+
+    def eager(self, node: Node) -> None:
+        """Run the recorded call itself (torch op or operator module) on real tensors at this point of the program."""
+        if all(isinstance(self.sym(o), (RealT, RealStack)) for o in node.outs) and node.outs:
+            return
+        getters: Dict[int, torch.Tensor] = {}
+        stack_shapes = set()
+
+        def bind(o):
+            if isinstance(o, LazyTensor):
+                getters[id(o)] = self.runtime_tensor(o)
+                if isinstance(self.sym(o), RealStack):
+                    stack_shapes.add(tuple(o.shape))
+            return o
+
+        lazy._tree_map(bind, node.args)
+        lazy._tree_map(bind, node.kwargs)
+        outs = []
+        for o in node.outs:
+            fmt = torch.channels_last if (o.dim() == 4 and o.shape[1] > 1) else torch.contiguous_format
+            outs.append(torch.empty(tuple(o.shape), dtype=o.dtype, device=self.dev, memory_format=fmt))
+
+        def sub(o):
+            return getters[id(o)] if isinstance(o, LazyTensor) else o
+
+        op, module, multi = node.op, node.module, node.multi
+
+        def run(_stream):
+            args = lazy._tree_map(sub, node.args)
+            kwargs = lazy._tree_map(sub, node.kwargs)
+            if isinstance(op, str):
+                res = module(*args)
+            else:
+                res = op(*args, **kwargs)
+            res = list(res) if multi else [res]
+            for dst, r in zip(outs, [r for r in res if isinstance(r, torch.Tensor)]):
+                dst.copy_(r)
+
+        self.steps.append(("eager", run))
+        self.eager_nodes.append(node.name)
+        is_stack_op = node.name in ("sige.gather", "sige.conv", "sige.scatter_gather")
+        for o, t in zip(node.outs, outs):
+            # pointwise math on a tile stack yields a tile stack (GauGAN's SPADE modulation between Gather and the conv)
+            self.env[id(o)] = RealStack(t) if (is_stack_op or (not isinstance(node.op, str) and tuple(o.shape) in stack_shapes)) else RealT(t)
+
+    # ------------------------------------------------------------------ node handlers
+    def _lower(self, node: Node) -> None:
+        h = getattr(self, "_h_" + node.name.replace(".", "_").strip("_"), None)
+        done = False
+        if h is not None:
+            done = h(node) is not False
+        if not done:
+            # unknown op: decide later (evaluated eagerly if and when a consumer needs its value)
+            pass
+
+    @staticmethod
+    def _bind(node: Node, names: Sequence[str], defaults: Dict[str, Any]):
+        vals = dict(defaults)
+        for n_, a in zip(names, node.args):
+            vals[n_] = a
+        vals.update(node.kwargs)
+        return vals
+
+    # ---- convolutions
+    def _conv_common(self, node: Node, x, weight, bias, stride, padding, dilation, groups) -> bool:
+        if not (_is_const(weight) and (bias is None or _is_const(bias))) or weight.dim() != 4:
+            return False
+        k, s, p = _pair(weight.shape[2:]), _pair(stride), (_pair(padding) if not isinstance(padding, str) else None)
+        if p is None or k[0] != k[1] or s[0] != s[1] or p[0] != p[1] or _pair(dilation) != (1, 1) or groups != 1:
+            return False
+        k, s, p = k[0], s[0], p[0]
+        cout, cin = int(weight.shape[0]), int(weight.shape[1])
+        out = node.outs[0]
+        v = self.sym(x)
+        if isinstance(v, GNVal):
+            if k == 3 and s == 1 and p == 1 and cout <= 8 and cin % 16 == 0 and v.act in (None, "swish"):
+                res = torch.empty((v.src.shape[0], cout, v.src.shape[2], v.src.shape[3]), dtype=self.dtype, device=self.dev)
+                v.src.readers.append(None)
+                x_raw = v.src.raw
+                slot = len(self.steps)
+                self.steps.append(("tail", None))
+                ex = self.ex
+
+                def prep(slot=slot, v=v, x_raw=x_raw, res=res):
+                    self.steps[slot] = ("tail", ex.prepare_tail(x_raw, v.groups, v.eps, v.weight, v.bias, v.act or "identity", weight, bias, res))
+
+                self._pending_prepare.append(prep)
+                self.env[id(out)] = RealT(res)
+                return True
+            return False
+        if isinstance(v, (Stack, RealStack)):
+            if p != 0 or cin % 64 != 0 or cout % 8 != 0:
+                return False
+            if isinstance(v, Stack) and (v.gather.activation_first and v.gather.activation_name != "identity"):
+                return False
+            block = int(v.gather.block_size[0]) if isinstance(v, Stack) else int(v.tensor.shape[2])
+            if isinstance(v, Stack) and v.gather.block_size[0] != v.gather.block_size[1]:
+                return False
+            if block < k or (block - k) % s != 0:
+                return False
+            self.env[id(out)] = ConvOut(node, v, weight, bias, k, s, 0)
+            return True
+        if isinstance(v, RealT) and v.tensor.dim() == 4 and cin <= 4 and k == 3 and s == 1 and p == 1 and cout % 8 == 0 and v.tensor.shape[1] == cin:
+            t = v.tensor
+            if not t.is_contiguous(memory_format=torch.channels_last):
+                return False
+            dst = self.fresh(t.shape[0], cout, t.shape[2], t.shape[3])
+            rec = ConvInRec(t, weight, bias, dst)
+            dst.producers.append(rec)
+            self.conv_ins.append(rec)
+            slot = len(self.steps)
+            self.steps.append(("conv_in", None))
+
+            def prep(slot=slot, rec=rec):
+                self.steps[slot] = ("conv_in", self.ex.prepare_conv_in(rec))
+
+            self._pending_prepare.append(prep)
+            self.env[id(out)] = Full([(dst, 0)])
+            return True
+        f = self.as_full(x)
+        if f is None or cin % 64 != 0 or cout % 8 != 0 or len(f.segs) > 2 or any(b.shape[1] % 64 for b, _ in f.segs):
+            return False
+        h, w = f.HW
+        if h % 4 or w % 4:
+            return False
+        if f.pad is not None:
+            if not (f.pad == (0, 1, 0, 1) and k == 3 and s == 2 and p == 0):
+                return False
+        elif not ((k == 3 and s == 1 and p == 1) or (k == 1 and s == 1 and p == 0)):
+            return False
+        if f.pre is not None and f.pre.act not in (None, "swish"):
+            return False
+        self.env[id(out)] = ConvOut(node, f, weight, bias, k, s, p)
+        return True
+
+    def _h_conv2d(self, node: Node):
+        a = self._bind(node, ("input", "weight", "bias", "stride", "padding", "dilation", "groups"),
+                       {"bias": None, "stride": 1, "padding": 0, "dilation": 1, "groups": 1})
+        return self._conv_common(node, a["input"], a["weight"], a["bias"], a["stride"], a["padding"], a["dilation"], a["groups"])
+
+    def _h_sige_conv(self, node: Node):
+        m = node.module
+        if isinstance(m.padding, str) or m.padding_mode != "zeros":
+            return False
+        x = node.args[0]
+        if not isinstance(self.sym(x), (Stack, RealStack)) and x.dim() == 4:      # SIGEConv2d in sparse mode always sees a tile stack
+            t = self.runtime_tensor(x)
+            if t.is_contiguous(memory_format=torch.channels_last):
+                self.env[id(x)] = RealStack(t)
+        return self._conv_common(node, node.args[0], m.weight, m.bias, m.stride, 0, m.dilation, m.groups)
+
+    # ---- operator modules
+    def _h_sige_gather(self, node: Node):
+        x, scale, shift = node.args
+        g = node.module
+        if not (scale is None or _is_const(scale)) or not (shift is None or _is_const(shift)):
+            return False
+        f = self.as_full(x)
+        if f is None or f.pre is not None or f.pad is not None:
+            return False
+        self.env[id(node.outs[0])] = Stack(f, g, scale, shift)
+        return True
+
+    def _tile_emit(self, node: Node, co: ConvOut, dst: Buf, residual: Optional[Buf] = None, shortcut=None, name: str = "", gather=None) -> None:
+        segs, pre, hw, idx, block, off, stack_src = self.tile_conv_args(co)
+        if stack_src is not None and gather is not None:      # a materialised stack scattered through `gather`'s tile set
+            idx, off = gather.active_indices.to(self.dev), int(gather.offset[0])
+        self.emit_conv(name or ("n%d" % node.index), segs, pre, hw, idx, block, co.weight, co.bias, co.stride, off, dst, residual=residual,
+                       shortcut=shortcut, stack_src=stack_src)
+
+    def _module_name(self, node: Node) -> str:
+        return self.module_names.get(id(node.module), "n%d" % node.index)
+
+    @staticmethod
+    def _same_gather(a, g) -> bool:
+        """Is `a` (a Gather, or the geometry stub a ScatterGather hands on) the tile set of Gather `g`?"""
+        return a is g or (getattr(a, "active_indices", None) is g.active_indices and tuple(a.block_size) == tuple(g.block_size)
+                          and tuple(a.offset) == tuple(g.offset))
+
+    def _h_sige_scatter(self, node: Node):
+        x, residual = node.args
+        m = node.module
+        co = self.sym(x)
+        if not (isinstance(co, ConvOut) and co.on_tiles and self.n_uses(x) == 1):
+            return False
+        g = m.gather.module
+        if isinstance(co.src, Stack) and not self._same_gather(co.src.gather, g):
+            return False
+        if isinstance(co.src, RealStack) and (int(co.src.tensor.shape[2]) != int(g.block_size[0]) or g.block_size[0] != g.block_size[1]):
+            return False
+        res_buf = None
+        if residual is not None:
+            if _is_const(residual):
+                return False
+            res_buf = self.plain_buf(residual)
+            if res_buf is None:
+                return False
+        cache = m.original_outputs[m.cache_id]
+        dst = self.cached(cache)
+        if res_buf is not None and tuple(res_buf.shape) != tuple(dst.shape):
+            return False
+        self._tile_emit(node, co, dst, residual=res_buf, name=self._module_name(node), gather=g)
+        self.env[id(node.outs[0])] = Full([(dst, 0)])
+        return True
+
+    def _h_sige_scatter_gather(self, node: Node):
+        x, scale, shift = node.args
+        m = node.module
+        co = self.sym(x)
+        if not (isinstance(co, ConvOut) and co.on_tiles and isinstance(co.src, Stack) and self.n_uses(x) == 1):
+            return False
+        if not (scale is None or _is_const(scale)) or not (shift is None or _is_const(shift)):
+            return False
+        g = m.gather.module
+        if not self._same_gather(co.src.gather, g):
+            return False
+        dst = self.cached(m.original_outputs[m.cache_id])
+        self._tile_emit(node, co, dst, name=self._module_name(node))
+
+        class _G:        # the second gather re-uses the paired gather's geometry with this module's activation
+            pass
+
+        g2 = _G()
+        g2.active_indices, g2.block_size, g2.offset = g.active_indices, g.block_size, g.offset
+        g2.activation_name, g2.activation_first = m.activation_name, m.activation_first
+        self.env[id(node.outs[0])] = Stack(Full([(dst, 0)]), g2, scale, shift)
+        return True
+
+    def _h_sige_scatter_block_residual(self, node: Node):
+        x, residual = node.args
+        m = node.module
+        co, sc = self.sym(x), self.sym(residual)
+        if not (isinstance(co, ConvOut) and isinstance(sc, ConvOut) and co.on_tiles and sc.on_tiles and self.n_uses(x) == 1 and self.n_uses(residual) == 1):
+            return False
+        if not (isinstance(co.src, Stack) and isinstance(sc.src, Stack)):
+            return False
+        mg, sg = m.main_gather.module, m.shortcut_gather.module
+        if not self._same_gather(co.src.gather, mg):
+            return False
+        if sc.src.gather is not sg or sc.k != 1 or sc.src.scale is not None or sc.src.shift is not None or sg.activation_name != "identity":
+            return False
+        cid = m.cache_id
+        dst = self.cached(m.original_outputs[cid])
+        skip = self.cached(m.original_residuals[cid])
+        idx, off = mg.active_indices.to(self.dev), int(mg.offset[0])
+        sidx, soff = sg.active_indices.to(self.dev), int(sg.offset[0])
+        sc_full: Full = sc.src.src
+        # the shortcut's active tiles must sit on the main conv's output-tile grid and be a subset of it: then evaluating the
+        # shortcut on those main tiles (and adding the cached shortcut output elsewhere) IS the reference's
+        # `out += fresh - cached` patch (sige/cuda/scatter_kernel.cu:46-74)
+        width = 1 << 16
+        main_key = (idx[:, 0].long() + off) * width + (idx[:, 1].long() + off)
+        sc_key = (sidx[:, 0].long() + soff) * width + (sidx[:, 1].long() + soff)
+        subset = bool(torch.isin(sc_key, main_key).all()) and tuple(mg.block_stride) == tuple(sg.block_stride) == (4, 4) \
+            and int(sg.block_size[0]) == 4 and int(mg.block_size[0]) == 6
+        fuse = (self.fuse_shortcut and self.tc5 and self.producer_preop and subset and co.k == 3 and co.stride == 1
+                and all(up == 0 for _, up in sc_full.segs) and len(sc_full.segs) <= 2 and sc_full.plain
+                and int(sc.weight.shape[1]) % 64 == 0)
+        name = self._module_name(node)
+        if fuse:
+            flags = torch.isin(main_key, sc_key).to(torch.uint8).contiguous()
+            shortcut = ([b for b, _ in sc_full.segs], sc.weight, sc.bias, flags)
+            self._tile_emit(node, co, dst, residual=skip, shortcut=shortcut, name=name)
+        else:
+            if not subset:
+                return False
+            # un-fused: the shortcut's own launch refreshes its tiles of `skip`, then conv2 adds `skip` as the residual
+            self._tile_emit(node, sc, skip, name=name + ".shortcut")
+            self._tile_emit(node, co, dst, residual=skip, name=name)
+        self.env[id(node.outs[0])] = Full([(dst, 0)])
+        return True
+
+    # ---- pointwise algebra
+    def _affine(self, node: Node, a, b, is_mul: bool):
+        x, c = (a, b) if isinstance(a, LazyTensor) else (b, a)
+        if isinstance(c, LazyTensor):
+            return None
+        v = self.sym(x)
+        if isinstance(v, ConvOut) and not v.on_tiles:
+            v = self.as_full(x)
+        if not isinstance(v, Full) or v.pad is not None:
+            return None
+        if isinstance(c, (int, float)):
+            cv = torch.full((v.C,), float(c), dtype=torch.float32, device=self.dev)
+            self._keepalive.append(cv)
+        elif _is_const(c):
+            try:
+                cv = self._chan_vec(c, v)
+            except TraceUnsupported:
+                return None
+        else:
+            return None
+        pre = v.pre.copy() if v.pre is not None else Pre()
+        if pre.act:
+            return None
+        if is_mul:
+            pre.scale = cv if pre.scale is None else pre.scale * cv
+            pre.shift = None if pre.shift is None else pre.shift * cv
+        else:
+            pre.shift = cv if pre.shift is None else pre.shift + cv
+        return Full(list(v.segs), pre, None)
+
+    def _h_mul(self, node: Node):
+        a, b = node.args[0], node.args[1]
+        out = node.outs[0]
+        sa, sb = (self.sym(a) if isinstance(a, LazyTensor) else None), (self.sym(b) if isinstance(b, LazyTensor) else None)
+        # x * sigmoid(x)
+        for x, s_ in ((a, sb), (b, sa)):
+            if isinstance(s_, Sig) and isinstance(x, LazyTensor) and s_.of is x:
+                v = self.sym(x)
+                if isinstance(v, ConvOut) and not v.on_tiles:
+                    v = self.as_full(x)
+                if isinstance(v, Full) and v.pad is None and not (v.pre and v.pre.act):
+                    pre = v.pre.copy() if v.pre is not None else Pre()
+                    pre.act = "swish"
+                    self.env[id(out)] = Full(list(v.segs), pre)
+                    return True
+                if isinstance(v, GNVal) and v.act is None:
+                    self.env[id(out)] = GNVal(v.src, v.groups, v.weight, v.bias, v.eps, "swish")
+                    return True
+                return False
+        for x, c in ((sa, b), (sb, a)):
+            if isinstance(x, Scores) and isinstance(c, (int, float)):
+                self.env[id(out)] = Scores(x.q, x.k, x.scale * float(c))
+                return True
+        r = self._affine(node, a, b, True)
+        if r is None:
+            return False
+        self.env[id(out)] = r
+        return True
+
+    _h_rmul = _h_mul
+
+    def _h_add(self, node: Node):
+        a, b = node.args[0], node.args[1]
+        if node.kwargs.get("alpha", 1) != 1 or len(node.args) > 2:
+            return False
+        out = node.outs[0]
+        if isinstance(a, LazyTensor) and isinstance(b, LazyTensor):
+            for x, r in ((a, b), (b, a)):
+                co = self.sym(x)
+                if not (isinstance(co, ConvOut) and not co.on_tiles and self.n_uses(x) == 1):
+                    continue
+                ro = self.sym(r)
+                src: Full = co.src
+                shortcut = None
+                res_buf = None
+                if (isinstance(ro, ConvOut) and not ro.on_tiles and ro.k == 1 and self.n_uses(r) == 1 and co.k == 3 and co.stride == 1
+                        and self.fuse_shortcut and self.tc5 and self.producer_preop and ro.src.plain and all(up == 0 for _, up in ro.src.segs) and len(ro.src.segs) <= 2
+                        and ro.src.HW == src.HW and int(ro.weight.shape[0]) == int(co.weight.shape[0]) and int(ro.weight.shape[1]) % 64 == 0):
+                    shortcut = ([b_ for b_, _ in ro.src.segs], ro.weight, ro.bias, None)     # dense block: the 1x1 shortcut on every tile
+                else:
+                    res_buf = self.plain_buf(r)
+                    if res_buf is None:
+                        continue
+                    h, w = src.HW
+                    oh, ow = (h // 2, w // 2) if co.stride == 2 else (h, w)
+                    if tuple(res_buf.shape) != (src.B, int(co.weight.shape[0]), oh, ow):
+                        continue
+                dst = self.force_dense(co, residual=res_buf, shortcut=shortcut)
+                self.env[id(out)] = Full([(dst, 0)])
+                return True
+            return False
+        r = self._affine(node, a, b, False)
+        if r is None:
+            return False
+        self.env[id(out)] = r
+        return True
+
+    _h_radd = _h_add
+
+    def _h_sigmoid(self, node: Node):
+        x = node.args[0]
+        if isinstance(self.sym(x), (Full, ConvOut, GNVal)):
+            self.env[id(node.outs[0])] = Sig(x)
+            return True
+        return False
+
+    def _h_silu(self, node: Node):
+        x = node.args[0]
+        v = self.sym(x)
+        if isinstance(v, ConvOut) and not v.on_tiles:
+            v = self.as_full(x)
+        if isinstance(v, Full) and v.pad is None and not (v.pre and v.pre.act):
+            pre = v.pre.copy() if v.pre is not None else Pre()
+            pre.act = "swish"
+            self.env[id(node.outs[0])] = Full(list(v.segs), pre)
+            return True
+        if isinstance(v, GNVal) and v.act is None:
+            self.env[id(node.outs[0])] = GNVal(v.src, v.groups, v.weight, v.bias, v.eps, "swish")
+            return True
+        return False
+
+    # ---- structural glue
+    def _h_cat(self, node: Node):
+        a = self._bind(node, ("tensors", "dim"), {"dim": 0})
+        if a["dim"] != 1:
+            return False
+        segs: List[Tuple[Buf, int]] = []
+        for t in a["tensors"]:
+            if not isinstance(t, LazyTensor):
+                return False
+            f = self.as_full(t)
+            if f is None or not f.plain:
+                return False
+            segs += f.segs
+        if len({(b.shape[0], b.shape[2] << up, b.shape[3] << up) for b, up in segs}) != 1:
+            return False
+        self.env[id(node.outs[0])] = Full(segs)
+        return True
+
+    _h_concat = _h_cat
+
+    def _h_interpolate(self, node: Node):
+        a = self._bind(node, ("input", "size", "scale_factor", "mode"), {"size": None, "scale_factor": None, "mode": "nearest"})
+        sf = a["scale_factor"]
+        if a["mode"] != "nearest" or a["size"] is not None or sf is None or any(float(s) != 2.0 for s in (sf if isinstance(sf, (tuple, list)) else (sf,))):
+            return False
+        f = self.as_full(a["input"])
+        if f is None or f.pad is not None or any(up for _, up in f.segs):
+            return False
+        self.env[id(node.outs[0])] = Full([(b, 1) for b, _ in f.segs], f.pre)
+        return True
+
+    def _h_pad(self, node: Node):
+        a = self._bind(node, ("input", "pad", "mode", "value"), {"mode": "constant", "value": None})
+        if a["mode"] != "constant" or a["value"] not in (None, 0, 0.0) or tuple(a["pad"]) != (0, 1, 0, 1):
+            return False
+        f = self.as_full(a["input"])
+        if f is None or f.pad is not None:
+            return False
+        self.env[id(node.outs[0])] = Full(list(f.segs), f.pre, (0, 1, 0, 1))
+        return True
+
+    def _h_group_norm(self, node: Node):
+        a = self._bind(node, ("input", "num_groups", "weight", "bias", "eps"), {"weight": None, "bias": None, "eps": 1e-5})
+        buf = None
+        f = self.as_full(a["input"])
+        if f is not None:
+            buf = f.single
+        if buf is None or not (a["weight"] is None or _is_const(a["weight"])) or not (a["bias"] is None or _is_const(a["bias"])):
+            return False
+        self.env[id(node.outs[0])] = GNVal(buf, int(a["num_groups"]), a["weight"], a["bias"], float(a["eps"]))
+        return True
+
+    # ---- attention core: split -> reshape/permute -> bmm -> *scale -> softmax -> permute -> bmm -> reshape
+    def _h_split(self, node: Node):
+        a = self._bind(node, ("tensor", "split_size_or_sections", "dim"), {"dim": 0})
+        sz = a["split_size_or_sections"]
+        if a["dim"] != 1 or not isinstance(sz, int):
+            return False
+        f = self.as_full(a["tensor"])
+        buf = f.single if f is not None else None
+        if buf is None or buf.shape[1] % sz:
+            return False
+        for i, o in enumerate(node.outs):
+            self.env[id(o)] = ChanSlice(buf, i * sz, (i + 1) * sz)
+        return True
+
+    def _h_reshape(self, node: Node):
+        x = node.args[0]
+        shape = node.args[1:] if not isinstance(node.args[1], (tuple, list, torch.Size)) else tuple(node.args[1])
+        shape = tuple(int(s) for s in shape)
+        v = self.sym(x)
+        out = node.outs[0]
+        if isinstance(v, ChanSlice):
+            B, _, H, W = v.buf.shape
+            if tuple(out.shape) == (B, v.c1 - v.c0, H * W):
+                self.env[id(out)] = Tok(v, "bcn")
+                return True
+            return False
+        if isinstance(v, AttnOut):
+            B, _, H, W = v.v.buf.shape
+            C = v.v.c1 - v.v.c0
+            if tuple(out.shape) == (B, C, H, W) and self._emit_attention(out, v):
+                return True
+            return False
+        return False
+
+    _h_view = _h_reshape
+
+    def _h_permute(self, node: Node):
+        x = node.args[0]
+        dims = node.args[1:] if not isinstance(node.args[1], (tuple, list)) else tuple(node.args[1])
+        v = self.sym(x)
+        if tuple(dims) != (0, 2, 1):
+            return False
+        if isinstance(v, Tok):
+            self.env[id(node.outs[0])] = Tok(v.sl, "bnc" if v.layout == "bcn" else "bcn")
+            return True
+        if isinstance(v, Probs):
+            self.env[id(node.outs[0])] = Probs(v.s, not v.transposed)
+            return True
+        return False
+
+    def _h_bmm(self, node: Node):
+        a, b = self.sym(node.args[0]), self.sym(node.args[1])
+        if isinstance(a, Tok) and isinstance(b, Tok) and a.layout == "bnc" and b.layout == "bcn":
+            self.env[id(node.outs[0])] = Scores(a.sl, b.sl)
+            return True
+        if isinstance(a, Tok) and a.layout == "bcn" and isinstance(b, Probs) and b.transposed:
+            self.env[id(node.outs[0])] = AttnOut(b.s, a.sl)
+            return True
+        return False
+
+    def _h_softmax(self, node: Node):
+        a = self._bind(node, ("input", "dim"), {"dim": None})
+        v = self.sym(a["input"])
+        if isinstance(v, Scores) and a["dim"] in (2, -1) and a.get("dtype") is None:
+            self.env[id(node.outs[0])] = Probs(v)
+            return True
+        return False
+
+    def _emit_attention(self, out: LazyTensor, v: AttnOut) -> bool:
+        q, k, vv = v.s.q, v.s.k, v.v
+        buf = q.buf
+        B, C3, H, W = buf.shape
+        C = q.c1 - q.c0
+        if not (self.fused_attention and k.buf is buf and vv.buf is buf and (q.c0, k.c0, vv.c0) == (0, C, 2 * C) and C3 == 3 * C):
+            return False
+        if not self.ex.attention_supported(H * W, C) or len(buf.producers) != 1 or not isinstance(buf.producers[0], FusedConv):
+            return False
+        prod: FusedConv = buf.producers[0]
+        if prod.spec.out_row_scale is not None or prod.spec.aux or any(r is None for r in buf.readers):
+            return False
+        # q <- q * scale: folded into the q rows of the producing 1x1 conv (the kernel takes pre-scaled q)
+        if v.s.scale != 1.0:
+            prod.spec.out_row_scale = (C, float(v.s.scale))
+        buf.readers.append(None)
+        dst = self.fresh(B, C, H, W)
+        tok = buf.raw.permute(0, 2, 3, 1).reshape(B, H * W, 3 * C)
+        o_tok = dst.raw.permute(0, 2, 3, 1).reshape(B, H * W, C)
+        self.steps.append(("attention", self.ex.prepare_attention(tok, o_tok, self.pdl)))
+        self.env[id(out)] = Full([(dst, 0)])
+        return True
+
+    # ------------------------------------------------------------------ outputs / post-pass
+    def _output(self, lt: LazyTensor) -> torch.Tensor:
+        return self.runtime_tensor(lt)
+
+    def _post(self) -> None:
+        # the stem only has to exist where it is read: if every reader gathers it through one index set, restrict it
+        for rec in self.conv_ins:
+            rd = rec.out.readers
+            if (self.sparse_stem and rd and all(r is not None for r in rd)
+                    and all(up_ == 0 and blk_ <= 6 and i_ is not None and torch.equal(i_, rd[0][0]) for (i_, blk_, up_) in rd)):
+                rec.tiles, rec.tile_size = rd[0][0].contiguous(), max(blk_ for (_, blk_, _) in rd)
+                for t_ in ([rec.out._raw] if rec.out.has_raw else []) + [v[0] for v in rec.out.views.values()]:
+                    t_.zero_()          # never read outside the tiles; defined contents all the same
+        for fc in self.fused:
+            s = fc.spec
+            if s.dst is not None and not s.aux:
+                _ = s.dst.raw             # a value nobody transformed: keep the raw destination
+            self.ex.prepare_conv(fc)
+        for prep in self._pending_prepare:
+            prep()
+
+
+# =====================================================================================================================
+# public object
+# =====================================================================================================================
+class FusedStep:
+    """Traced + fused + graph-captured sparse forward of ``model`` for inputs shaped like ``args``.
+
+    ``step(*args)`` copies the tensor arguments into the static inputs, replays the program and returns the static
+    output tensor(s) (valid until the next call).  ``replay()`` skips the input copy."""
+
+    def __init__(self, model: nn.Module, *args, use_graph: bool = True, executor=None, **options):
+        if getattr(model, "mode", "sparse") != "sparse":
+            raise RuntimeError("FusedStep: run the dense pass, set_masks() and set_mode('sparse') first")
+        tensors = [a for a in args if isinstance(a, torch.Tensor)]
+        if not tensors:
+            raise TraceUnsupported("no tensor argument")
+        x = tensors[0]
+        self.dev, self.dtype = x.device, x.dtype
+        if executor is None:
+            if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
+                raise TraceUnsupported("the fused step needs CUDA fp16/bf16 inputs (tensor-core path); got %s %s" % (x.device, x.dtype))
+            executor = CudaExecutor(x.device, x.dtype)
+        self.ex = executor
+        self.model = model
+        self.static_inputs: List[torch.Tensor] = []
+        for t in tensors:
+            if t.dim() == 4:
+                s = torch.empty(t.shape, dtype=t.dtype, device=t.device, memory_format=torch.channels_last)
+            else:
+                s = torch.empty_like(t)
+            s.copy_(t)
+            self.static_inputs.append(s)
+        self._arg_template = [a if not isinstance(a, torch.Tensor) else None for a in args]
+        names = {id(m): n for n, m in model.named_modules()}
+        with torch.no_grad(), lazy.tracing() as tape:
+            it = iter(lazy.make_input(s, tape) for s in self.static_inputs)
+            largs = [next(it) if a is None else a for a in self._arg_template]
+            outs = nn.Module.__call__(model, *largs)
+        self.tape = tape
+        with torch.no_grad():
+            self.low = Lowering(tape, outs, self.static_inputs, executor, self.dtype, self.dev, module_names=names, **options)
+        self.steps = self.low.steps
+        self.fused = self.low.fused
+        self.outputs = self.low.outputs
+        self.output = self.outputs if isinstance(self.outputs, torch.Tensor) else None
+        self.eager_nodes = self.low.eager_nodes
+        self.graph = None
+        self.launches_per_step = 0
+        self._finalize(use_graph)
+
+    # ------------------------------------------------------------------ execution
+    def run_eager(self):
+        stream = torch.cuda.current_stream(self.dev).cuda_stream if self.dev.type == "cuda" else 0
+        with torch.no_grad():
+            for _kind, fn in self.steps:
+                fn(stream)
+        return self.outputs
+
+    def _finalize(self, use_graph: bool) -> None:
+        if self.dev.type != "cuda":
+            self.run_eager()
+            return
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.run_eager()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        before = self.ex.launch_counter()
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.run_eager()
+        else:
+            self.run_eager()
+        self.launches_per_step = self.ex.launch_counter() - before
+
+    def replay(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return self.outputs
+        return self.run_eager()
+
+    def __call__(self, *args):
+        tensors = [a for a in args if isinstance(a, torch.Tensor)]
+        for s, t in zip(self.static_inputs, tensors):
+            s.copy_(t, non_blocking=True)
+        return self.replay()
+
+    def matches(self, args) -> bool:
+        tensors = [a for a in args if isinstance(a, torch.Tensor)]
+        if len(tensors) != len(self.static_inputs) or len(args) != len(self._arg_template):
+            return False
+        for s, t in zip(self.static_inputs, tensors):
+            if s.shape != t.shape or s.dtype != t.dtype or s.device != t.device:
+                return False
+        return all((a is None and isinstance(b, torch.Tensor)) or (a is not None and not isinstance(b, torch.Tensor) and a == b)
+                   for a, b in zip(self._arg_template, args))
+
+    # ------------------------------------------------------------------ accounting
+    def algorithmic_bytes(self) -> int:
+        return sum(f.bytes for f in self.fused)
+
+    def algorithmic_flops(self) -> int:
+        return sum(f.flops for f in self.fused)

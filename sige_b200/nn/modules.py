@@ -26,9 +26,9 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from .. import ops
+from .. import lazy, ops
 from ..masks import reduce_mask
-from .state import SIGEModule, SIGEModuleWrapper
+from .state import SIGEModule, SIGEModuleWrapper, bump_cache_generation
 
 
 def activation(x: torch.Tensor, activation_name: str) -> torch.Tensor:
@@ -74,6 +74,10 @@ class SIGEConv2d(nn.Conv2d, SIGEModule):
         return self._packed[1], self._packed[2]
 
     def _sparse_forward(self, x: torch.Tensor) -> torch.Tensor:
+        if lazy.is_lazy(x):      # deferred execution (sige_b200.fused): recorded, fused with its gather / scatter later
+            ro = (x.shape[2] - self.dilation[0] * (self.kernel_size[0] - 1) - 1) // self.stride[0] + 1
+            so = (x.shape[3] - self.dilation[1] * (self.kernel_size[1] - 1) - 1) // self.stride[1] + 1
+            return lazy.record_module_call("sige.conv", self, (x,), (x.shape[0], self.out_channels, ro, so), x)
         if not x.is_cuda:
             raise RuntimeError("SIGEConv2d sparse mode needs a CUDA tensor (no CPU backend); got %s" % x.device)
         if isinstance(self.padding, str) or self.padding_mode != "zeros":
@@ -147,6 +151,9 @@ class Gather(SIGEModule):
             self.input_res = x.shape[2:]
             return x
         if self.mode == "sparse":
+            if lazy.is_lazy(x, scale, shift):
+                n = self.active_indices.size(0)
+                return lazy.record_module_call("sige.gather", self, (x, scale, shift), (x.shape[0] * n, x.shape[1], *self.block_size), x)
             idx = self.active_indices = _on(self.active_indices, x)
             return ops.gather(x, self.block_size[0], self.block_size[1], idx, scale, shift, self.activation_name,
                               self.activation_first)
@@ -194,10 +201,15 @@ class Scatter(SIGEModule):
             out = x if residual is None else x + residual
             self.output_res = out.shape[2:]
             self.original_outputs[self.cache_id] = out if ops.layout_of(out) >= 0 else out.contiguous()
+            bump_cache_generation()
             return out
         if self.mode == "sparse":
             g = self.gather.module
             cached = self.original_outputs[self.cache_id]
+            if lazy.is_lazy(x, residual):
+                if self.sparse_update:
+                    raise lazy.TraceUnsupported("sparse_update=True runs through the eager operator modules")
+                return lazy.record_module_call("sige.scatter", self, (x, residual), tuple(cached.shape), x if lazy.is_lazy(x) else residual)
             out = ops.scatter(x, cached, g.offset[0], g.offset[1], g.model_stride[0], g.model_stride[1],
                               _on(g.active_indices, x), residual)
             if self.sparse_update:
@@ -237,10 +249,16 @@ class ScatterWithBlockResidual(SIGEModule):
             self.output_res = out.shape[2:]
             self.original_outputs[self.cache_id] = out if ops.layout_of(out) >= 0 else out.contiguous()
             self.original_residuals[self.cache_id] = residual if ops.layout_of(residual) >= 0 else residual.contiguous()
+            bump_cache_generation()
             return out
         if self.mode == "sparse":
             mg, sg = self.main_gather.module, self.shortcut_gather.module
             y0, y1 = self.original_outputs[self.cache_id], self.original_residuals[self.cache_id]
+            if lazy.is_lazy(x, residual):
+                if self.sparse_update:
+                    raise lazy.TraceUnsupported("sparse_update=True runs through the eager operator modules")
+                return lazy.record_module_call("sige.scatter_block_residual", self, (x, residual), tuple(y0.shape),
+                                               x if lazy.is_lazy(x) else residual)
             idx0, idx1 = _on(mg.active_indices, x), _on(sg.active_indices, x)
             out = ops.scatter_with_block_residual(x, y0, residual, y1, mg.offset[0], mg.offset[1], mg.model_stride[0],
                                                   mg.model_stride[1], idx0, idx1)
@@ -282,9 +300,16 @@ class ScatterGather(SIGEModule):
         if self.mode == "full":
             self.output_res = x.shape[2:]
             self.original_outputs[self.cache_id] = x if ops.layout_of(x) >= 0 else x.contiguous()
+            bump_cache_generation()
             return x
         if self.mode == "sparse":
             cached = self.original_outputs[self.cache_id]
+            if lazy.is_lazy(x, scale, shift):
+                if self.sparse_update:
+                    raise lazy.TraceUnsupported("sparse_update=True runs through the eager operator modules")
+                n = g.active_indices.size(0)
+                return lazy.record_module_call("sige.scatter_gather", self, (x, scale, shift),
+                                               (cached.size(0) * n, x.shape[1], *g.block_size), x)
             idx = _on(g.active_indices, x)
             self.scatter_map = _on(self.scatter_map, x)
             out = ops.scatter_gather(x, cached, g.block_size[0], g.block_size[1], idx, self.scatter_map, scale, shift,

@@ -18,6 +18,7 @@ accepted next to fp32 (the reference rejects them, base.py:15,55-63).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -25,6 +26,14 @@ from torch import nn
 
 MODES = ("full", "sparse", "profile")
 SUPPORTED_DTYPES = [torch.float32, torch.float16, torch.bfloat16]
+
+# Bumped whenever a Scatter* / ScatterGather module (re)fills a cache in `full` mode: compiled fused steps that were
+# built from older caches are stale.
+_cache_generation = [0]
+
+
+def bump_cache_generation() -> None:
+    _cache_generation[0] += 1
 
 
 class SIGEModule(nn.Module):
@@ -104,13 +113,26 @@ class SIGEModuleWrapper:
 
 class SIGEModel(nn.Module):
     """Top-level wrapper: broadcasts mode / masks / cache controls to every SIGEModule below it
-    (reference base.py:95-129)."""
+    (reference base.py:95-129).
+
+    Beyond the reference: in ``sparse`` mode on a CUDA fp16/bf16 input the forward is run as a FUSED STEP
+    (``sige_b200.fused``): traced once on lazy handles, lowered to one fused sm_100a launch per wrapped layer,
+    captured in a CUDA graph and replayed on every later call — the model file itself is unchanged.  The compiled step
+    is keyed on (set_masks call, cache generation, cache_id, argument shapes) and rebuilt when any of them changes;
+    ``set_fused(False)`` (or SIGE_FUSED=0) keeps the eager operator modules, which is also what a forward that cannot
+    be traced falls back to (fp32 always runs eagerly: the tensor-core kernels are fp16/bf16)."""
 
     def __init__(self, call_super: bool = True):
         if call_super:
             super().__init__()
         self.mode = "full"
         self.timestamp = 0
+        self._sige_cache_id = 0
+        self._sige_sparse_update = False
+        self._fused_enabled = os.environ.get("SIGE_FUSED", "1") != "0"
+        self._fused_options: Dict = {}
+        self._fused_steps: Dict = {}
+        self.fused_step = None          # the step object that served the last fused call (for introspection / benchmarks)
 
     def _sige_modules(self):
         for m in self.modules():
@@ -129,13 +151,65 @@ class SIGEModel(nn.Module):
             m.set_mode(mode)
 
     def clear_cache(self):
+        bump_cache_generation()
+        self.__dict__.get("_fused_steps", {}).clear()
         for m in self._sige_modules():
             m.clear_cache()
 
     def set_cache_id(self, cache_id: int):
+        self.__dict__["_sige_cache_id"] = cache_id
         for m in self._sige_modules():
             m.set_cache_id(cache_id)
 
     def set_sparse_update(self, sparse_update: bool):
+        self.__dict__["_sige_sparse_update"] = sparse_update
         for m in self._sige_modules():
             m.set_sparse_update(sparse_update)
+
+    # ---- fused step -------------------------------------------------------------------------------------------------
+    def set_fused(self, enabled: bool = True, **options):
+        """Enable / disable the fused step and set its options (see sige_b200.fused.Lowering)."""
+        self.__dict__["_fused_enabled"] = bool(enabled)
+        self.__dict__["_fused_options"] = dict(options)
+        self.__dict__.setdefault("_fused_steps", {}).clear()
+        return self
+
+    def _fused_lookup(self, args):
+        d = self.__dict__
+        if not d.get("_fused_enabled", False) or d.get("mode") != "sparse" or d.get("_sige_sparse_update", False) or torch.is_grad_enabled():
+            return None
+        x = args[0] if args else None
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16)):
+            return None
+        from .. import lazy
+
+        if isinstance(x, lazy.LazyTensor):
+            return None
+        sig = tuple((tuple(a.shape), a.dtype, str(a.device)) if isinstance(a, torch.Tensor) else ("v", a) for a in args)
+        try:
+            hash(sig)
+        except TypeError:
+            return None
+        key = (d.get("timestamp", 0), _cache_generation[0], d.get("_sige_cache_id", 0), sig)
+        steps = d.setdefault("_fused_steps", {})
+        if key not in steps:
+            for k in [k for k in steps if k[0] != key[0] or k[1] != key[1]]:
+                del steps[k]           # older masks / older caches: their buffers are garbage now
+            from ..fused import FusedStep
+
+            try:
+                steps[key] = FusedStep(self, *args, **d.get("_fused_options", {}))
+            except lazy.TraceUnsupported as e:
+                import warnings
+
+                warnings.warn("sige: this forward cannot run as a fused step (%s); using the eager operator modules" % (e,))
+                steps[key] = None
+        return steps[key]
+
+    def __call__(self, *args, **kwargs):
+        step = None if kwargs else self._fused_lookup(args)
+        if step is None:
+            return super().__call__(*args, **kwargs)
+        self.__dict__["fused_step"] = step
+        out = step(*args)
+        return out.clone() if isinstance(out, torch.Tensor) else type(out)(o.clone() if isinstance(o, torch.Tensor) else o for o in out)

@@ -121,10 +121,10 @@ def measure_layers(layers, dtype, flush, reps: int = 10):
 
 
 def measure_dominant_kernel(model, dtype, flush):
-    from .workloads.ddpm import synthetic_inputs
+    from .workloads.ddpm import DDPMConfig, synthetic_inputs
 
     dev = next(model.parameters()).device
-    _, x1, _, t = synthetic_inputs(model.cfg, 0.012, seed=0)
+    _, x1, _, t = synthetic_inputs(getattr(model, "cfg", DDPMConfig()), 0.012, seed=0)
     x = x1.to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
     layers = conv_layers_of_step(model, x, t.to(dev))
     return measure_layers(layers, dtype, flush)

@@ -20,6 +20,10 @@ committed fixtures:
     ddpm_small_golden.npz DDPM U-Net miniature (64x64): full-pass and sparse-pass outputs
     ddpm256_golden.npz    DDPM 256x256 @1.2 % edit: sparse-pass output + tile counts
     ddpm256_r30_golden.npz  same at a 30 % edit (1296 tiles at 256x256)
+    ddpm256_r05_golden.npz, ddpm256_r15_golden.npz   the middle of BASELINE.json configs[4]'s sweep (sub-sampled output
+                          + checksums: the full tensor is regenerated on the GPU box only for r = 1.2 % / 30 %)
+
+    python tests/golden/make_golden.py --only ddpm256_r05,ddpm256_r15     regenerate a subset
 """
 from __future__ import annotations
 
@@ -85,6 +89,9 @@ def main():
     import numpy as np
     import torch
 
+    only = None
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
     ref_cpu = _reference_package()
     from sige.nn import Gather, Scatter, SIGEConv2d, SIGEModel, SIGEModule  # reference classes
     from sige.utils import downsample_mask, reduce_mask  # reference functions
@@ -92,6 +99,12 @@ def main():
     torch.set_num_threads(8)
     t = torch.from_numpy
 
+    if only is None:
+        _ops_and_example(ref_cpu, np, torch, t, Gather, Scatter, SIGEConv2d, SIGEModel, SIGEModule, reduce_mask)
+    _ddpm(np, torch, Gather, downsample_mask, only)
+
+
+def _ops_and_example(ref_cpu, np, torch, t, Gather, Scatter, SIGEConv2d, SIGEModel, SIGEModule, reduce_mask):
     # ------------------------------------------------------------------ ops
     rng = np.random.default_rng(20240924)
     out = {}
@@ -191,7 +204,13 @@ def main():
                         sparse_out_sub=sp.numpy()[:, ::4, ::4, ::4], dense_sparse_maxerr=np.array([err]),
                         out_abs_sum=np.array([float(sp.double().abs().sum())]))
 
+
+
+def _ddpm(np, torch, Gather, downsample_mask, only):
     # ------------------------------------------------------------------ DDPM U-Nets
+    sys.path.insert(0, REPO)
+    from sige_b200.workloads.ddpm import DDPMConfig, SIGEDDPMUNet, init_deterministic, synthetic_inputs
+
     sys.path.insert(0, os.path.join(REF, "diffusion"))
     from models.ddpm_arch.sige_fused_unet import SIGEFusedUNet  # the REFERENCE model
 
@@ -226,9 +245,12 @@ def main():
             payload["full0_out"] = full0.numpy()
         np.savez_compressed(os.path.join(HERE, tag + "_golden.npz"), **payload)
 
-    run_ddpm(DDPMConfig.small(), 0.05, "ddpm_small", keep_full=True)
-    run_ddpm(DDPMConfig(), 0.012, "ddpm256", keep_full=False)
-    run_ddpm(DDPMConfig(), 0.30, "ddpm256_r30", keep_full=False)      # BASELINE.json configs[4]: the large end of the edit sweep
+    jobs = [(DDPMConfig.small(), 0.05, "ddpm_small", True), (DDPMConfig(), 0.012, "ddpm256", False),
+            (DDPMConfig(), 0.30, "ddpm256_r30", False),      # BASELINE.json configs[4]: the large end of the edit sweep
+            (DDPMConfig(), 0.05, "ddpm256_r05", False), (DDPMConfig(), 0.15, "ddpm256_r15", False)]
+    for cfg, ratio, tag, keep in jobs:
+        if only is None or tag in only:
+            run_ddpm(cfg, ratio, tag, keep_full=keep)
 
 
 if __name__ == "__main__":

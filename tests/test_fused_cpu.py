@@ -1,0 +1,171 @@
+"""Tracing + lowering of an unmodified forward (sige_b200.lazy / sige_b200.fused), checked on the CPU.
+
+The launch records the lowering produces are interpreted by tests/sim_executor.py (plain fp32 torch ops following
+the contract of include/sige_b200.h) and the result is compared with the golden output the REFERENCE produced for the
+same weights and inputs (tests/golden/*.npz, made by tests/golden/make_golden.py).  This pins WHICH launches are
+emitted, with which buffers, folds and index lists; the kernels themselves are checked on the GPU.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, golden
+
+sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.path.insert(0, os.path.join(REPO, "baseline"))
+
+
+def _prepared(kind, cfg, ratio):
+    import loader
+    from sige.utils import downsample_mask
+    from sige_b200.workloads.ddpm import SIGEDDPMUNet, init_deterministic, synthetic_inputs
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if kind == "reference":
+            if not loader.available():
+                pytest.skip("baseline/_ref absent (python baseline/build_ref.py)")
+            model = loader.reference_ddpm_on_this_repo(cfg)
+        else:
+            model = SIGEDDPMUNet(cfg)
+        model = init_deterministic(model, seed=0).eval()
+    x0, x1, mask, t = synthetic_inputs(cfg, ratio, seed=0)
+    with torch.no_grad():
+        model.set_mode("full")
+        model(x0, t)
+        model.set_masks(downsample_mask(mask, min_res=8))
+        model.set_mode("sparse")
+    return model, x1, t
+
+
+@pytest.mark.parametrize("kind", ["reference", "intree"])
+@pytest.mark.parametrize("opts", [{}, {"producer_preop": False}, {"fuse_shortcut": False, "sparse_stem": False}, {"tc5": False}])
+def test_traced_ddpm_small_matches_reference_golden(kind, opts):
+    from sige_b200.fused import FusedStep
+    from sige_b200.workloads.ddpm import DDPMConfig
+    from sim_executor import SimExecutor
+
+    G = golden("ddpm_small_golden.npz")
+    model, x1, t = _prepared(kind, DDPMConfig.small(), float(G["ratio"][0]))
+    with torch.no_grad():
+        step = FusedStep(model, x1, t, executor=SimExecutor(), **opts)
+    assert step.eager_nodes == [], "every op of the DDPM forward must be lowered to a fused launch"
+    kinds = [k for k, _ in step.steps]
+    assert kinds.count("conv_in") == 1 and kinds.count("tail") == 1 and kinds.count("attention") == 4
+    n_sc = sum(1 for f in step.fused if f.spec.shortcut is not None)
+    assert (n_sc > 0) == (opts.get("fuse_shortcut", True) and opts.get("tc5", True) and opts.get("producer_preop", True))
+    ref = G["sparse_out"]
+    out = step.output.numpy()
+    assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-5
+    # a replay rewrites the same tiles with the same values
+    again = step.replay().numpy().copy()
+    assert np.array_equal(out, again)
+
+
+def test_traced_reference_ddpm256_launch_list():
+    """The north-star model file, unmodified: 86 fused launches + stem + 6 attention cores + tail, nothing eager."""
+    from sige_b200.fused import FusedStep
+    from sige_b200.workloads.ddpm import DDPMConfig
+    from sim_executor import SimExecutor
+
+    G = golden("ddpm256_golden.npz")
+    model, x1, t = _prepared("reference", DDPMConfig(), float(G["ratio"][0]))
+    with torch.no_grad():
+        step = FusedStep(model, x1, t, executor=SimExecutor())
+    assert step.eager_nodes == []
+    assert len(step.fused) == 86 and [k for k, _ in step.steps].count("attention") == 6
+    names = [f.name for f in step.fused]
+    assert "down.0.block.0.scatter_gather" in names and "up.0.block.2.scatter" in names
+    # tile counts of the reference (golden): 64 tiles at 256^2
+    assert step.fused[0].spec.N == 64
+    ref = G["sparse_out"]
+    assert np.abs(step.output.numpy() - ref).max() / np.abs(ref).max() < 1e-5
+
+
+def test_eager_islands_keep_the_result_exact():
+    """An op the lowering does not know (here: the attention core with its kernel disabled) runs as recorded torch calls
+    between the fused launches; everything around it stays fused."""
+    from sige_b200.fused import FusedStep
+    from sige_b200.workloads.ddpm import DDPMConfig
+    from sim_executor import SimExecutor
+
+    G = golden("ddpm_small_golden.npz")
+    model, x1, t = _prepared("intree", DDPMConfig.small(), float(G["ratio"][0]))
+    with torch.no_grad():
+        step = FusedStep(model, x1, t, executor=SimExecutor(), fused_attention=False)
+    assert "softmax" in step.eager_nodes and len(step.fused) == 34
+    ref = G["sparse_out"]
+    assert np.abs(step.output.numpy() - ref).max() / np.abs(ref).max() < 1e-5
+
+
+def test_foreign_math_on_the_tile_stack_falls_back_per_op():
+    """GauGAN-style: plain torch math on the gathered stack between Gather and the conv
+    (reference gaugan/models/sige_normalization.py:84-86).  The gather is materialised, the torch ops run as recorded,
+    and the conv + scatter still go out as ONE fused launch that reads the stack."""
+    from torch import nn
+
+    from sige.nn import Gather, Scatter, SIGEConv2d, SIGEModel, SIGEModule
+    from sige_b200.fused import FusedStep
+    from sige_b200.masks import reduce_mask  # noqa: F401
+    from sim_executor import SimExecutor
+
+    class Block(SIGEModule):
+        def __init__(self):
+            super().__init__()
+            self.conv = SIGEConv2d(64, 64, 3, padding=1)
+            self.gather = Gather(self.conv, 6)
+            self.scatter = Scatter(self.gather)
+
+        def forward(self, x, gamma):
+            h = self.gather(x)
+            if self.mode == "sparse":
+                h = nn.functional.leaky_relu(h * (1 + gamma), 0.2)
+            else:
+                h = nn.functional.leaky_relu(x * (1 + gamma), 0.2)
+            return self.scatter(self.conv(h))
+
+    class Net(SIGEModel):
+        def __init__(self):
+            super().__init__()
+            self.block = Block()
+
+        def forward(self, x):
+            return self.block(x, 0.25)
+
+    torch.manual_seed(0)
+    net = Net().eval()
+    x0 = torch.randn(1, 64, 24, 32)
+    mask = torch.zeros(24, 32, dtype=torch.bool)
+    mask[5:9, 20:27] = True
+    x1 = x0 + torch.randn_like(x0) * mask
+    with torch.no_grad():
+        net.set_mode("full")
+        net(x0)
+        dense = net(x1)
+        net(x0)
+        net.set_masks({(24, 32): mask})
+        net.set_mode("sparse")
+        step = FusedStep(net, x1, executor=SimExecutor())
+    assert len(step.fused) == 1 and step.fused[0].spec.src_is_stack and step.fused[0].spec.dst is not None
+    assert any(n.startswith("gather") for n in step.eager_nodes) and "leaky_relu" in step.eager_nodes
+    assert torch.allclose(step.output, dense, atol=1e-5)
+
+
+def test_value_dependent_forward_is_rejected():
+    from sige.nn import SIGEModel
+    from sige_b200.fused import FusedStep
+    from sige_b200.lazy import TraceUnsupported
+    from sim_executor import SimExecutor
+
+    class Net(SIGEModel):
+        def forward(self, x):
+            return x * 2 if float(x.sum()) > 0 else x
+
+    net = Net().eval()
+    net.set_mode("sparse")
+    with pytest.raises(TraceUnsupported):
+        FusedStep(net, torch.ones(1, 8, 4, 4), executor=SimExecutor())

@@ -1,11 +1,13 @@
-"""In-graph timeline of the DDPM step engine: every tcgen05 fused launch stamps globaltimer into its own trace
+"""In-graph timeline of the fused DDPM step: every tcgen05 fused launch stamps globaltimer into its own trace
 buffer (pointer captured with the kernel parameters), the CUDA graph is replayed, and the start/end of each kernel
 plus the gaps between consecutive kernels are printed.  Development aid, GPU only."""
 import ctypes, os, sys, warnings
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "baseline"))
 import torch
+import loader
 from sige_b200 import _cabi
-from sige_b200.engine import DDPMStepEngine, FusedConv
+from sige_b200.fused import FusedConv, FusedStep
 from sige_b200.masks import downsample_mask
 from sige_b200.workloads.ddpm import DDPMConfig, SIGEDDPMUNet, init_deterministic, synthetic_inputs
 
@@ -13,8 +15,13 @@ dev = torch.device("cuda", 0)
 cfg = DDPMConfig()
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
-    model = init_deterministic(SIGEDDPMUNet(cfg), seed=0).eval().to(dev).half().to(memory_format=torch.channels_last)
-x0, x1, mask, t = synthetic_inputs(cfg, 0.012, seed=0)
+    net = loader.reference_ddpm_on_this_repo(cfg) if loader.available() else SIGEDDPMUNet(cfg)
+    model = init_deterministic(net, seed=0).eval().to(dev).half().to(memory_format=torch.channels_last)
+ratio = 0.012
+for a in sys.argv[1:]:
+    if a.startswith("--ratio="):
+        ratio = float(a.split("=")[1])
+x0, x1, mask, t = synthetic_inputs(cfg, ratio, seed=0)
 cl = lambda a: a.to(dev).half().contiguous(memory_format=torch.channels_last)
 with torch.no_grad():
     model.set_mode("full"); model(cl(x0), t.to(dev))
@@ -28,8 +35,7 @@ def hook(fc):
     i = order.setdefault(id(fc), len(order))
     lib.sige_debug_set_trace(buf.data_ptr() + i * SLOT * 8)
 FusedConv.trace_hook = hook
-eng = DDPMStepEngine(model, cl(x1), use_graph=True, tc5=True, pdl="--no-pdl" not in sys.argv, branches="--no-branches" not in sys.argv,
-                     fused_attention="--no-fused-attention" not in sys.argv)
+eng = FusedStep(model, cl(x1), t.to(dev), use_graph=True, tc5=True, pdl="--no-pdl" not in sys.argv, fused_attention="--no-fused-attention" not in sys.argv)
 FusedConv.trace_hook = None
 lib.sige_debug_set_trace(None)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
