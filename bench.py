@@ -339,14 +339,20 @@ def run_ours(args):
     cfg = DDPMConfig()
     torch.backends.cudnn.benchmark = True
 
-    model, model_label = build_model(cfg, args.model)
-    model = model.to(dev).to(dtype).to(memory_format=torch.channels_last)
+    path = args.path
+    model, model_label = build_model(cfg, args.model if path == "fused" else "intree")
+    # fused: the reference's own flow — fp32 model, fp32 dense pass on the original image (untimed, as in the reference's
+    # Runner.profile) — with the sparse steps on the fp16/bf16 tensor-core path (set_fused(dtype=...)).
+    # modules: a half, channels-last model through the eager operator modules (in-tree model only: the reference's model
+    # file computes its time embedding in fp32 and cannot run its dense pass in half).
+    io_dtype = torch.float32 if path == "fused" else dtype
+    model = model.to(dev).to(io_dtype)
+    if path != "fused":
+        model = model.to(memory_format=torch.channels_last)
     # every rank edits the SAME original image with its OWN edit (seed + rank)
     x0, x1, mask, t = synthetic_inputs(cfg, args.ratio, seed=0, edit_seed=rank)
-    fmt = torch.channels_last
-    x0d = x0.to(dev).to(dtype).contiguous(memory_format=fmt)
+    x0d = x0.to(dev).to(io_dtype)
     td = t.to(dev)
-    path = args.path
 
     log("model built (%s); dense pass on the original image" % model_label)
     with torch.no_grad():
@@ -362,13 +368,13 @@ def run_ours(args):
         model.set_mode("sparse")
 
     log("masks set; building the step (path=%s)" % path)
-    x_host = x1.to(dtype).contiguous().pin_memory()
+    x_host = x1.to(io_dtype).contiguous().pin_memory()
     x_dev = x_host.to(dev)
-    out_host = torch.empty((1, cfg.out_ch, cfg.image_size, cfg.image_size), dtype=dtype).pin_memory()
+    out_host = torch.empty((1, cfg.out_ch, cfg.image_size, cfg.image_size), dtype=io_dtype).pin_memory()
     use_graph = not (args.no_graph or args.ncu)
 
     if path == "fused":
-        model.set_fused(True, use_graph=use_graph, pdl=not args.no_pdl, ksplit=args.ksplit, tc5=not args.no_tc5, producer_preop=not args.no_producer_preop,
+        model.set_fused(True, dtype=dtype, use_graph=use_graph, pdl=not args.no_pdl, ksplit=args.ksplit, tc5=not args.no_tc5, producer_preop=not args.no_producer_preop,
                         fuse_shortcut=not args.no_fuse_shortcut, fused_attention=not args.no_fused_attention, sparse_stem=not args.dense_stem)
         with torch.no_grad():
             model(x_dev, td)                 # first sparse call: trace -> lower -> capture
@@ -478,7 +484,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
             "config": {
                 "workload": workload_name(args.ratio), "model_file": model_label,
-                "path": path + (" (model(x, t) -> SIGEModel fused step: traced, lowered, CUDA graph)" if path == "fused" else ""),
+                "path": path + (" (model(x, t) -> SIGEModel fused step: traced, lowered, CUDA graph; fp32 model + fp32 I/O, %s arithmetic)" % args.dtype if path == "fused" else ""),
                 "edits_per_gpu": 1, "parallelism": "edits sharded 1/GPU, caches broadcast once (%d bytes), no per-step collective" % nbytes,
                 "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                 "timing": "per-step CUDA events on the launching stream, max over ranks",

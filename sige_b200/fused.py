@@ -856,10 +856,13 @@ class Lowering:
         outs = []
         for o in node.outs:
             fmt = torch.channels_last if (o.dim() == 4 and o.shape[1] > 1) else torch.contiguous_format
-            outs.append(torch.empty(tuple(o.shape), dtype=o.dtype, device=self.dev, memory_format=fmt))
+            outs.append(torch.empty(tuple(o.shape), dtype=self.dtype if o.dtype.is_floating_point else o.dtype, device=self.dev, memory_format=fmt))
 
         def sub(o):
-            return getters[id(o)] if isinstance(o, LazyTensor) else o
+            if not isinstance(o, LazyTensor):
+                return o
+            g = getters[id(o)]
+            return g if g.dtype == o.dtype else g.to(o.dtype)      # mixed precision: the recorded call saw the model's dtype
 
         op, module, multi = node.op, node.module, node.multi
 
@@ -1403,24 +1406,29 @@ class FusedStep:
     ``step(*args)`` copies the tensor arguments into the static inputs, replays the program and returns the static
     output tensor(s) (valid until the next call).  ``replay()`` skips the input copy."""
 
-    def __init__(self, model: nn.Module, *args, use_graph: bool = True, executor=None, **options):
+    def __init__(self, model: nn.Module, *args, use_graph: bool = True, executor=None, dtype: Optional[torch.dtype] = None, **options):
+        """``dtype``: arithmetic / storage type of the fused step (fp16 or bf16).  Defaults to the input's dtype; an fp32
+        model (the reference's own precision: its dense pass then stays exactly the reference's) runs its sparse steps on
+        the tensor cores with ``dtype=torch.float16`` — activations, caches and weights are converted once at build."""
         if getattr(model, "mode", "sparse") != "sparse":
             raise RuntimeError("FusedStep: run the dense pass, set_masks() and set_mode('sparse') first")
         tensors = [a for a in args if isinstance(a, torch.Tensor)]
         if not tensors:
             raise TraceUnsupported("no tensor argument")
         x = tensors[0]
-        self.dev, self.dtype = x.device, x.dtype
+        self.dev, self.dtype = x.device, (dtype or x.dtype)
         if executor is None:
-            if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
-                raise TraceUnsupported("the fused step needs CUDA fp16/bf16 inputs (tensor-core path); got %s %s" % (x.device, x.dtype))
-            executor = CudaExecutor(x.device, x.dtype)
+            if not x.is_cuda or self.dtype not in (torch.float16, torch.bfloat16):
+                raise TraceUnsupported("the fused step needs CUDA tensors and an fp16/bf16 compute dtype (tensor-core path); got %s %s" % (x.device, self.dtype))
+            executor = CudaExecutor(x.device, self.dtype)
         self.ex = executor
         self.model = model
         self.static_inputs: List[torch.Tensor] = []
+        self._arg_dtypes = [t.dtype for t in tensors]
         for t in tensors:
+            dt = self.dtype if (t.dtype.is_floating_point and t.dim() == 4) else t.dtype
             if t.dim() == 4:
-                s = torch.empty(t.shape, dtype=t.dtype, device=t.device, memory_format=torch.channels_last)
+                s = torch.empty(t.shape, dtype=dt, device=t.device, memory_format=torch.channels_last)
             else:
                 s = torch.empty_like(t)
             s.copy_(t)
@@ -1428,7 +1436,7 @@ class FusedStep:
         self._arg_template = [a if not isinstance(a, torch.Tensor) else None for a in args]
         names = {id(m): n for n, m in model.named_modules()}
         with torch.no_grad(), lazy.tracing() as tape:
-            it = iter(lazy.make_input(s, tape) for s in self.static_inputs)
+            it = iter(lazy.make_input(s, tape, dtype=dt) for s, dt in zip(self.static_inputs, self._arg_dtypes))
             largs = [next(it) if a is None else a for a in self._arg_template]
             outs = nn.Module.__call__(model, *largs)
         self.tape = tape
@@ -1487,8 +1495,8 @@ class FusedStep:
         tensors = [a for a in args if isinstance(a, torch.Tensor)]
         if len(tensors) != len(self.static_inputs) or len(args) != len(self._arg_template):
             return False
-        for s, t in zip(self.static_inputs, tensors):
-            if s.shape != t.shape or s.dtype != t.dtype or s.device != t.device:
+        for s, t, dt in zip(self.static_inputs, tensors, self._arg_dtypes):
+            if s.shape != t.shape or dt != t.dtype or s.device != t.device:
                 return False
         return all((a is None and isinstance(b, torch.Tensor)) or (a is not None and not isinstance(b, torch.Tensor) and a == b)
                    for a, b in zip(self._arg_template, args))

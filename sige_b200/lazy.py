@@ -224,7 +224,7 @@ class tracing:
         return False
 
 
-def make_input(t: torch.Tensor, tape: Tape) -> LazyTensor:
-    lt = LazyTensor(t.shape, t.dtype, t.device, strides=None, node=None, slot=len(tape.inputs), tape=tape)
+def make_input(t: torch.Tensor, tape: Tape, dtype: Optional[torch.dtype] = None) -> LazyTensor:
+    lt = LazyTensor(t.shape, dtype or t.dtype, t.device, strides=None, node=None, slot=len(tape.inputs), tape=tape)
     tape.inputs.append(lt)
     return lt

@@ -120,7 +120,9 @@ class SIGEModel(nn.Module):
     captured in a CUDA graph and replayed on every later call — the model file itself is unchanged.  The compiled step
     is keyed on (set_masks call, cache generation, cache_id, argument shapes) and rebuilt when any of them changes;
     ``set_fused(False)`` (or SIGE_FUSED=0) keeps the eager operator modules, which is also what a forward that cannot
-    be traced falls back to (fp32 always runs eagerly: the tensor-core kernels are fp16/bf16)."""
+    be traced falls back to.  An fp32 model (the reference's own precision) keeps its dense pass exactly as the reference
+    computes it and runs its sparse steps on the tensor cores after ``set_fused(True, dtype=torch.float16)``; without that
+    opt-in fp32 inputs always run through the eager fp32 operator modules."""
 
     def __init__(self, call_super: bool = True):
         if call_super:
@@ -179,7 +181,8 @@ class SIGEModel(nn.Module):
         if not d.get("_fused_enabled", False) or d.get("mode") != "sparse" or d.get("_sige_sparse_update", False) or torch.is_grad_enabled():
             return None
         x = args[0] if args else None
-        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16)):
+        compute = d.get("_fused_options", {}).get("dtype")
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and (compute or x.dtype) in (torch.float16, torch.bfloat16)):
             return None
         from .. import lazy
 
@@ -212,4 +215,9 @@ class SIGEModel(nn.Module):
             return super().__call__(*args, **kwargs)
         self.__dict__["fused_step"] = step
         out = step(*args)
-        return out.clone() if isinstance(out, torch.Tensor) else type(out)(o.clone() if isinstance(o, torch.Tensor) else o for o in out)
+        like = args[0].dtype      # results are fresh tensors in the caller's dtype (the static buffers are reused by the next call)
+
+        def fresh(o):
+            return o.to(like, copy=True) if (isinstance(o, torch.Tensor) and o.dtype.is_floating_point) else (o.clone() if isinstance(o, torch.Tensor) else o)
+
+        return fresh(out) if isinstance(out, torch.Tensor) else type(out)(fresh(o) for o in out)

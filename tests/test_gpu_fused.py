@@ -30,6 +30,9 @@ def _model(kind, cfg):
 
 
 def _prepared(kind, cfg, ratio, dtype, channels_last=True):
+    """dtype fp32: the reference's own flow — fp32 model, fp32 dense pass — with the sparse steps opted into fp16 tensor-core
+    arithmetic (set_fused(dtype=...)); dtype fp16: a half model end to end (the in-tree workload supports it; the
+    reference's model file computes its time embedding in fp32 and cannot run its dense pass in half)."""
     from sige.utils import downsample_mask
     from sige_b200.workloads.ddpm import synthetic_inputs
 
@@ -42,6 +45,8 @@ def _prepared(kind, cfg, ratio, dtype, channels_last=True):
         model(x0.to(DEV).to(dtype), t.to(DEV))
         model.set_masks(downsample_mask(mask.to(DEV), min_res=8))
         model.set_mode("sparse")
+    if dtype == torch.float32:
+        model.set_fused(True, dtype=torch.float16)
     return model, x1.to(DEV).to(dtype), t.to(DEV)
 
 
@@ -67,7 +72,7 @@ def test_reference_model_file_unmodified_runs_fused(channels_last):
     from sige_b200.workloads.ddpm import DDPMConfig
 
     G = golden("ddpm256_golden.npz")
-    model, x1, t = _prepared("reference", DDPMConfig(), float(G["ratio"][0]), torch.float16, channels_last)
+    model, x1, t = _prepared("reference", DDPMConfig(), float(G["ratio"][0]), torch.float32, channels_last)
     assert type(model).__module__ == "models.ddpm_arch.sige_fused_unet"
     pristine = [(n, v.clone()) for n, v in cache_tensors(model)]
     with torch.no_grad():
@@ -85,18 +90,20 @@ def test_reference_model_file_unmodified_runs_fused(channels_last):
         assert _cabi.lib().sige_tile_conv_plan(ctypes_ref(f.desc), ctypes_ref(pl)) == 0
         n_tc5 += pl.path
     assert n_tc5 >= 81, "the tcgen05 kernel must carry the step (%d of %d launches)" % (n_tc5, len(step.fused))
-    assert out1.data_ptr() != out2.data_ptr() and torch.equal(out1, out2), "results are fresh tensors, replay is idempotent"
+    assert out1.dtype == torch.float32 and out1.data_ptr() != out2.data_ptr() and torch.equal(out1, out2), "results are fresh tensors, replay is idempotent"
     for (n, a), (_, b) in zip(pristine, cache_tensors(model)):
         assert torch.equal(a, b), "the fused step must not touch the module caches (%s)" % n
     e_max, e_rms, e_rel = _errs(out1.float().cpu().numpy(), G["sparse_out"])
     print("reference model fused (channels_last=%s): max %.3g rms %.3g rel %.3g, %d launches/step" % (channels_last, e_max, e_rms, e_rel, step.launches_per_step))
     assert e_max <= TOL_MAX and e_rms <= TOL_RMS and e_rel <= TOL_REL
-    # the eager operator modules give the same answer (different evaluation order: fp16 network tolerance)
+    # the eager fp32 operator modules reproduce the reference to fp32 accuracy; the fp16 fused step stays within the fp16 tolerance of them
     model.set_fused(False)
     with torch.no_grad():
         via_modules = model(x1, t).float()
+    m_max, _, _ = _errs(via_modules.cpu().numpy(), G["sparse_out"])
     e_mod = float((out1.float() - via_modules).abs().max() / via_modules.abs().max())
-    assert model.fused_step is step and e_mod <= TOL_MAX
+    print("eager fp32 modules vs reference golden: %.3g; fused fp16 vs modules: %.3g" % (m_max, e_mod))
+    assert model.fused_step is step and m_max <= 2e-5 and e_mod <= TOL_MAX
 
 
 def ctypes_ref(obj):
@@ -148,7 +155,7 @@ def test_fused_step_edit_sweep_vs_reference_golden(tag, tol_max, tol_rms):
     from sige_b200.workloads.ddpm import DDPMConfig
 
     G = golden(tag + "_golden.npz")
-    model, x1, t = _prepared("reference", DDPMConfig(), float(G["ratio"][0]), torch.float16)
+    model, x1, t = _prepared("reference", DDPMConfig(), float(G["ratio"][0]), torch.float32)
     with torch.no_grad():
         out = model(x1, t).float().cpu().numpy()
     assert model.fused_step is not None and model.fused_step.eager_nodes == []
