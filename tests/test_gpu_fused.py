@@ -15,6 +15,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _exact_fp32_dense_pass():
+    """The dense pass of an fp32 model goes through cuDNN; TF32 (torch's default for convolutions) would put 1e-3-level
+    noise into the caches and hide what the sparse path itself contributes."""
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+
+
 def _model(kind, cfg):
     import loader
     from sige_b200.workloads.ddpm import SIGEDDPMUNet, init_deterministic
