@@ -107,6 +107,7 @@ class ConvSpec:
         self.residual: Optional[torch.Tensor] = None
         self.aux: List[Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], str]] = []
         self.shortcut = None                                 # (src tensors, weight fp32 OI11, bias fp32, flags uint8 [N] or None)
+        self.shortcut_key = None
         self.pdl = False
         self.tc5 = False
         self.ksplit = 0
@@ -194,7 +195,10 @@ class ConvInRec:
 # =====================================================================================================================
 # executors
 # =====================================================================================================================
-_PACKED: Dict = {}       # packed weights survive re-compilation (new masks, same weights)
+# Packed weights survive re-compilation (new masks, same weights).  Keyed by the IDENTITY of the parameter object (held
+# weakly and re-checked) + its version counter — never by address: the caching allocator hands a freed model's addresses to
+# the next one.
+_PACKED: Dict = {}
 
 
 class CudaExecutor:
@@ -208,11 +212,20 @@ class CudaExecutor:
         self.ops, self.device, self.dtype = ops, device, dtype
 
     def _pack(self, w: torch.Tensor, key) -> torch.Tensor:
-        if key is not None and key in _PACKED:
-            return _PACKED[key]
+        """key: None (do not cache) or (parameter object, tag)."""
+        import weakref
+
+        if key is not None:
+            param, tag = key
+            k = (id(param), tag, self.dtype)
+            hit = _PACKED.get(k)
+            if hit is not None and hit[0]() is param and hit[1] == param._version and hit[2].device == param.device:
+                return hit[2]
         wp = self.ops.pack_conv_weight(w.contiguous(), self.dtype)
         if key is not None:
-            _PACKED[key] = wp
+            for dead in [kk for kk, vv in _PACKED.items() if vv[0]() is None]:
+                del _PACKED[dead]
+            _PACKED[k] = (weakref.ref(param), param._version, wp)
         return wp
 
     def prepare_conv(self, fc: FusedConv) -> None:
@@ -229,7 +242,7 @@ class CudaExecutor:
             if b is not None:
                 b = b.clone()
                 b[:rows] *= f
-            key = None if key is None else key + (("rows", rows, f),)
+            key = None
         wp = self._pack(w, key)
         b32 = None if b is None else b.float().contiguous()
         d = ops.tile_conv_descriptor()
@@ -275,7 +288,7 @@ class CudaExecutor:
         d.n_src2 = 0
         if s.shortcut is not None:
             sc_tensors, sc_w, sc_b, sc_flags = s.shortcut
-            w2 = self._pack(sc_w, None if s.weight_key is None else s.weight_key + ("shortcut",))
+            w2 = self._pack(sc_w, s.shortcut_key)
             b2 = None if sc_b is None else sc_b.float().contiguous()
             d.n_src2 = len(sc_tensors)
             for i, t in enumerate(sc_tensors):
@@ -586,7 +599,7 @@ class Lowering:
         s.name = name
         w32 = weight.detach().float()
         b32 = None if bias is None else bias.detach().float()
-        key = (weight.data_ptr(), weight._version, tuple(weight.shape), self.dtype, str(self.dev))
+        key = (weight, "w")
         if weight_fold is not None:        # exact fold of a per-input-channel affine (no activation) into a 1x1 conv
             f_scale, f_shift = weight_fold
             assert w32.shape[2] == 1 and w32.shape[3] == 1
@@ -594,7 +607,7 @@ class Lowering:
                 b32 = (torch.zeros(w32.shape[0], device=w32.device) if b32 is None else b32) + (w32[:, :, 0, 0] @ f_shift.to(w32.device))
             if f_scale is not None:
                 w32 = w32 * f_scale.to(w32.device).view(1, -1, 1, 1)
-            key = key + ("fold", None if f_scale is None else (f_scale.data_ptr(), f_scale._version), None if f_shift is None else (f_shift.data_ptr(), f_shift._version))
+            key = None                      # folded with per-image statistics: never cached
             self._keepalive.append(weight_fold)
         s.weight, s.bias, s.weight_key = w32, b32, key
         s.k, s.stride, s.off, s.block = int(weight.shape[2]), stride, off, block
@@ -642,6 +655,7 @@ class Lowering:
             for b_ in sc_bufs:
                 b_.readers.append((idx, block, 0))      # the fused shortcut reads the centre 4x4 of conv2's 6x6 tiles
             s.shortcut = ([b_.raw for b_ in sc_bufs], sc_w.detach().float(), None if sc_b is None else sc_b.detach().float(), sc_flags)
+            s.shortcut_key = (sc_w, "w")
         fc = FusedConv(s)
         if n == 0:
             return None

@@ -77,7 +77,7 @@ def _ddpm(cfg, dtype, cl):
     model = model.to(DEV).to(dtype)
     if cl:
         model = model.to(memory_format=torch.channels_last)
-    return model
+    return model.set_fused(False)      # this file checks the eager operator modules; the fused step has tests/test_gpu_fused.py
 
 
 def _sparse_step(model, cfg, ratio, dtype, cl):
