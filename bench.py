@@ -64,6 +64,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--ratio", type=float, default=0.012)
+    ap.add_argument("--edits", type=int, default=1, help="independent edits of the same original image per GPU, batched in one fused step "
+                                                         "(each with its own mask; weights are read once per step)")
+    ap.add_argument("--total-edits", type=int, default=0, help="BASELINE.json configs[4]: a FIXED batch of edits sharded over the GPUs "
+                                                               "(strong scaling); overrides --edits with total/world per GPU")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--path", default="fused", choices=["fused", "modules"],
                     help="fused = model(x, t) as a traced, fused, graph-captured step (the default behaviour of SIGEModel); "
@@ -349,8 +353,28 @@ def run_ours(args):
     model = model.to(dev).to(io_dtype)
     if path != "fused":
         model = model.to(memory_format=torch.channels_last)
-    # every rank edits the SAME original image with its OWN edit (seed + rank)
-    x0, x1, mask, t = synthetic_inputs(cfg, args.ratio, seed=0, edit_seed=rank)
+    # every rank edits the SAME original image with its OWN edits (edit seed = global edit number; edits after the first of a
+    # rank are moved to other places of the image so that the batch does not share tiles)
+    n_edits = args.edits
+    if args.total_edits:
+        if args.total_edits % world:
+            raise SystemExit("--total-edits must be a multiple of the number of GPUs")
+        n_edits = args.total_edits // world
+    if n_edits > 1 and path != "fused":
+        raise SystemExit("a batch of independent edits runs as a fused step only")
+    x0 = None
+    edit_x, edit_masks = [], []
+    for e in range(n_edits):
+        ge = rank * n_edits + e
+        x0, x1e, mask_e, t = synthetic_inputs(cfg, args.ratio, seed=0, edit_seed=ge)
+        if e > 0:
+            g = torch.Generator().manual_seed(1000 + ge)
+            shift = tuple(int(v) for v in torch.randint(-96, 97, (2,), generator=g))
+            mask_e = torch.roll(mask_e, shift, (0, 1))
+            x1e = x0 + torch.roll(x1e - x0, shift, (2, 3))
+        edit_x.append(x1e)
+        edit_masks.append(mask_e)
+    x1 = torch.cat(edit_x, 0)
     x0d = x0.to(dev).to(io_dtype)
     td = t.to(dev)
 
@@ -364,13 +388,18 @@ def run_ours(args):
             nbytes = broadcast_caches(model, src=0)
         else:
             nbytes = 0
-        model.set_masks(downsample_mask(mask.to(dev), min_res=8))
+        if n_edits == 1:
+            model.set_masks(downsample_mask(edit_masks[0].to(dev), min_res=8))
+        else:
+            from sige_b200.masks import stack_mask_pyramids
+
+            model.set_masks(stack_mask_pyramids([downsample_mask(m.to(dev), min_res=8) for m in edit_masks]))
         model.set_mode("sparse")
 
-    log("masks set; building the step (path=%s)" % path)
+    log("masks set; building the step (path=%s, %d edit(s) per GPU)" % (path, n_edits))
     x_host = x1.to(io_dtype).contiguous().pin_memory()
     x_dev = x_host.to(dev)
-    out_host = torch.empty((1, cfg.out_ch, cfg.image_size, cfg.image_size), dtype=io_dtype).pin_memory()
+    out_host = torch.empty((n_edits, cfg.out_ch, cfg.image_size, cfg.image_size), dtype=io_dtype).pin_memory()
     use_graph = not (args.no_graph or args.ncu)
 
     if path == "fused":
@@ -458,8 +487,8 @@ def run_ours(args):
     ms_e2e = region(args.steps, True)
     clocks = sampler.stop()
 
-    value = world * args.steps / (ms / 1e3)
-    e2e_value = world * args.steps / (ms_e2e / 1e3)
+    value = world * n_edits * args.steps / (ms / 1e3)            # denoising steps of ONE edit per second, summed over edits and GPUs
+    e2e_value = world * n_edits * args.steps / (ms_e2e / 1e3)
 
     log("timed: %.3f ms/step resident, %.3f ms/step e2e; roofline + cpu baseline" % (ms / args.steps, ms_e2e / args.steps))
     roof = None
@@ -481,11 +510,12 @@ def run_ours(args):
         line = {
             "metric": "DDPM 256x256 denoising steps/sec @1.2% edit", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
+            "scaling": "strong" if args.total_edits else "weak", "vs_baseline": None, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
             "config": {
                 "workload": workload_name(args.ratio), "model_file": model_label,
                 "path": path + (" (model(x, t) -> SIGEModel fused step: traced, lowered, CUDA graph; fp32 model + fp32 I/O, %s arithmetic)" % args.dtype if path == "fused" else ""),
-                "edits_per_gpu": 1, "parallelism": "edits sharded 1/GPU, caches broadcast once (%d bytes), no per-step collective" % nbytes,
+                "edits_per_gpu": n_edits, "total_edits": n_edits * world,
+                "parallelism": "edits sharded %d/GPU (batched in one fused step), caches broadcast once (%d bytes), no per-step collective" % (n_edits, nbytes),
                 "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                 "timing": "per-step CUDA events on the launching stream, max over ranks",
             },

@@ -69,7 +69,7 @@ class Buf:
     def raw(self) -> torch.Tensor:
         if self._raw is None:
             if self.cached_init is not None:
-                self._raw = self.owner.clone_cache(self.cached_init)
+                self._raw = self.owner.clone_cache(self.cached_init, self.shape[0])
             else:
                 self._raw = self.owner.empty(*self.shape)
         return self._raw
@@ -89,6 +89,7 @@ class ConvSpec:
         self.B = 1
         self.H = self.W = 0
         self.idx: Optional[torch.Tensor] = None
+        self.tile_img: Optional[torch.Tensor] = None         # int32 [N]: a batch of independent edits (idx = concatenated lists)
         self.N = 0
         self.block = 0
         self.scale: Optional[torch.Tensor] = None            # fp32 [Cin] or [B, Cin]
@@ -147,18 +148,18 @@ class FusedConv:
     # ---- accounting (algorithmic bytes / flops of one fused launch)
     @property
     def tiles(self) -> int:
-        return self.spec.B * self.spec.N
+        return self.spec.N if self.spec.tile_img is not None else self.spec.B * self.spec.N
 
     @property
     def out_elems(self) -> int:
         s = self.spec
         ro = (s.block - s.k) // s.stride + 1
-        return s.B * s.N * s.Cout * ro * ro
+        return self.tiles * s.Cout * ro * ro
 
     @property
     def bytes(self) -> int:
         s = self.spec
-        n = s.B * s.N
+        n = self.tiles
         dsts = (1 if (s.dst is not None and s.dst.has_raw) or s.dst_stack is not None else 0) + (1 if s.residual is not None else 0) + len(s.aux)
         b = 2 * (n * s.Cin * s.block * s.block + s.k * s.k * s.Cout * s.Cin + self.out_elems * dsts)
         if s.shortcut is not None:
@@ -170,9 +171,9 @@ class FusedConv:
     def flops(self) -> int:
         s = self.spec
         ro = (s.block - s.k) // s.stride + 1
-        f = 2 * s.B * s.N * ro * ro * s.Cout * s.Cin * s.k * s.k
+        f = 2 * self.tiles * ro * ro * s.Cout * s.Cin * s.k * s.k
         if s.shortcut is not None:
-            f += 2 * s.B * s.N * ro * ro * s.Cout * int(s.shortcut[1].shape[1])
+            f += 2 * self.tiles * ro * ro * s.Cout * int(s.shortcut[1].shape[1])
         return f
 
 
@@ -183,6 +184,7 @@ class ConvInRec:
         self.x, self.weight, self.bias, self.out = x, weight, bias, out
         self.aux: List = []
         self.tiles: Optional[torch.Tensor] = None   # tile origins when every reader gathers the stem through ONE index set
+        self.tile_img: Optional[torch.Tensor] = None
         self.tile_size = 6
 
     def can_aux(self) -> bool:
@@ -298,6 +300,7 @@ class CudaExecutor:
             d.bias2 = None if b2 is None else b2.data_ptr()
             d.sc_flags = None if sc_flags is None else sc_flags.data_ptr()
             keep += [w2, b2]
+        d.tile_img = None if s.tile_img is None else s.tile_img.data_ptr()
         fc.desc, fc.keep = d, keep
         fc.launch_fn = lambda stream, d=d: ops.launch_tile_conv(d, stream)
 
@@ -309,7 +312,7 @@ class CudaExecutor:
         out = rec.out.raw
 
         def run(_stream):
-            ops.conv_in_nhwc(rec.x, w, b, out=out, aux=aux, tiles=rec.tiles, tile_size=rec.tile_size)
+            ops.conv_in_nhwc(rec.x, w, b, out=out, aux=aux, tiles=rec.tiles, tile_size=rec.tile_size, tile_img=rec.tile_img)
 
         return run
 
@@ -506,17 +509,21 @@ class Lowering:
     def empty(self, b: int, c: int, h: int, w: int) -> torch.Tensor:
         return torch.empty((b, c, h, w), dtype=self.dtype, device=self.dev, memory_format=torch.channels_last)
 
-    def clone_cache(self, cache: torch.Tensor) -> torch.Tensor:
-        return cache.detach().to(self.dtype).clone(memory_format=torch.channels_last)
+    def clone_cache(self, cache: torch.Tensor, batch: int) -> torch.Tensor:
+        c = cache.detach().to(self.dtype)
+        if batch != c.shape[0]:            # a batch of edits of ONE original image: every edit starts from the same cached activation
+            c = c.expand(batch, *c.shape[1:])
+        return c.clone(memory_format=torch.channels_last)
 
     def fresh(self, b: int, c: int, h: int, w: int) -> Buf:
         """A buffer that is completely rewritten every step (dense layers)."""
         return Buf(self, (b, c, h, w))
 
-    def cached(self, cache: torch.Tensor) -> Buf:
+    def cached(self, cache: torch.Tensor, batch: Optional[int] = None) -> Buf:
         """A buffer initialised from a module cache; only active tiles are rewritten per step.  The program owns a
-        copy (the module's cache stays pristine)."""
-        return Buf(self, cache.shape, cached_init=cache.detach())
+        copy (the module's cache stays pristine).  `batch`: number of independent edits sharing the cache."""
+        shape = tuple(cache.shape) if batch is None else (batch, *cache.shape[1:])
+        return Buf(self, shape, cached_init=cache.detach())
 
     def vec(self, v: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         """fp32 contiguous copy of a per-channel vector (kept alive; one copy per distinct source)."""
@@ -586,7 +593,7 @@ class Lowering:
     def emit_conv(self, name: str, segs: Sequence[Tuple[Buf, int]], pre: Optional[Pre], hw: Tuple[int, int], idx: torch.Tensor, block: int,
                   weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, off: int, dst: Optional[Buf], residual: Optional[Buf] = None,
                   shortcut=None, stack_src: Optional[torch.Tensor] = None, dst_stack: Optional[torch.Tensor] = None,
-                  weight_fold: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Optional[FusedConv]:
+                  weight_fold: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, tile_img: Optional[torch.Tensor] = None) -> Optional[FusedConv]:
         """Each source is (buffer, upsample flag); `pre` spans the concatenated channels.  An affine source is read from the
         pre-transformed view its producer maintains, else the gather stage applies the pre-op."""
         if stack_src is not None:            # rows are b*N + i (reference sige/cuda/gather_kernel.cu:30)
@@ -612,7 +619,7 @@ class Lowering:
         s.weight, s.bias, s.weight_key = w32, b32, key
         s.k, s.stride, s.off, s.block = int(weight.shape[2]), stride, off, block
         s.B, s.H, s.W = B, hw[0], hw[1]
-        s.idx, s.N = idx, n
+        s.idx, s.N, s.tile_img = idx, n, tile_img
         s.pdl, s.tc5, s.ksplit = self.pdl, self.tc5, self.ksplit
         if stack_src is not None:
             s.src_is_stack = True
@@ -643,17 +650,17 @@ class Lowering:
             else:
                 tensors = [b_.raw for (b_, _) in segs]
             for (b_, up_) in segs:
-                b_.readers.append((idx, block, up_))
+                b_.readers.append((idx, block, up_, tile_img))
             s.srcs = [(t, up) for t, (_, up) in zip(tensors, segs)]
             del gather_side
         if residual is not None:
-            residual.readers.append((idx, block, 0))
+            residual.readers.append((idx, block, 0, tile_img))
             s.residual = residual.raw
         s.dst, s.dst_stack = dst, dst_stack
         if shortcut is not None:
             sc_bufs, sc_w, sc_b, sc_flags = shortcut
             for b_ in sc_bufs:
-                b_.readers.append((idx, block, 0))      # the fused shortcut reads the centre 4x4 of conv2's 6x6 tiles
+                b_.readers.append((idx, block, 0, tile_img))      # the fused shortcut reads the centre 4x4 of conv2's 6x6 tiles
             s.shortcut = ([b_.raw for b_ in sc_bufs], sc_w.detach().float(), None if sc_b is None else sc_b.detach().float(), sc_flags)
             s.shortcut_key = (sc_w, "w")
         fc = FusedConv(s)
@@ -729,16 +736,18 @@ class Lowering:
         return (pre.scale is not None and pre.scale.dim() == 2) or (pre.shift is not None and pre.shift.dim() == 2)
 
     def tile_conv_args(self, co: ConvOut):
-        """(segs, pre, hw, idx, block, off, stack_src) of a conv on tiles."""
+        """(segs, pre, hw, idx, block, off, stack_src, tile_img) of a conv on tiles."""
         st = co.src
         if isinstance(st, RealStack):
             t = st.tensor
-            return None, None, (t.shape[2], t.shape[3]), None, int(t.shape[2]), 0, t
+            return None, None, (t.shape[2], t.shape[3]), None, int(t.shape[2]), 0, t, None
         g = st.gather
         pre = None
         if st.scale is not None or st.shift is not None or g.activation_name != "identity":
             pre = Pre(self._chan_vec(st.scale, st.src), self._chan_vec(st.shift, st.src), None if g.activation_name == "identity" else g.activation_name)
-        return st.src.segs, pre, st.src.HW, g.active_indices.to(self.dev), int(g.block_size[0]), int(g.offset[0]), None
+        timg = getattr(g, "tile_images", None)
+        return (st.src.segs, pre, st.src.HW, g.active_indices.to(self.dev), int(g.block_size[0]), int(g.offset[0]), None,
+                None if timg is None else timg.to(self.dev))
 
     def _chan_vec(self, t: Optional[torch.Tensor], f: Full) -> Optional[torch.Tensor]:
         """(1|B, C, 1, 1) broadcast operand -> fp32 [C] (or [B, C]) vector."""
@@ -820,6 +829,8 @@ class Lowering:
     def materialize_stack(self, lt: LazyTensor, st: Stack) -> torch.Tensor:
         src = self.plain_of_full(st.src)
         g = st.gather
+        if getattr(g, "tile_images", None) is not None:
+            raise TraceUnsupported("foreign ops on the tile stack of a batch of independent edits")
         src.readers.append(None)
         x = src.raw
         idx = g.active_indices.to(self.dev)
@@ -842,7 +853,9 @@ class Lowering:
 
     def force_stack(self, lt: LazyTensor, co: ConvOut) -> torch.Tensor:
         """Emit a conv on tiles whose result stays a stack (a foreign op consumes it)."""
-        segs, pre, hw, idx, block, off, stack_src = self.tile_conv_args(co)
+        segs, pre, hw, idx, block, off, stack_src, timg = self.tile_conv_args(co)
+        if timg is not None:
+            raise TraceUnsupported("foreign ops on the tile stack of a batch of independent edits")
         n = int(idx.shape[0]) if idx is not None else int(stack_src.shape[0])
         B = 1 if stack_src is not None else segs[0][0].shape[0]
         ro = (block - co.k) // co.stride + 1
@@ -1017,11 +1030,11 @@ class Lowering:
         return True
 
     def _tile_emit(self, node: Node, co: ConvOut, dst: Buf, residual: Optional[Buf] = None, shortcut=None, name: str = "", gather=None) -> None:
-        segs, pre, hw, idx, block, off, stack_src = self.tile_conv_args(co)
+        segs, pre, hw, idx, block, off, stack_src, timg = self.tile_conv_args(co)
         if stack_src is not None and gather is not None:      # a materialised stack scattered through `gather`'s tile set
             idx, off = gather.active_indices.to(self.dev), int(gather.offset[0])
         self.emit_conv(name or ("n%d" % node.index), segs, pre, hw, idx, block, co.weight, co.bias, co.stride, off, dst, residual=residual,
-                       shortcut=shortcut, stack_src=stack_src)
+                       shortcut=shortcut, stack_src=stack_src, tile_img=timg)
 
     def _module_name(self, node: Node) -> str:
         return self.module_names.get(id(node.module), "n%d" % node.index)
@@ -1051,7 +1064,7 @@ class Lowering:
             if res_buf is None:
                 return False
         cache = m.original_outputs[m.cache_id]
-        dst = self.cached(cache)
+        dst = self.cached(cache, g.num_edits)
         if res_buf is not None and tuple(res_buf.shape) != tuple(dst.shape):
             return False
         self._tile_emit(node, co, dst, residual=res_buf, name=self._module_name(node), gather=g)
@@ -1069,14 +1082,14 @@ class Lowering:
         g = m.gather.module
         if not self._same_gather(co.src.gather, g):
             return False
-        dst = self.cached(m.original_outputs[m.cache_id])
+        dst = self.cached(m.original_outputs[m.cache_id], g.num_edits)
         self._tile_emit(node, co, dst, name=self._module_name(node))
 
         class _G:        # the second gather re-uses the paired gather's geometry with this module's activation
             pass
 
         g2 = _G()
-        g2.active_indices, g2.block_size, g2.offset = g.active_indices, g.block_size, g.offset
+        g2.active_indices, g2.block_size, g2.offset, g2.tile_images = g.active_indices, g.block_size, g.offset, g.tile_images
         g2.activation_name, g2.activation_first = m.activation_name, m.activation_first
         self.env[id(node.outs[0])] = Stack(Full([(dst, 0)]), g2, scale, shift)
         return True
@@ -1095,8 +1108,8 @@ class Lowering:
         if sc.src.gather is not sg or sc.k != 1 or sc.src.scale is not None or sc.src.shift is not None or sg.activation_name != "identity":
             return False
         cid = m.cache_id
-        dst = self.cached(m.original_outputs[cid])
-        skip = self.cached(m.original_residuals[cid])
+        dst = self.cached(m.original_outputs[cid], mg.num_edits)
+        skip = self.cached(m.original_residuals[cid], mg.num_edits)
         idx, off = mg.active_indices.to(self.dev), int(mg.offset[0])
         sidx, soff = sg.active_indices.to(self.dev), int(sg.offset[0])
         sc_full: Full = sc.src.src
@@ -1106,6 +1119,9 @@ class Lowering:
         width = 1 << 16
         main_key = (idx[:, 0].long() + off) * width + (idx[:, 1].long() + off)
         sc_key = (sidx[:, 0].long() + soff) * width + (sidx[:, 1].long() + soff)
+        if mg.tile_images is not None:         # batch of edits: a tile is (image, origin)
+            main_key = main_key + mg.tile_images.to(self.dev).long() * (width * width)
+            sc_key = sc_key + sg.tile_images.to(self.dev).long() * (width * width)
         subset = bool(torch.isin(sc_key, main_key).all()) and tuple(mg.block_stride) == tuple(sg.block_stride) == (4, 4) \
             and int(sg.block_size[0]) == 4 and int(mg.block_size[0]) == 6
         fuse = (self.fuse_shortcut and self.tc5 and self.producer_preop and subset and co.k == 3 and co.stride == 1
@@ -1397,9 +1413,12 @@ class Lowering:
         # the stem only has to exist where it is read: if every reader gathers it through one index set, restrict it
         for rec in self.conv_ins:
             rd = rec.out.readers
+            def same_img(a, b):
+                return (a is None and b is None) or (a is not None and b is not None and torch.equal(a, b))
+
             if (self.sparse_stem and rd and all(r is not None for r in rd)
-                    and all(up_ == 0 and blk_ <= 6 and i_ is not None and torch.equal(i_, rd[0][0]) for (i_, blk_, up_) in rd)):
-                rec.tiles, rec.tile_size = rd[0][0].contiguous(), max(blk_ for (_, blk_, _) in rd)
+                    and all(up_ == 0 and blk_ <= 6 and i_ is not None and torch.equal(i_, rd[0][0]) and same_img(ti_, rd[0][3]) for (i_, blk_, up_, ti_) in rd)):
+                rec.tiles, rec.tile_size, rec.tile_img = rd[0][0].contiguous(), max(r[1] for r in rd), rd[0][3]
                 for t_ in ([rec.out._raw] if rec.out.has_raw else []) + [v[0] for v in rec.out.views.values()]:
                     t_.zero_()          # never read outside the tiles; defined contents all the same
         for fc in self.fused:

@@ -60,6 +60,9 @@ def reduce_mask(
     block, step, pad = _pair(block_size), _pair(stride), _pair(padding)
     if mask.dim() != 2:
         raise ValueError("reduce_mask expects a 2-D mask, got %d-D" % mask.dim())
+    # binarise exactly like the reference (max-pool of the float mask, then > 0.5, sige/utils.py:27-29): a soft mask counts
+    # where it exceeds 0.5; integer / bool masks where they are non-zero
+    mask = (mask > 0.5) if mask.is_floating_point() else (mask != 0)
     if mask.is_cuda:
         from . import ops
 
@@ -71,6 +74,24 @@ def reduce_mask(
         n = idx.shape[0]
         print("Block Sparsity: %d/%d=%.2f%%" % (n, total, 100 * n / total))
     return idx
+
+
+def reduce_mask_batched(masks: torch.Tensor, block_size: IntPair, stride: IntPair, padding: IntPair):
+    """[E, H, W] masks of E INDEPENDENT EDITS of one original image -> (int32 [N, 2] tile origins, int32 [N] image index):
+    the per-edit lists of ``reduce_mask`` concatenated in edit order (an extension over the reference, whose ops share one
+    tile list across the batch; consumed by the fused step, include/sige_b200.h `tile_img`)."""
+    if masks.dim() != 3:
+        raise ValueError("reduce_mask_batched expects [E, H, W] masks")
+    parts = [reduce_mask(masks[e], block_size, stride, padding) for e in range(masks.shape[0])]
+    idx = torch.cat(parts, 0).contiguous()
+    img = torch.cat([torch.full((p.shape[0],), e, dtype=torch.int32, device=idx.device) for e, p in enumerate(parts)], 0).contiguous()
+    return idx, img
+
+
+def stack_mask_pyramids(pyramids) -> Dict[Tuple[int, int], torch.Tensor]:
+    """[{res: [H, W]} per edit] -> {res: [E, H, W]}: the ``set_masks`` argument for a batch of independent edits."""
+    keys = list(pyramids[0].keys())
+    return {k: torch.stack([p[k] for p in pyramids], 0) for k in keys}
 
 
 def _axis_or(m, radius: int, axis: int):

@@ -27,7 +27,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .. import lazy, ops
-from ..masks import reduce_mask
+from ..masks import reduce_mask, reduce_mask_batched
 from .state import SIGEModule, SIGEModuleWrapper, bump_cache_generation
 
 
@@ -141,6 +141,9 @@ class Gather(SIGEModule):
         self.load_runtime("gather")
         self.input_res: Optional[Tuple[int, int]] = None
         self.active_indices: Optional[torch.Tensor] = None
+        # a batch of INDEPENDENT EDITS (3-D masks [E, H, W] given to set_masks): active_indices is the concatenation of the
+        # per-edit tile lists and tile_images[i] names the edit of tile i; None = the reference's shared tile list
+        self.tile_images: Optional[torch.Tensor] = None
 
     def forward(self, x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None) -> torch.Tensor:
         self.check_dtype(x, scale, shift)
@@ -153,7 +156,9 @@ class Gather(SIGEModule):
         if self.mode == "sparse":
             if lazy.is_lazy(x, scale, shift):
                 n = self.active_indices.size(0)
-                return lazy.record_module_call("sige.gather", self, (x, scale, shift), (x.shape[0] * n, x.shape[1], *self.block_size), x)
+                rows = n if self.tile_images is not None else x.shape[0] * n
+                return lazy.record_module_call("sige.gather", self, (x, scale, shift), (rows, x.shape[1], *self.block_size), x)
+            self._no_batched_edits()
             idx = self.active_indices = _on(self.active_indices, x)
             return ops.gather(x, self.block_size[0], self.block_size[1], idx, scale, shift, self.activation_name,
                               self.activation_first)
@@ -176,8 +181,20 @@ class Gather(SIGEModule):
         self.mask = masks[res]
         key = ("active_indices", *res, *self.block_size, *self.block_stride, *self.offset)
         if key not in cache:
-            cache[key] = reduce_mask(self.mask, self.block_size, self.block_stride, self.offset, verbose=self.verbose)
-        self.active_indices = cache[key]
+            if self.mask.dim() == 3:      # [E, H, W]: one mask per edit
+                cache[key] = reduce_mask_batched(self.mask, self.block_size, self.block_stride, self.offset)
+            else:
+                cache[key] = (reduce_mask(self.mask, self.block_size, self.block_stride, self.offset, verbose=self.verbose), None)
+        self.active_indices, self.tile_images = cache[key]
+
+    @property
+    def num_edits(self) -> Optional[int]:
+        return None if self.tile_images is None else int(self.mask.shape[0])
+
+    def _no_batched_edits(self):
+        if self.tile_images is not None:
+            raise NotImplementedError("a batch of independent edits (3-D masks) runs as a fused step only: CUDA fp16/bf16 "
+                                      "(or set_fused(True, dtype=...)); the eager operator modules share one tile list across the batch")
 
 
 class Scatter(SIGEModule):
@@ -209,7 +226,9 @@ class Scatter(SIGEModule):
             if lazy.is_lazy(x, residual):
                 if self.sparse_update:
                     raise lazy.TraceUnsupported("sparse_update=True runs through the eager operator modules")
-                return lazy.record_module_call("sige.scatter", self, (x, residual), tuple(cached.shape), x if lazy.is_lazy(x) else residual)
+                shape = tuple(cached.shape) if g.num_edits is None else (g.num_edits, *cached.shape[1:])
+                return lazy.record_module_call("sige.scatter", self, (x, residual), shape, x if lazy.is_lazy(x) else residual)
+            g._no_batched_edits()
             out = ops.scatter(x, cached, g.offset[0], g.offset[1], g.model_stride[0], g.model_stride[1],
                               _on(g.active_indices, x), residual)
             if self.sparse_update:
@@ -257,8 +276,9 @@ class ScatterWithBlockResidual(SIGEModule):
             if lazy.is_lazy(x, residual):
                 if self.sparse_update:
                     raise lazy.TraceUnsupported("sparse_update=True runs through the eager operator modules")
-                return lazy.record_module_call("sige.scatter_block_residual", self, (x, residual), tuple(y0.shape),
-                                               x if lazy.is_lazy(x) else residual)
+                shape = tuple(y0.shape) if mg.num_edits is None else (mg.num_edits, *y0.shape[1:])
+                return lazy.record_module_call("sige.scatter_block_residual", self, (x, residual), shape, x if lazy.is_lazy(x) else residual)
+            mg._no_batched_edits()
             idx0, idx1 = _on(mg.active_indices, x), _on(sg.active_indices, x)
             out = ops.scatter_with_block_residual(x, y0, residual, y1, mg.offset[0], mg.offset[1], mg.model_stride[0],
                                                   mg.model_stride[1], idx0, idx1)
@@ -308,8 +328,9 @@ class ScatterGather(SIGEModule):
                 if self.sparse_update:
                     raise lazy.TraceUnsupported("sparse_update=True runs through the eager operator modules")
                 n = g.active_indices.size(0)
-                return lazy.record_module_call("sige.scatter_gather", self, (x, scale, shift),
-                                               (cached.size(0) * n, x.shape[1], *g.block_size), x)
+                rows = n if g.tile_images is not None else cached.size(0) * n
+                return lazy.record_module_call("sige.scatter_gather", self, (x, scale, shift), (rows, x.shape[1], *g.block_size), x)
+            g._no_batched_edits()
             idx = _on(g.active_indices, x)
             self.scatter_map = _on(self.scatter_map, x)
             out = ops.scatter_gather(x, cached, g.block_size[0], g.block_size[1], idx, self.scatter_map, scale, shift,
@@ -333,6 +354,9 @@ class ScatterGather(SIGEModule):
         super().set_mask(masks, cache, timestamp)
         g = self.gather.module
         g.set_mask(masks, cache, timestamp)  # the paired gather owns the index list
+        if g.tile_images is not None:         # batch of independent edits: fused step only, which needs no scatter map
+            self.scatter_map = None
+            return
         h, w = g.mask.shape
         key = ("scatter_map", h, w, *g.block_size, *g.kernel_size, *g.offset, *g.model_stride)
         if key not in cache:

@@ -61,10 +61,17 @@ class SimExecutor:
                 padded = F.pad(full, (P, P, P, P))                  # zero AFTER the pre-op
                 idx = s.idx.tolist()
                 tiles, coords = [], []
-                for bi in range(B):
-                    for (iy, ix) in idx:
+                if s.tile_img is not None:          # batch of independent edits: tile i belongs to image tile_img[i]
+                    assert len(idx) == s.N == s.tile_img.numel()
+                    for bi, (iy, ix) in zip(s.tile_img.tolist(), idx):
+                        assert 0 <= bi < B
                         tiles.append(padded[bi, :, iy + P:iy + P + R, ix + P:ix + P + R])
                         coords.append((bi, iy, ix))
+                else:
+                    for bi in range(B):
+                        for (iy, ix) in idx:
+                            tiles.append(padded[bi, :, iy + P:iy + P + R, ix + P:ix + P + R])
+                            coords.append((bi, iy, ix))
                 X = torch.stack(tiles)
                 M = X.shape[0]
             out = F.conv2d(X, w, b, stride=st)
@@ -119,21 +126,23 @@ class SimExecutor:
             self.launches += 1
             y = F.conv2d(rec.x.float(), rec.weight.float(), None if rec.bias is None else rec.bias.float(), padding=1)
             B, C, H, W = y.shape
+            sel = torch.zeros((B, H, W), dtype=torch.bool)
             if rec.tiles is None:
-                sel = torch.ones((H, W), dtype=torch.bool)
+                sel[:] = True
             else:
-                sel = torch.zeros((H, W), dtype=torch.bool)
-                for (iy, ix) in rec.tiles.tolist():
-                    sel[max(iy, 0):max(iy + rec.tile_size, 0), max(ix, 0):max(ix + rec.tile_size, 0)] = True
+                imgs = [None] * rec.tiles.shape[0] if rec.tile_img is None else rec.tile_img.tolist()
+                for bi, (iy, ix) in zip(imgs, rec.tiles.tolist()):
+                    sel[slice(None) if bi is None else bi, max(iy, 0):max(iy + rec.tile_size, 0), max(ix, 0):max(ix + rec.tile_size, 0)] = True
+            sel4 = sel[:, None].expand_as(y)
             if rec.out.has_raw:
-                rec.out.raw[:, :, sel] = y[:, :, sel]
+                rec.out.raw[sel4] = y[sel4].to(rec.out.raw.dtype)
             for (view, sc, sh, act) in rec.aux:
                 z = y
                 if sc is not None:
                     z = z * sc.view(1, -1, 1, 1)
                 if sh is not None:
                     z = z + sh.view(1, -1, 1, 1)
-                view[:, :, sel] = _act(z, act)[:, :, sel]
+                view[sel4] = _act(z, act)[sel4].to(view.dtype)
 
         return run
 

@@ -169,3 +169,40 @@ def test_value_dependent_forward_is_rejected():
     net.set_mode("sparse")
     with pytest.raises(TraceUnsupported):
         FusedStep(net, torch.ones(1, 8, 4, 4), executor=SimExecutor())
+
+
+def test_batch_of_independent_edits_equals_one_edit_at_a_time():
+    """E edits of ONE original image, each with its own mask, in one fused step (per-tile image index; weights read once):
+    row e of the batched output == the single-edit fused output of edit e (BASELINE.json configs[4])."""
+    from sige.utils import downsample_mask
+    from sige_b200.fused import FusedStep
+    from sige_b200.masks import stack_mask_pyramids
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
+    from sim_executor import SimExecutor
+
+    cfg = DDPMConfig.small()
+    model, _, t = _prepared("reference", cfg, 0.05)
+    edits = []
+    for e, (ratio, shift) in enumerate([(0.05, (0, 0)), (0.02, (-14, 9)), (0.09, (11, -13))]):
+        x0, x1, mask, _ = synthetic_inputs(cfg, ratio, seed=0, edit_seed=e)
+        mask = torch.roll(mask, shift, (0, 1))                      # edits at different places
+        x1 = x0 + torch.roll(x1 - x0, shift, (2, 3))
+        edits.append((x1, mask))
+    singles = []
+    with torch.no_grad():
+        for x1, mask in edits:
+            model.set_masks(downsample_mask(mask, min_res=8))
+            singles.append(FusedStep(model, x1, t, executor=SimExecutor()).output.clone())
+        model.set_masks(stack_mask_pyramids([downsample_mask(m, min_res=8) for _, m in edits]))
+        xb = torch.cat([x for x, _ in edits], 0)
+        step = FusedStep(model, xb, t, executor=SimExecutor())
+    assert step.eager_nodes == [] and step.output.shape[0] == 3
+    sparse = [f for f in step.fused if f.spec.tile_img is not None]
+    assert len(sparse) > 10 and sparse[0].spec.N == sum(int((f.spec.tile_img == e).sum()) for f in sparse[:1] for e in range(3))
+    for e in range(3):
+        assert torch.allclose(step.output[e], singles[e][0], atol=2e-5), "edit %d differs from its single-edit step" % e
+    # the eager operator modules share one tile list across the batch: they must refuse, not mis-compute
+    model.set_fused(False)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        with torch.no_grad():
+            model(xb, t)
