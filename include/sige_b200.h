@@ -211,12 +211,12 @@ typedef struct {
     const void *w2_packed;  /* sige_pack_conv_weight of the 1x1 weights */
     const float *bias2;     /* fp32 [Cout] or NULL */
     const uint8_t *sc_flags;/* [N] per main tile, or NULL */
-    /* ---- optional per-tile image index: a batch of INDEPENDENT EDITS in one launch ----
-     * NULL (the reference's layout, sige/cuda/gather_kernel.cu:30): every image of the batch uses the same N tile origins,
-     * tile row b*N + i.  Non-NULL: `idx` is the concatenation of the per-image tile lists (N entries in total, each edit
-     * with its own mask) and tile_img[i] in [0, B) names the image tile i reads from and writes to; weights are read once
-     * for the whole batch.  Full-tensor source and destination only (no stacks). */
-    const int32_t *tile_img;
+    /* ---- per-image tile lists: a batch of INDEPENDENT EDITS in one launch ----
+     * 0 (the reference's layout, sige/cuda/gather_kernel.cu:30): every image of the batch uses the same N tile origins.
+     * 1: `idx` (and `sc_flags`) hold B*N entries, row b*N + i = tile i of image b — each edit has its own mask; lists shorter
+     * than N are padded with SIGE_TILE_NONE origins (such a tile reads zeros and writes nothing).  Weights are read once for
+     * the whole batch.  Full-tensor source and destination only (no stacks). */
+    int idx_per_image;
 } sige_tile_conv_t;
 
 /* Launch with programmatic dependent launch: the kernel prefetches its weights while the previous kernel
@@ -225,6 +225,8 @@ typedef struct {
 /* Use the tcgen05 / TMEM / TMA kernel when the geometry allows (3x3 s1 on 6x6 tiles, 1x1 on 4x4 tiles,
  * Cout % 64 == 0); otherwise the mma.sync kernel runs. */
 #define SIGE_CONV_TC5 2
+/* Origin of a padding entry of a per-image tile list (both coordinates). */
+#define SIGE_TILE_NONE (-30000)
 
 /* Fused gather -> (affine+SiLU) -> conv (+bias) -> (+residual) -> scatter, one launch. */
 int sige_tile_conv(const sige_tile_conv_t *p, sige_stream_t stream);
@@ -258,12 +260,12 @@ int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out,
                       int H, int W, int Cin, int Cout, int n_aux, const sige_conv_aux_t *aux,
                       sige_stream_t stream);
 /* The same stem evaluated only inside a list of R x S pixel tiles (tile t = rows idx[2t] .. +R-1, columns idx[2t+1] ..
- * +S-1; pixels outside the image are skipped).  tile_img == NULL: the same n_tiles tiles in every image of the batch;
- * else tile t belongs to image tile_img[t] only (see sige_tile_conv_t.tile_img).  When every consumer
+ * +S-1; pixels outside the image are skipped).  idx_per_image == 0: the same n_tiles tiles in every image of the batch;
+ * 1: idx holds B*n_tiles entries, row b*n_tiles + i = tile i of image b (see sige_tile_conv_t.idx_per_image).  When every consumer
  * of the stem reads it through Gather with one index set (reference sige/nn/gather.py:76-89), nothing else is read. */
 int sige_conv_in_nhwc_tiles(const void *x, const void *w, const void *bias, void *out, int dtype, int B,
                             int H, int W, int Cin, int Cout, const int32_t *idx, int n_tiles, int R, int S,
-                            const int32_t *tile_img, int n_aux, const sige_conv_aux_t *aux, sige_stream_t stream);
+                            int idx_per_image, int n_aux, const sige_conv_aux_t *aux, sige_stream_t stream);
 /* GroupNorm statistics folded to per-channel fp32 (scale, shift) [B, C]: GroupNorm(x) == x*scale + shift.
  * Deterministic two-stage reduction; `workspace` holds sige_group_norm_fold_workspace(B, C) floats. */
 int sige_group_norm_fold_workspace(int B, int C);

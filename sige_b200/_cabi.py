@@ -22,6 +22,7 @@ NCHW, NHWC = 0, 1
 ACT_IDENTITY, ACT_SWISH = 0, 1
 CONV_PDL = 1
 CONV_TC5 = 2
+TILE_NONE = -30000
 
 
 class SigeLibraryMissing(ImportError):
@@ -73,7 +74,7 @@ class TileConv(Structure):
         ("ksplit", c_int), ("flags", c_int),
         ("n_aux", c_int), ("aux", ConvAux * 2),
         ("n_src2", c_int), ("src2", ConvSrc * 2), ("Cin2", c_int), ("w2_packed", c_void_p), ("bias2", c_void_p), ("sc_flags", c_void_p),
-        ("tile_img", c_void_p),
+        ("idx_per_image", c_int),
     ]
 
 
@@ -99,7 +100,7 @@ PROTOTYPES = {
     "sige_tile_conv_generic": (_I, [_P, _P, _P, _P] + [_I] * 14 + [_P]),
     "sige_tile_conv_plan": (_I, [_P, _P]),
     "sige_conv_in_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "sige_conv_in_nhwc_tiles": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _P, _P]),
+    "sige_conv_in_nhwc_tiles": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "sige_group_norm_fold_workspace": (_I, [_I, _I]),
     "sige_group_norm_fold": (_I, [_P, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P, _P, _I, _P]),
     "sige_conv_out_nhwc": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -159,7 +159,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv_in_tiles_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *__restrict__ bias,
                                                             T *__restrict__ out, int H, int W, int Cin, int Cout,
                                                             const int32_t *__restrict__ idx, int n_tiles, int NT, int R, int S,
-                                                            const int32_t *__restrict__ tile_img, int n_aux, InAux a0, InAux a1) {
+                                                            int idx_per_image, int n_aux, InAux a0, InAux a1) {
     extern __shared__ float wsm[];   // same layout as conv_in_kernel
     const int K = 9 * Cin, OV = Cout / 8;
     const int pitch = conv_in_pitch(Cin);
@@ -188,8 +188,7 @@ __global__ void __launch_bounds__(256) conv_in_tiles_kernel(const T *__restrict_
         const int xx = q % S; q /= S;
         const int yy = q % R;
         const int t = q / R;
-        int b = t / n_tiles, tt = t - b * n_tiles;
-        if (tile_img) { b = __ldg(tile_img + t); tt = t; }     // a batch of independent edits: every tile names its image
+        const int b = t / n_tiles, tt = idx_per_image ? t : t - b * n_tiles;      // per-image lists: row b*n_tiles + i
         const int hh = __ldg(idx + 2 * tt) + yy, ww = __ldg(idx + 2 * tt + 1) + xx;
         if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
         float acc[8];
@@ -524,7 +523,7 @@ int sige_conv_in_nhwc(const void *x, const void *w, const void *bias, void *out,
 }
 
 int sige_conv_in_nhwc_tiles(const void *x, const void *w, const void *bias, void *out, int dtype, int B, int H, int W, int Cin, int Cout,
-                            const int32_t *idx, int n_tiles, int R, int S, const int32_t *tile_img, int n_aux, const sige_conv_aux_t *aux,
+                            const int32_t *idx, int n_tiles, int R, int S, int idx_per_image, int n_aux, const sige_conv_aux_t *aux,
                             sige_stream_t stream) {
     SIGE_REQUIRE(x && w && out && idx, "sige_conv_in_nhwc_tiles: null pointer");
     SIGE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 4 && Cout > 0 && Cout % 8 == 0, "sige_conv_in_nhwc_tiles: needs Cin <= 4 and Cout %% 8 == 0");
@@ -533,7 +532,7 @@ int sige_conv_in_nhwc_tiles(const void *x, const void *w, const void *bias, void
     if (n_tiles == 0) return 0;
     const size_t smem = sizeof(float) * ((size_t)(Cout / 8) * conv_in_pitch(Cin) + Cout);
     SIGE_REQUIRE(smem <= 48 * 1024, "sige_conv_in_nhwc_tiles: weights do not fit in shared memory");
-    const int NT = tile_img ? n_tiles : B * n_tiles;
+    const int NT = B * n_tiles;
     const long long total = (long long)NT * R * S * (Cout / 8);
     SIGE_REQUIRE(total < 2147483647LL && (long long)B * H * W * Cout < 2147483647LL * 8, "sige_conv_in_nhwc_tiles: tensor too large");
     const long long want_blocks = (total + 255) / 256;
@@ -546,8 +545,8 @@ int sige_conv_in_nhwc_tiles(const void *x, const void *w, const void *bias, void
         ia[i] = InAux{aux[i].ptr, aux[i].scale, aux[i].shift, aux[i].act};
     }
     switch (dtype) {
-        case SIGE_F16: launch_pdl(conv_in_tiles_kernel<__half>, dim3(grid), dim3(256), smem, st, (const __half *)x, (const __half *)w, (const __half *)bias, (__half *)out, H, W, Cin, Cout, idx, n_tiles, NT, R, S, tile_img, n_aux, ia[0], ia[1]); break;
-        case SIGE_BF16: launch_pdl(conv_in_tiles_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)w, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)out, H, W, Cin, Cout, idx, n_tiles, NT, R, S, tile_img, n_aux, ia[0], ia[1]); break;
+        case SIGE_F16: launch_pdl(conv_in_tiles_kernel<__half>, dim3(grid), dim3(256), smem, st, (const __half *)x, (const __half *)w, (const __half *)bias, (__half *)out, H, W, Cin, Cout, idx, n_tiles, NT, R, S, idx_per_image, n_aux, ia[0], ia[1]); break;
+        case SIGE_BF16: launch_pdl(conv_in_tiles_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)w, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)out, H, W, Cin, Cout, idx, n_tiles, NT, R, S, idx_per_image, n_aux, ia[0], ia[1]); break;
         default: set_error("sige_conv_in_nhwc_tiles: dtype must be f16/bf16"); return 1;
     }
     return check_launch("sige_conv_in_nhwc_tiles");

@@ -52,8 +52,8 @@ struct ConvParams {
     int H, W;               // logical source extent
     int src_is_stack;
     const int32_t *idx;
-    int N, NT;              // tiles per batch element, total tiles (B*N; == N with a per-tile image index)
-    const int32_t *tile_img; // per-tile image index (batch of independent edits) or nullptr: image = tile / N
+    int N, NT;              // tiles per batch element, total tiles (B*N)
+    int idx_per_image;      // 1: idx holds B*N entries (row b*N + i = tile i of image b), else N shared by all images
     int R, S, RS;
     const float *scale, *shift;
     int affine_bstride;
@@ -164,7 +164,7 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
             ld_smem[k] = pix * 128 + ((u ^ halo_key(y, x)) << 4);
             const int t = tile0 + tl;
             if (t < p.NT) {
-                const int n = t % p.N, b = p.tile_img ? __ldg(p.tile_img + t) : t / p.N;
+                const int n = p.idx_per_image ? t : t % p.N, b = t / p.N;
                 int hh = y, ww = x, img = t;
                 if (!p.src_is_stack) {
                     hh += __ldg(p.idx + 2 * n); ww += __ldg(p.idx + 2 * n + 1); img = b;
@@ -361,10 +361,10 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
         const int t = tile0 + tl;
         int hh = oy, ww = ox, img = t;
         if (!p.dst_is_stack) {
-            const int nn = t % p.N;
+            const int nn = p.idx_per_image ? t : t % p.N;
             hh += (p.offH + __ldg(p.idx + 2 * nn)) / p.stride;
             ww += (p.offW + __ldg(p.idx + 2 * nn + 1)) / p.stride;
-            img = p.tile_img ? __ldg(p.tile_img + t) : t / p.N;
+            img = t / p.N;
         }
         if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) continue;
         float v[8];
@@ -554,8 +554,7 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
         SIGE_REQUIRE(x.act == SIGE_ACT_IDENTITY || x.act == SIGE_ACT_SWISH, "sige_tile_conv: aux %d unknown activation", i);
     }
 
-    SIGE_REQUIRE(a->tile_img == nullptr || (!a->src_is_stack && !a->dst_is_stack && a->B <= 255),
-                 "sige_tile_conv: a per-tile image index needs full-tensor source and destination and B <= 255");
+    SIGE_REQUIRE(!a->idx_per_image || (!a->src_is_stack && !a->dst_is_stack), "sige_tile_conv: per-image tile lists need full-tensor source and destination");
     SIGE_REQUIRE(a->n_src2 >= 0 && a->n_src2 <= 2, "sige_tile_conv: n_src2 must be 0, 1 or 2");
     if (a->n_src2 > 0) {
         int c2 = 0;
@@ -580,8 +579,8 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     p.W = a->src_is_stack ? a->S : a->W;
     p.idx = a->idx;
     p.N = a->N;
-    p.NT = a->tile_img ? a->N : a->B * a->N;
-    p.tile_img = a->tile_img;
+    p.NT = a->B * a->N;
+    p.idx_per_image = a->idx_per_image ? 1 : 0;
     p.R = a->R; p.S = a->S; p.RS = a->R * a->S;
     p.scale = a->scale; p.shift = a->shift; p.affine_bstride = a->affine_bstride; p.act = a->act;
     p.w = a->w_packed; p.bias = a->bias;

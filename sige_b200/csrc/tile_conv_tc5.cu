@@ -42,7 +42,6 @@ constexpr int NPROD = 32 * NPROD_WARPS;
 constexpr int A_COPY_BYTES = 6 * TILES * 4 * 128;        // one kx-copy: [6][8][4] rows x 128 B = 24576
 constexpr int A_BUF_BYTES = 3 * A_COPY_BYTES;            // 73728 per 64-channel chunk
 constexpr int EPI_PAD = 4;
-static_assert(TILES == 8, "setup warp: 16 lanes of tile origins + 8 shortcut flags + 8 image indices");
 
 struct Seg {
     const void *ptr;
@@ -82,7 +81,7 @@ struct Params {
     int C0_2, Cin2;
     const float *bias2;
     const unsigned char *sc_flags;
-    const int32_t *tile_img;   // per-tile image index (batch of independent edits), or nullptr: image = tile / N
+    int idx_per_image;         // 1: idx / sc_flags hold B*N entries (row b*N + i = tile i of image b), else N shared by all images
     int ksplit;
     int pdl;
     int push_async;            // split-K exchange: 1 = st.async + per-owner mbarrier, 0 = plain remote stores + cluster barrier
@@ -317,7 +316,6 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     const int c_first = chunk_of(j_begin), c_last = chunk_of(j_end - 1);
     int32_t *s_idx = reinterpret_cast<int32_t *>(smem + C::OFF_CONST);          // [TILES][2] tile origins of this CTA
     unsigned char *s_flags = smem + C::OFF_CONST + 64;                          // [TILES] 1 = evaluate the fused shortcut on this tile
-    unsigned char *s_img = smem + C::OFF_CONST + 72;                            // [TILES] image (batch element) of each tile
     float *s_const = reinterpret_cast<float *>(smem + C::OFF_CONST + 80);       // bias | aux0 scale | aux0 shift | aux1 scale | aux1 shift | bias2
 
     if (tid == 0) SIGE_TRACE(0);
@@ -338,16 +336,11 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         if (lane < 2 * TILES) {
             const int t = tile0 + (lane >> 1);
             int v = 0;
-            if (t < p.NT && p.idx) v = __ldg(p.idx + 2 * (t % p.N) + (lane & 1));
+            if (t < p.NT && p.idx) v = __ldg(p.idx + 2 * (p.idx_per_image ? t : t % p.N) + (lane & 1));
             s_idx[lane] = v;
         } else if (lane < 2 * TILES + TILES) {
             const int tl = lane - 2 * TILES, t = tile0 + tl;
-            s_flags[tl] = (p.Cin2 > 0 && t < p.NT && (p.sc_flags == nullptr || __ldg(p.sc_flags + (t % p.N)))) ? 1 : 0;
-        } else {
-            const int tl = lane - 3 * TILES, t = tile0 + tl;
-            int img = 0;
-            if (t < p.NT) img = p.tile_img ? __ldg(p.tile_img + t) : (p.NT != p.N ? t / p.N : 0);
-            s_img[tl] = (unsigned char)img;
+            s_flags[tl] = (p.Cin2 > 0 && t < p.NT && (p.sc_flags == nullptr || __ldg(p.sc_flags + (p.idx_per_image ? t : t % p.N)))) ? 1 : 0;
         }
     } else if (warp >= 3 && warp < 9) {
         // per-channel epilogue constants of this CTA's BN output channels
@@ -378,7 +371,8 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         const int t = tile0 + tl;
         int hh = oy, ww = ox, img = t;
         if (!p.dst_is_stack) {
-            img = s_img[tl];
+            img = 0;
+            if (p.NT != p.N) img = t / p.N;
             hh += p.offH + s_idx[2 * tl];
             ww += p.offW + s_idx[2 * tl + 1];
         }
@@ -502,7 +496,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                         if (!p.src_is_stack) {
                             hh += s_idx[2 * tl];
                             ww += s_idx[2 * tl + 1];
-                            img = s_img[tl];                             // batch > 1: SD (shared tile list) or a batch of edits
+                            img = (p.NT != p.N) ? t / p.N : 0;          // batch > 1 only (SD); DDPM is batch 1
                         }
                         if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
                             g_off[k] = ((img * Hs + (hh >> seg.up)) * Ws + (ww >> seg.up)) * seg.C + (q & 7) * 8;
@@ -544,7 +538,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 uint4 v = regs[k];
                 const int u = (ptid + k * NPROD) & 7;
                 if (pre && g_off[k] >= 0) {
-                    const int ab_k = s_img[g_xyt[k] >> 8];      // batch index (per-sample affine: SD)
+                    const int ab_k = (p.NT != p.N) ? (tile0 + (g_xyt[k] >> 8)) / p.N : 0;      // batch index (batch > 1: SD only)
                     const int ch = c * KC + u * 8;
                     T *e = reinterpret_cast<T *>(&v);
                     float sc[8], sh[8];
@@ -601,7 +595,8 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 const int y = 1 + (rem >> 2), xx = 1 + (rem & 3);
                 const int t = tile0 + tl;
                 if (q < TILES * 16 * 8 && t < p.NT && s_flags[tl]) {
-                    const int b = s_img[tl];
+                    int b = 0;
+                    if (p.NT != p.N) b = t / p.N;
                     const int hh = y + s_idx[2 * tl], ww = xx + s_idx[2 * tl + 1];
                     if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) {
                         const T *src = reinterpret_cast<const T *>(seg.ptr) + (((long long)b * Hs + (hh >> seg.up)) * Ws + (ww >> seg.up)) * seg.C + cl + u * 8;
@@ -946,8 +941,7 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.W = a->src_is_stack ? a->S : a->W;
     p.idx = a->idx;
     p.N = a->N;
-    p.NT = a->tile_img ? a->N : a->B * a->N;
-    p.tile_img = a->tile_img;
+    p.NT = a->B * a->N;
     p.scale = a->scale; p.shift = a->shift; p.affine_bstride = a->affine_bstride; p.act = a->act;
     p.bias = a->bias;
     p.Cin = a->Cin; p.Cout = a->Cout; p.taps = a->kH * a->kW;
@@ -965,6 +959,7 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.Cin2 = a->n_src2 > 0 ? a->Cin2 : 0;
     p.bias2 = a->n_src2 > 0 ? a->bias2 : nullptr;
     p.sc_flags = a->n_src2 > 0 ? a->sc_flags : nullptr;
+    p.idx_per_image = a->idx_per_image ? 1 : 0;
     p.ksplit = a->ksplit;
     static int trig_env = getenv("SIGE_TC5_LATE_TRIGGER") ? atoi(getenv("SIGE_TC5_LATE_TRIGGER")) : 1;     // A/B knob
     p.pdl = (a->flags & SIGE_CONV_PDL) ? (trig_env ? 2 : 1) : 0;
@@ -994,7 +989,7 @@ extern "C" int sige_tile_conv_plan(const sige_tile_conv_t *a, sige_tile_conv_pla
     SIGE_REQUIRE(a && out, "sige_tile_conv_plan: null pointer");
     out->path = 0; out->bn = 0; out->ksplit = 0; out->deep_ring = 0; out->grid_x = out->grid_y = out->grid_z = 0;
     if (!((a->flags & SIGE_CONV_TC5) && tc5_supported(a))) return 0;      // mma.sync / CUDA-core paths
-    const long long NT = a->tile_img ? (long long)a->N : (long long)a->B * a->N;
+    const long long NT = (long long)a->B * a->N;
     const tc5::Plan pl = tc5::decide(NT, a->Cin, a->Cout, a->kH * a->kW, a->n_src2 > 0 ? a->Cin2 : 0, a->ksplit);
     out->path = 1;
     out->bn = pl.bn;

@@ -230,6 +230,29 @@ class CudaExecutor:
             _PACKED[k] = (weakref.ref(param), param._version, wp)
         return wp
 
+    def per_image_tiles(self, idx: torch.Tensor, tile_img: torch.Tensor, batch: int, flags: Optional[torch.Tensor] = None):
+        """(idx [N, 2] concatenated per-edit lists, tile_img [N]) -> the C-ABI's per-image layout: ([B*Nmax, 2] with row
+        b*Nmax + i = tile i of image b, padded with SIGE_TILE_NONE; Nmax; flags padded with 0)."""
+        from ._cabi import TILE_NONE
+
+        key = (idx.data_ptr(), tile_img.data_ptr(), int(idx.shape[0]), batch)
+        memo = self.__dict__.setdefault("_per_image", {})
+        if key not in memo:
+            img = tile_img.long()
+            counts = torch.bincount(img, minlength=batch)
+            nmax = max(1, int(counts.max()))
+            starts = torch.cumsum(counts, 0) - counts
+            rows = img * nmax + (torch.arange(img.numel(), device=img.device) - starts[img])
+            padded = torch.full((batch * nmax, 2), TILE_NONE, dtype=torch.int32, device=idx.device)
+            padded[rows] = idx
+            memo[key] = (padded.contiguous(), nmax, rows, idx, tile_img)
+        padded, nmax, rows = memo[key][:3]
+        pflags = None
+        if flags is not None:
+            pflags = torch.zeros((batch * nmax,), dtype=torch.uint8, device=idx.device)
+            pflags[rows] = flags
+        return padded, nmax, pflags
+
     def prepare_conv(self, fc: FusedConv) -> None:
         ops = self.ops
         from ._cabi import CONV_PDL, CONV_TC5
@@ -254,8 +277,13 @@ class CudaExecutor:
             d.src[i].ptr, d.src[i].C, d.src[i].up = t.data_ptr(), t.shape[1], up
         d.B, d.H, d.W = s.B, s.H, s.W
         d.src_is_stack = 1 if s.src_is_stack else 0
-        d.idx = None if s.idx is None else s.idx.data_ptr()
-        d.N = s.N
+        idx_t, n_per, sc_flags_t = s.idx, s.N, (None if s.shortcut is None else s.shortcut[3])
+        d.idx_per_image = 0
+        if s.tile_img is not None:           # batch of independent edits -> padded per-image tile lists
+            idx_t, n_per, sc_flags_t = self.per_image_tiles(s.idx, s.tile_img, s.B, sc_flags_t)
+            d.idx_per_image = 1
+        d.idx = None if idx_t is None else idx_t.data_ptr()
+        d.N = n_per
         d.R = d.S = s.block
         d.scale = None if s.scale is None else s.scale.data_ptr()
         d.shift = None if s.shift is None else s.shift.data_ptr()
@@ -298,9 +326,9 @@ class CudaExecutor:
             d.Cin2 = int(sc_w.shape[1])
             d.w2_packed = w2.data_ptr()
             d.bias2 = None if b2 is None else b2.data_ptr()
-            d.sc_flags = None if sc_flags is None else sc_flags.data_ptr()
+            d.sc_flags = None if sc_flags_t is None else sc_flags_t.data_ptr()
             keep += [w2, b2]
-        d.tile_img = None if s.tile_img is None else s.tile_img.data_ptr()
+        keep += [idx_t, sc_flags_t]
         fc.desc, fc.keep = d, keep
         fc.launch_fn = lambda stream, d=d: ops.launch_tile_conv(d, stream)
 
@@ -310,9 +338,13 @@ class CudaExecutor:
         b = None if rec.bias is None else rec.bias.detach().to(self.dtype).contiguous()
         aux = [ops.conv_aux(v, sc, sh, act) for (v, sc, sh, act) in rec.aux]
         out = rec.out.raw
+        tiles, per_image = rec.tiles, False
+        if rec.tiles is not None and rec.tile_img is not None:
+            tiles, _, _ = self.per_image_tiles(rec.tiles, rec.tile_img, rec.x.shape[0])
+            per_image = True
 
         def run(_stream):
-            ops.conv_in_nhwc(rec.x, w, b, out=out, aux=aux, tiles=rec.tiles, tile_size=rec.tile_size, tile_img=rec.tile_img)
+            ops.conv_in_nhwc(rec.x, w, b, out=out, aux=aux, tiles=tiles, tile_size=rec.tile_size, tiles_per_image=per_image)
 
         return run
 

@@ -410,7 +410,7 @@ def conv_aux(view: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[
 
 
 def conv_in_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
-                 aux=None, tiles: Optional[torch.Tensor] = None, tile_size: int = 6, tile_img: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 aux=None, tiles: Optional[torch.Tensor] = None, tile_size: int = 6, tiles_per_image: bool = False) -> torch.Tensor:
     """3x3 pad-1 conv with Cin <= 4 on a channels-last image (reference sige_fused_unet.py:395).  With ``tiles`` (int32
     [N, 2] tile origins) only the pixels inside those tile_size x tile_size tiles of ``out`` are written."""
     _require_cuda(x, weight, bias, tiles)
@@ -428,9 +428,10 @@ def conv_in_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
             arr[i] = aux[i]
         if tiles is not None:
             assert tiles.dtype == torch.int32 and tiles.dim() == 2 and tiles.shape[1] == 2 and tiles.is_contiguous()
+            n_tiles = int(tiles.shape[0]) // B if tiles_per_image else int(tiles.shape[0])
             _cabi.check(_cabi.lib().sige_conv_in_nhwc_tiles(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), _dt(x),
-                                                           B, H, W, Cin, Cout, tiles.data_ptr(), int(tiles.shape[0]), int(tile_size), int(tile_size),
-                                                           None if tile_img is None else tile_img.data_ptr(), n_aux, arr, _stream(x)), "sige_conv_in_nhwc_tiles")
+                                                           B, H, W, Cin, Cout, tiles.data_ptr(), n_tiles, int(tile_size), int(tile_size),
+                                                           int(bool(tiles_per_image)), n_aux, arr, _stream(x)), "sige_conv_in_nhwc_tiles")
         else:
             _cabi.check(_cabi.lib().sige_conv_in_nhwc(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), _dt(x), B, H, W,
                                                      Cin, Cout, n_aux, arr, _stream(x)), "sige_conv_in_nhwc")

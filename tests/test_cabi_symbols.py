@@ -31,7 +31,7 @@ def test_prototype_table_matches_header(cabi_lib):
 
     assert set(_cabi.PROTOTYPES) == _declared()
     lib = _cabi.lib()
-    assert lib.sige_abi_version() == 1
+    assert lib.sige_abi_version() == 2
     assert lib.sige_built_arch() == b"sm_100a"
     assert lib.sige_activation_from_name(b"identity") == 0
     assert lib.sige_activation_from_name(b"swish") == 1

@@ -224,7 +224,7 @@ def test_batch_of_independent_edits_on_gpu():
         out = model(torch.cat([x for x, _ in edits], 0), t)
     step = model.fused_step
     assert step.eager_nodes == [] and out.shape[0] == len(edits)
-    assert sum(1 for f in step.fused if f.spec.tile_img is not None) >= 40
+    assert sum(1 for f in step.fused if f.spec.tile_img is not None) >= 30
     for e in range(len(edits)):
         d = float((out[e] - singles[e][0]).abs().max() / singles[e][0].abs().max())
         print("edit %d: batched vs single %.3g" % (e, d))
