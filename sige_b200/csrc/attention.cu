@@ -283,14 +283,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_kernel(const Params p) 
 
 template <typename T, int C, int KS> static int launch(const Params &p, int B, cudaStream_t stream) {
     using L = Lay<C, KS>;
-    static bool configured = false;
-    if (!configured) {
+    static int attr_dev = -1;       // the opt-in is per device (and per kernel instantiation)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
         if (cudaFuncSetAttribute(attention_kernel<T, C, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) {
             set_error("sige_attention_tokens: cannot reserve %d bytes of shared memory", L::TOTAL);
             (void)cudaGetLastError();
             return 2;
         }
-        configured = true;
+        attr_dev = dev;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L::N / QB, KS, B);

@@ -112,6 +112,14 @@ def _idx(active_indices: torch.Tensor) -> torch.Tensor:
     return active_indices if active_indices.is_contiguous() else active_indices.contiguous()
 
 
+def _same_dtype(what: str, ref: torch.Tensor, **tensors) -> None:
+    """The kernels take ONE dtype per call from `ref`; a mismatch (e.g. an fp16 stack under autocast against an fp32 cache)
+    would reinterpret memory."""
+    for name, t in tensors.items():
+        if t is not None and t.dtype != ref.dtype:
+            raise TypeError("%s: %s is %s but the cached tensor is %s" % (what, name, t.dtype, ref.dtype))
+
+
 def _bump(n: int = 1) -> None:
     global launch_count
     launch_count += n
@@ -181,6 +189,9 @@ def scatter(x, y, offset_h: int, offset_w: int, stride_h: int, stride_w: int, ac
     if Cx != C:
         raise ValueError("scatter: channel mismatch %d vs %d" % (Cx, C))
     N = idx.shape[0]
+    _same_dtype("scatter", y, x=x)
+    if x.shape[0] != B * N:
+        raise ValueError("scatter: the stack has %d rows, expected B*N = %d*%d" % (x.shape[0], B, N))
     if inplace:
         out, y_ptr = y, None
     else:
@@ -214,6 +225,9 @@ def scatter_with_block_residual(x0, y0, x1, y1, offset_h: int, offset_w: int, st
     if out is None:
         out = _empty_like_layout(y0.shape, y0, layout)
     N0, N1 = idx0.shape[0], idx1.shape[0]
+    _same_dtype("scatter_with_block_residual", y0, x0=x0, x1=x1, y1=y1)
+    if x0.shape[0] != B * N0 or x1.shape[0] != B * N1 or x0.shape[1] != C or x1.shape[1] != C or tuple(y1.shape) != tuple(y0.shape):
+        raise ValueError("scatter_with_block_residual: stack / cache shapes do not match the index lists")
     with torch.cuda.device(y0.device):
         _cabi.check(
             _cabi.lib().sige_scatter_with_block_residual(
@@ -263,6 +277,9 @@ def scatter_gather(x, y, bsize_h: int, bsize_w: int, active_indices, scatter_map
         return out
     if x.shape[1] != C:
         raise ValueError("scatter_gather: channel mismatch %d vs %d" % (x.shape[1], C))
+    _same_dtype("scatter_gather", y, x=x)
+    if tuple(scatter_map.shape) != (H, W, 3) or scatter_map.dtype != torch.int32:
+        raise ValueError("scatter_gather: scatter_map must be int32 [H, W, 3] = [%d, %d, 3]" % (H, W))
     smap = scatter_map if scatter_map.is_contiguous() else scatter_map.contiguous()
     sc, sh = _bcast(scale), _bcast(shift)
     with torch.cuda.device(y.device):

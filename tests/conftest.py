@@ -19,6 +19,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device AND the built library: skip them (loudly) anywhere else, e.g. a plain `pytest tests`
+    in the build container."""
+    try:
+        import torch
+
+        have_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200) — run on the GPU box: pytest -m gpu")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def cabi_lib():
     """Path of libsige_b200.so (built on demand when nvcc is available)."""

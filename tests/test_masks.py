@@ -15,6 +15,23 @@ def test_reduce_mask_kats_host(mask, bs, st, pad, expected):
     assert got.tolist() == expected
 
 
+def test_reduce_mask_soft_mask_binarises_like_the_reference():
+    """The reference max-pools the FLOAT mask and tests > 0.5 (sige/utils.py:27-29): 0.3 is inactive, 0.7 active."""
+    m = torch.tensor([[0.3, 0.0], [0.0, 0.7]])
+    assert reduce_mask(m, 1, 1, 0).tolist() == [[1, 1]]
+    assert reduce_mask(torch.tensor([[0, -3], [0, 0]]), 1, 1, 0).tolist() == [[0, 1]]      # integer masks: non-zero
+
+
+def test_reduce_mask_batched_concatenates_per_edit_lists():
+    from sige_b200.masks import reduce_mask_batched
+
+    rng = np.random.default_rng(5)
+    masks = torch.from_numpy(rng.random((3, 20, 24)) < 0.04)
+    idx, img = reduce_mask_batched(masks, 6, 4, 1)
+    parts = [reduce_mask(masks[e], 6, 4, 1) for e in range(3)]
+    assert idx.tolist() == torch.cat(parts).tolist() and img.tolist() == sum(([e] * p.shape[0] for e, p in enumerate(parts)), [])
+
+
 def test_reduce_mask_none_and_empty():
     m = torch.zeros(8, 8, dtype=torch.bool)
     assert reduce_mask(m, None, 4, 1) is None
