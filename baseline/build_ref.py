@@ -19,7 +19,7 @@ tracked by git):
     stable-diffusion/ldm  the SD model files that use sige.nn (import / shape tests)
     gaugan/models         the GauGAN generators that use sige.nn
     example.py, assets/mask.npy
-    stubs/                two-line stand-ins for `easydict` and `torchprofile` (absent from this image,
+    stubs/                few-line stand-ins for `easydict`, `torchprofile`, `omegaconf.listconfig` (absent from this image,
                           no network) — only so that the model files import
 
 Used by: bench.py --impl reference (the reference's python + sige.cpu + oneDNN on the host cores),
@@ -73,6 +73,9 @@ STUBS = {
         "            raise AttributeError(k)\n"
     ),
     "torchprofile/__init__.py": "def profile_macs(*args, **kwargs):\n    return 0\n",
+    # stable-diffusion/ldm/modules/diffusionmodules/sige_openaimodel.py:266 imports it only to test `type(context_dim) == ListConfig`
+    "omegaconf/__init__.py": "from .listconfig import ListConfig  # noqa: F401\n",
+    "omegaconf/listconfig.py": "class ListConfig(list):\n    pass\n",
 }
 
 
@@ -124,11 +127,9 @@ def _build_ext(name: str, sources, with_cuda: bool, verbose: bool) -> str:
 
 def build(force: bool = False, cuda: bool = True, verbose: bool = False):
     """Returns baseline/_ref (or None when the reference tree is absent and nothing was prebuilt)."""
-    if installed(need_cuda=cuda) and not force:
-        return OUT
     if not ref_available():
         return OUT if installed(need_cuda=False) else None
-    os.makedirs(OUT, exist_ok=True)
+    os.makedirs(OUT, exist_ok=True)     # python trees + stubs are refreshed every time (cheap); the extensions only when missing
     for src, dst, exts in PY_TREES:
         if os.path.isdir(os.path.join(REF_ROOT, src)):
             _copy_tree(src, dst, exts)

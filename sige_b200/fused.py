@@ -527,6 +527,7 @@ class Lowering:
         self._vecs: Dict = {}
         self._pending_prepare: List[Callable[[], None]] = []
         self.env: Dict[int, Any] = {}
+        self._alias_of: Dict[int, LazyTensor] = {}
         self.uses: Dict[int, int] = {}
         self._keepalive: List = []
         for lt, t in zip(tape.inputs, static_inputs):
@@ -706,7 +707,10 @@ class Lowering:
 
     # ------------------------------------------------------------------ forcing / materialising values
     def sym(self, lt) -> Any:
-        return self.env.get(id(lt))
+        v = self.env.get(id(lt))
+        if v is None and id(lt) in self._alias_of:        # identity op on a value that has no symbolic form (yet)
+            return self.sym(self._alias_of[id(lt)])
+        return v
 
     def as_full(self, lt: LazyTensor) -> Optional[Full]:
         """The value as a Full (emitting a pending conv / evaluating an un-lowered producer eagerly and wrapping its
@@ -724,10 +728,17 @@ class Lowering:
         if not isinstance(v, RealT):
             if lt.node is None:
                 return None
-            self.eager(lt.node)            # an island the lowering does not know: its result feeds the fused layers again
+            t = self.runtime_tensor(lt)    # an island the lowering does not know: its result feeds the fused layers again
             v = self.sym(lt)
-        if isinstance(v, RealT) and v.tensor.is_contiguous(memory_format=torch.channels_last):
-            f = Full([(Buf(self, v.tensor.shape, raw=v.tensor), 0)])
+            if not isinstance(v, RealT):
+                v = RealT(t)
+        if isinstance(v, RealT):
+            t = v.tensor
+            if not t.is_contiguous(memory_format=torch.channels_last):      # the fused kernels read NHWC
+                src, t = t, torch.empty(tuple(t.shape), dtype=self.dtype, device=self.dev, memory_format=torch.channels_last)
+                self.steps.append(("eager", lambda _s, src=src, t=t: t.copy_(src)))
+                self.eager_nodes.append("to_nhwc")
+            f = Full([(Buf(self, t.shape, raw=t), 0)])
             self.env[id(lt)] = f
             return f
         return None
@@ -817,6 +828,8 @@ class Lowering:
         if isinstance(v, Stack):
             return self.materialize_stack(lt, v)
         # speculative symbolic kinds (or nothing yet): evaluate the producing node eagerly
+        if v is None and id(lt) in self._alias_of:
+            return self.runtime_tensor(self._alias_of[id(lt)])
         if lt.node is None:
             raise TraceUnsupported("input without a binding")
         self.eager(lt.node)
@@ -854,8 +867,9 @@ class Lowering:
             out.copy_(z)
 
         self.steps.append(("eager", run))
-        self.eager_nodes.append("materialize(%s)" % (lt.node.name if lt.node is not None else "input"))
-        self.env[id(lt)] = Full([(Buf(self, out.shape, raw=out), 0)])
+        self.eager_nodes.append("materialize(%s)" % (lt.node.name if (lt is not None and lt.node is not None) else "value"))
+        if lt is not None:
+            self.env[id(lt)] = Full([(Buf(self, out.shape, raw=out), 0)])
         return out
 
     def materialize_stack(self, lt: LazyTensor, st: Stack) -> torch.Tensor:
@@ -881,7 +895,8 @@ class Lowering:
     def plain_of_full(self, f: Full) -> Buf:
         if f.single is not None:
             return f.single
-        raise TraceUnsupported("gather of a concatenated / upsampled tensor outside a fused conv")
+        t = self.materialize_full(None, f)         # concatenated / upsampled / pre-op'ed value needed as one tensor
+        return Buf(self, t.shape, raw=t)
 
     def force_stack(self, lt: LazyTensor, co: ConvOut) -> torch.Tensor:
         """Emit a conv on tiles whose result stays a stack (a foreign op consumes it)."""
@@ -901,11 +916,14 @@ class Lowering:
         if all(isinstance(self.sym(o), (RealT, RealStack)) for o in node.outs) and node.outs:
             return
         getters: Dict[int, torch.Tensor] = {}
+        lazy_strides: Dict[int, Tuple[int, ...]] = {}
         stack_shapes = set()
 
         def bind(o):
             if isinstance(o, LazyTensor):
                 getters[id(o)] = self.runtime_tensor(o)
+                with torch._C.DisableTorchFunctionSubclass():
+                    lazy_strides[id(o)] = tuple(o.stride())
                 if isinstance(self.sym(o), RealStack):
                     stack_shapes.add(tuple(o.shape))
             return o
@@ -914,14 +932,22 @@ class Lowering:
         lazy._tree_map(bind, node.kwargs)
         outs = []
         for o in node.outs:
-            fmt = torch.channels_last if (o.dim() == 4 and o.shape[1] > 1) else torch.contiguous_format
-            outs.append(torch.empty(tuple(o.shape), dtype=self.dtype if o.dtype.is_floating_point else o.dtype, device=self.dev, memory_format=fmt))
+            with torch._C.DisableTorchFunctionSubclass():
+                st = tuple(o.stride())
+            # the recorded memory layout: later `view`s of this value were validated against exactly these strides
+            outs.append(torch.empty_strided(tuple(o.shape), st, dtype=self.dtype if o.dtype.is_floating_point else o.dtype, device=self.dev))
 
         def sub(o):
             if not isinstance(o, LazyTensor):
                 return o
             g = getters[id(o)]
-            return g if g.dtype == o.dtype else g.to(o.dtype)      # mixed precision: the recorded call saw the model's dtype
+            if g.dtype != o.dtype:
+                g = g.to(o.dtype)                 # mixed precision: the recorded call saw the model's dtype
+            want = lazy_strides[id(o)]
+            if g.dim() >= 2 and tuple(g.stride()) != want and g.numel() > 0:
+                # ... and the model's memory layout (NHWC buffers vs the strides `view` was recorded on)
+                g = torch.empty_strided(tuple(g.shape), want, dtype=g.dtype, device=g.device).copy_(g)
+            return g
 
         op, module, multi = node.op, node.module, node.multi
 
@@ -1045,8 +1071,11 @@ class Lowering:
         x = node.args[0]
         if not isinstance(self.sym(x), (Stack, RealStack)) and x.dim() == 4:      # SIGEConv2d in sparse mode always sees a tile stack
             t = self.runtime_tensor(x)
-            if t.is_contiguous(memory_format=torch.channels_last):
-                self.env[id(x)] = RealStack(t)
+            if not t.is_contiguous(memory_format=torch.channels_last):
+                src, t = t, torch.empty(tuple(t.shape), dtype=self.dtype, device=self.dev, memory_format=torch.channels_last)
+                self.steps.append(("eager", lambda _s, src=src, t=t: t.copy_(src)))
+                self.eager_nodes.append("to_nhwc")
+            self.env[id(x)] = RealStack(t)
         return self._conv_common(node, node.args[0], m.weight, m.bias, m.stride, 0, m.dilation, m.groups)
 
     # ---- operator modules
@@ -1292,6 +1321,40 @@ class Lowering:
         if isinstance(v, GNVal) and v.act is None:
             self.env[id(node.outs[0])] = GNVal(v.src, v.groups, v.weight, v.bias, v.eps, "swish")
             return True
+        return False
+
+    # ---- identities in inference / in the step's single compute dtype
+    def _alias(self, node: Node, x) -> bool:
+        if not isinstance(x, LazyTensor):
+            return False
+        v = self.sym(x)
+        if isinstance(v, (Sig,)):
+            return False
+        out = node.outs[0]
+        if v is None:
+            self._alias_of[id(out)] = x
+        else:
+            self.env[id(out)] = v
+        self.uses[id(out)] = self.uses.get(id(out), 0) + self.uses.get(id(x), 1) - 1
+        return True
+
+    def _h_dropout(self, node: Node):
+        a = self._bind(node, ("input", "p", "training", "inplace"), {"p": 0.5, "training": True, "inplace": False})
+        return (not a["training"] or a["p"] == 0) and not a["inplace"] and self._alias(node, a["input"])
+
+    def _h_float(self, node: Node):        # GroupNorm32 of the SD code: `super().forward(x.float()).type(x.dtype)`
+        return self._alias(node, node.args[0])
+
+    _h_half = _h_float
+    _h_contiguous = _h_float
+
+    def _h_type(self, node: Node):
+        a = self._bind(node, ("input", "dtype"), {"dtype": None})
+        return isinstance(a["dtype"], torch.dtype) and a["dtype"].is_floating_point and self._alias(node, a["input"])
+
+    def _h_to(self, node: Node):
+        if len(node.args) == 2 and isinstance(node.args[1], torch.dtype) and node.args[1].is_floating_point and not node.kwargs:
+            return self._alias(node, node.args[0])
         return False
 
     # ---- structural glue

@@ -128,6 +128,8 @@ class LazyTensor(torch.Tensor):
             if attr in ("T", "mT", "H", "mH", "real"):
                 return _record(func, args, kwargs)
             raise TraceUnsupported("attribute %s of a lazy tensor" % attr)
+        if name == "type" and (len(args) > 1 or kwargs):
+            return _record(func, args, kwargs)          # x.type(dtype) is a cast, x.type() a query
         if name in _META_METHODS:
             if name in ("data_ptr",):
                 raise TraceUnsupported("data_ptr() of a lazy tensor")

@@ -151,3 +151,54 @@ def test_ddpm256_sparse_step_half_channels_last(dtype, tol):
     ref = G["sparse_out"]
     err = float(np.abs(out.float().cpu().numpy() - ref).max() / np.abs(ref).max())
     assert err <= tol, err
+
+
+def test_multi_step_cached_flow_with_sparse_update_matches_reference_kernels():
+    """The cache-per-step protocol of the reference's interactive demo (diffusion_demo/samplers/ddim_ddpm_sampler.py:60-66,
+    sige/nn/scatter.py:40,59-60): a dense pass per step id fills `original_outputs[step]`, later edits run sparse for all
+    steps with NO dense pass, and `sparse_update=True` writes each sparse result back so that the next edit is incremental.
+    Same flow on the GPU kernels and on the reference's CPU kernels (oracle/_ref): outputs and caches agree."""
+    from oracle.cpu_runtime import reference_cpu_runtime
+    from sige.utils import downsample_mask
+    from sige_b200.parallel import cache_tensors
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
+
+    cfg = DDPMConfig.small()
+    steps = [0, 1, 2]
+
+    def flow(model, dev):
+        outs = []
+        x0, xa, mask_a, t = synthetic_inputs(cfg, 0.05, seed=0, edit_seed=1)
+        _, xb, mask_b, _ = synthetic_inputs(cfg, 0.10, seed=0, edit_seed=2)
+        xb = xa + (xb - x0)                                  # second edit on top of the first
+        with torch.no_grad():
+            model.set_mode("full")
+            for s in steps:                                  # dense pass of every step, cached under its id
+                model.set_cache_id(s)
+                model((x0 * (1.0 + 0.1 * s)).to(dev), (t + 10 * s).to(dev))
+            model.set_mode("sparse")
+            model.set_sparse_update(True)
+            for x_edit, mask in ((xa, mask_a), (xb, mask_a | mask_b)):
+                model.set_masks(downsample_mask(mask.to(dev), min_res=8))
+                for s in steps:
+                    model.set_cache_id(s)
+                    outs.append(model((x_edit * (1.0 + 0.1 * s)).to(dev), (t + 10 * s).to(dev)).cpu())
+        return outs, [(n, v.detach().cpu().float()) for n, v in cache_tensors(model)]
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gpu_outs, gpu_caches = flow(_ddpm(cfg, torch.float32, False), DEV)
+    with reference_cpu_runtime():
+        from sige_b200.workloads.ddpm import SIGEDDPMUNet, init_deterministic
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cpu_model = init_deterministic(SIGEDDPMUNet(cfg), seed=0).eval()
+        cpu_outs, cpu_caches = flow(cpu_model, "cpu")
+    assert len(gpu_outs) == 6
+    for i, (a, b) in enumerate(zip(gpu_outs, cpu_outs)):
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err <= 2e-5, "sparse_update flow, output %d: %g" % (i, err)
+    assert len(gpu_caches) == len(cpu_caches) > 3 * 10
+    for (n, a), (_, b) in zip(gpu_caches, cpu_caches):
+        assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max())), "cache %s after the incremental edits" % n
