@@ -497,9 +497,17 @@ def run_ours(args):
         try:
             from sige_b200 import roofline
 
-            roof = roofline.measure_engine(runner, flush) if path == "fused" else roofline.measure_dominant_kernel(model, dtype, flush)
+            if path == "fused":
+                fused_opts = dict(model.__dict__.get("_fused_options", {}))
+                roof = roofline.measure_in_graph(model, (x_dev, td), fused_opts, flush)
+                iso = roofline.measure_engine(runner, flush)          # the same launches one at a time, cold L2, launch latency included
+                roof["isolated_cold"] = {k: iso[k] for k in ("achieved", "frac", "avg_launch_us", "note")}
+            else:
+                roof = roofline.measure_dominant_kernel(model, dtype, flush)
         except Exception as e:  # noqa: BLE001
-            roof = {"error": repr(e)}
+            import traceback
+
+            roof = {"error": repr(e), "trace": traceback.format_exc()[-1500:]}
         log("roofline done")
         if world == 1 and not args.no_cpu_baseline:
             try:

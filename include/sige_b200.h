@@ -285,6 +285,16 @@ int sige_attention_tokens_supported(int N, int C, int dtype);
 int sige_attention_tokens(const void *qkv, void *out, int B, int N, int C, int dtype, int flags,
                           sige_stream_t stream);
 
+/* ------------------------------------------------------------------------- */
+/* diagnostics                                                                */
+/* ------------------------------------------------------------------------- */
+/* In-kernel timeline: while `buf` (device int64, 16 slots per CTA of the NEXT sige_tile_conv launch that takes the tcgen05
+ * path) is set, that launch stamps %globaltimer per CTA — slot 0 entry, 3 dependency released + loads issued, 4 halo stored,
+ * 5/6 MMA issue begin/end, 7 accumulator ready, 8/9 exchange, 10 stored, 11 exit.  The pointer is baked into the launch's
+ * kernel parameters (so it survives CUDA-graph capture); call again (NULL to stop) before the next launch.  bench.py derives
+ * the in-step roofline from these stamps; returns 0. */
+int sige_debug_set_trace(void *buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,7 @@ PROTOTYPES = {
     "sige_conv_out_nhwc": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "sige_attention_tokens_supported": (_I, [_I, _I, _I]),
     "sige_attention_tokens": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "sige_debug_set_trace": (_I, [_P]),
 }
 
 _lib = None

@@ -914,7 +914,10 @@ static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaSt
 }  // namespace tc5
 
 static long long *g_trace = nullptr;
-extern "C" void sige_debug_set_trace(void *buf) { g_trace = reinterpret_cast<long long *>(buf); }
+extern "C" int sige_debug_set_trace(void *buf) {
+    g_trace = reinterpret_cast<long long *>(buf);
+    return 0;
+}
 
 // Can the tcgen05 kernel take this layer?  (3x3 stride 1 on 6x6 tiles, or 1x1 on 4x4 tiles; Cout % 64 == 0)
 bool tc5_supported(const sige_tile_conv_t *a) {

@@ -197,6 +197,32 @@ class Gather(SIGEModule):
                                       "(or set_fused(True, dtype=...)); the eager operator modules share one tile list across the batch")
 
 
+def prefill_active_indices(modules, masks: Dict, cache: Dict) -> int:
+    """All mask reductions of one ``set_masks`` call with ONE host synchronisation: every distinct (resolution, tile
+    geometry) of the model's Gathers is launched first, then the counts come back in a single device->host copy (the
+    reference pays one ``torch.nonzero`` sync per geometry, sige/utils.py:30).  Fills `cache` with the entries
+    ``Gather.set_mask`` looks up.  Returns the number of launches."""
+    pending = []
+    for g in modules:
+        if not isinstance(g, Gather) or g.input_res is None:
+            continue
+        res = tuple(g.input_res)
+        mask = masks.get(res)
+        if mask is None or not mask.is_cuda or mask.dim() != 2:
+            continue
+        key = ("active_indices", *res, *g.block_size, *g.block_stride, *g.offset)
+        if key in cache or any(k == key for k, _, _ in pending):
+            continue
+        m = (mask > 0.5) if mask.is_floating_point() else (mask != 0)      # same binarisation as masks.reduce_mask
+        out, count = ops.reduce_mask_cuda_launch(m, g.block_size, g.block_stride, g.offset)
+        pending.append((key, out, count))
+    if pending:
+        counts = torch.cat([c for _, _, c in pending]).cpu().tolist()      # the one sync
+        for (key, out, _), n in zip(pending, counts):
+            cache[key] = (out[:n].contiguous(), None)
+    return len(pending)
+
+
 class Scatter(SIGEModule):
     """Pastes the conv's output tiles into (a copy of) the cached original output
     (reference scatter.py:9-63)."""

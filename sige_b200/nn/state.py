@@ -142,10 +142,25 @@ class SIGEModel(nn.Module):
                 yield m
 
     def set_masks(self, masks: Dict[Tuple[int, int], torch.Tensor]):
+        """Difference-mask pyramid -> active tile lists of every module (reference base.py:102-108).
+
+        Beyond the reference: (i) calling it again with the SAME mask tensors (Stable Diffusion's sampler does, every step:
+        stable-diffusion/ldm/models/diffusion/ddim.py:203-204) is a no-op — no kernel, no host sync, compiled fused steps stay
+        valid; (ii) a new pyramid costs ONE host synchronisation for all geometries together (the reference pays one
+        ``torch.nonzero`` sync per geometry)."""
+        sig = tuple(sorted((tuple(res), t.data_ptr(), t._version, tuple(t.shape), str(t.dtype), str(t.device)) for res, t in masks.items()))
+        d = self.__dict__
+        if d.get("_mask_sig") == sig and d.get("_mask_modules") == sum(1 for _ in self._sige_modules()):
+            return
         self.timestamp += 1
         shared: Dict = {}  # geometry-keyed memo shared by all modules during this call
-        for m in self._sige_modules():
+        from .modules import prefill_active_indices
+
+        mods = list(self._sige_modules())
+        prefill_active_indices(mods, masks, shared)
+        for m in mods:
             m.set_mask(masks, shared, self.timestamp)
+        d["_mask_sig"], d["_mask_keep"], d["_mask_modules"] = sig, list(masks.values()), len(mods)     # (the tensors are kept alive: their addresses are part of the key)
 
     def set_mode(self, mode: str):
         self.mode = mode

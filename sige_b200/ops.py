@@ -128,8 +128,8 @@ def _bump(n: int = 1) -> None:
 # --------------------------------------------------------------------------------------
 # a1: reduce_mask on device          (reference sige/utils.py:8-37)
 # --------------------------------------------------------------------------------------
-def reduce_mask_cuda(mask: torch.Tensor, block_size, stride, padding) -> torch.Tensor:
-    """bool/uint8 [H,W] CUDA mask -> int32 [N,2] active tile origins, row-major, bit-exact."""
+def reduce_mask_cuda_launch(mask: torch.Tensor, block_size, stride, padding):
+    """Enqueue the ordered-compaction kernel; returns (idx buffer [capacity, 2], device count [1]) WITHOUT synchronising."""
     _require_cuda(mask)
     H, W = mask.shape
     m8 = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
@@ -144,7 +144,13 @@ def reduce_mask_cuda(mask: torch.Tensor, block_size, stride, padding) -> torch.T
             "sige_reduce_mask",
         )
     _bump()
-    n = int(count.item())  # the one host sync of set_masks (the reference's torch.nonzero syncs too)
+    return out, count
+
+
+def reduce_mask_cuda(mask: torch.Tensor, block_size, stride, padding) -> torch.Tensor:
+    """bool/uint8 [H,W] CUDA mask -> int32 [N,2] active tile origins, row-major, bit-exact."""
+    out, count = reduce_mask_cuda_launch(mask, block_size, stride, padding)
+    n = int(count.item())  # one host sync (the reference's torch.nonzero syncs too); SIGEModel.set_masks batches all geometries into one
     return out[:n].contiguous()
 
 

@@ -20,6 +20,9 @@ from .nn import SIGEConv2d
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+TRAFFIC_CAPTURE = "r02_tileconv_dram_traffic_step.csv"      # ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of `bench.py --ncu`
+
+
 def peaks():
     p = os.path.join(_REPO, "MEASURED_PEAKS.json")
     try:
@@ -35,7 +38,7 @@ def profiled_traffic():
     launch; None if the capture is absent."""
     import csv
 
-    path = os.path.join(_REPO, "profiles", "r01j_tileconv_dram_traffic_step.csv")
+    path = os.path.join(_REPO, "profiles", TRAFFIC_CAPTURE)
     try:
         rows = [r for r in csv.reader(open(path)) if len(r) > 10]
         hdr = rows[0]
@@ -163,4 +166,101 @@ def measure_engine(engine, flush, reps: int = 5):
                    "frac": tot_flops / (tot_ms * 1e-3) / 1e12 / pk["bf16_tflops"]},
         "slowest": [{"layer": n, "us": 1e3 * ms, "tiles": t, "GBps": by / (ms * 1e-3) / 1e9} for n, ms, by, fl, t in slow],
         "note": "cold L2 (flushed before every launch); launch latency included in the event bracket",
+    }
+
+
+def measure_in_graph(model, args, options, flush, reps: int = 5):
+    """IN-STEP roofline of the dominant kernel (tc5::tile_conv_tc5_kernel): a second fused step is built whose tcgen05
+    launches stamp %globaltimer per CTA into a trace buffer (pointer baked into the captured kernel parameters), the
+    CUDA graph is replayed after an L2 flush, and per launch  start = first CTA's entry, end = last CTA's exit.
+    Programmatic dependent launch lets a layer's prologue overlap its predecessor, so the time CHARGED to launch i is its
+    exclusive part  end_i - max(start_i, end_{i-1})  — the charges add up to the union of the kernel's intervals, which is
+    <= the step time by construction.  achieved = sum(algorithmic bytes of those launches) / sum(charged time)."""
+    import ctypes
+
+    from . import _cabi
+    from .fused import FusedConv, FusedStep
+
+    lib = _cabi.lib()
+    dev = args[0].device
+    order, sizes = {}, []
+
+    def plan_ctas(fc):
+        pl = _cabi.TileConvPlan()
+        lib.sige_tile_conv_plan(ctypes.byref(fc.desc), ctypes.byref(pl))
+        return pl.grid_x * pl.grid_y * pl.grid_z if pl.path == 1 else 0
+
+    # pass 1 (no trace): learn the grids, size the trace buffer
+    opts = dict(options)
+    opts.pop("use_graph", None)
+    with torch.no_grad():
+        probe = FusedStep(model, *args, use_graph=False, **opts)
+    ctas = [plan_ctas(f) for f in probe.fused]
+    offs, tot = [], 0
+    for c in ctas:
+        offs.append(tot)
+        tot += c * 16
+    del probe
+    buf = torch.zeros(max(tot, 16), dtype=torch.int64, device=dev)
+    state = {"i": 0}
+
+    def hook(fc):
+        i = order.setdefault(id(fc), len(order))
+        lib.sige_debug_set_trace(buf.data_ptr() + offs[i] * 8 if (i < len(offs) and ctas[i] > 0) else None)
+
+    FusedConv.trace_hook = hook
+    try:
+        with torch.no_grad():
+            step = FusedStep(model, *args, use_graph=True, **opts)
+    finally:
+        FusedConv.trace_hook = None
+        lib.sige_debug_set_trace(None)
+    assert len(step.fused) == len(ctas)
+    charged = [0.0] * len(ctas)
+    first_last = []
+    for r in range(reps):
+        buf.zero_()
+        if flush is not None:
+            flush.fill_(r)
+        torch.cuda.synchronize(dev)
+        step.replay()
+        torch.cuda.synchronize(dev)
+        host = buf.cpu()
+        iv = []
+        for i, f in enumerate(step.fused):
+            if ctas[i] == 0:
+                continue
+            t = host[offs[i]:offs[i] + ctas[i] * 16].view(ctas[i], 16)
+            st, en = t[:, 0][t[:, 0] > 0], t[:, 11][t[:, 11] > 0]
+            if st.numel() and en.numel():
+                iv.append((int(st.min()), int(en.max()), i))
+        iv.sort()
+        prev_end = 0
+        for st, en, i in iv:
+            charged[i] += max(0, en - max(st, prev_end)) / 1e3 / reps          # us
+            prev_end = max(prev_end, en)
+        if iv:
+            first_last.append((iv[-1][1] - iv[0][0]) / 1e3)
+    traced = [i for i in range(len(ctas)) if ctas[i] > 0 and charged[i] > 0]
+    tot_us = sum(charged[i] for i in traced)
+    tot_bytes = float(sum(step.fused[i].bytes for i in traced))
+    tot_flops = float(sum(step.fused[i].flops for i in traced))
+    pk = peaks()
+    achieved = tot_bytes / (tot_us * 1e-6) / 1e9 if tot_us else 0.0
+    traffic = profiled_traffic()
+    slow = sorted(traced, key=lambda i: -charged[i])[:5]
+    return {
+        "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+        "traffic": traffic, "traffic_source": ("profiles/%s (ncu capture of `bench.py --ncu`, same kernel build; not measured in this run)" % TRAFFIC_CAPTURE) if traffic else None,
+        "kernel": "sige::tc5::tile_conv_tc5_kernel (%d of the %d fused gather-conv-scatter launches of one step; the rest run on mma.sync)" % (len(traced), len(ctas)),
+        "launches": len(traced), "avg_launch_us": tot_us / max(1, len(traced)), "sum_in_graph_us": tot_us,
+        "first_start_to_last_end_us": sorted(first_last)[len(first_last) // 2] if first_last else None,
+        "algorithmic_bytes_per_launch": tot_bytes / max(1, len(traced)), "algorithmic_bytes_per_step": float(step.algorithmic_bytes()),
+        "peak_source": pk["source"],
+        "tensor": {"achieved_tflops": tot_flops / (tot_us * 1e-6) / 1e12 if tot_us else 0.0, "peak_tflops": pk["bf16_tflops"],
+                   "frac": (tot_flops / (tot_us * 1e-6) / 1e12 / pk["bf16_tflops"]) if tot_us else 0.0},
+        "slowest": [{"layer": step.fused[i].name, "us": charged[i], "tiles": step.fused[i].tiles,
+                     "GBps": step.fused[i].bytes / (charged[i] * 1e-6) / 1e9} for i in slow],
+        "method": "in-graph %globaltimer stamps (first CTA entry .. last CTA exit per launch), L2 flushed before the replay, "
+                  "overlap with the predecessor (PDL prologue) charged once; median-free mean of %d replays" % reps,
     }

@@ -230,3 +230,29 @@ def test_batch_of_independent_edits_on_gpu():
         print("edit %d: batched vs single %.3g" % (e, d))
         # same arithmetic per tile; split-K / tile-width choices differ with the total tile count -> fp16 reassociation only
         assert d <= 3e-3
+
+
+def test_set_masks_again_with_the_same_masks_is_free():
+    """Stable Diffusion's sampler calls set_masks(conv_masks) before every step with the same dict
+    (stable-diffusion/ldm/models/diffusion/ddim.py:203-204): no kernel, no host sync, the compiled step stays valid."""
+    from sige.utils import downsample_mask
+    from sige_b200 import ops
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
+
+    cfg = DDPMConfig.small()
+    model, x1, t = _prepared("intree", cfg, 0.05, torch.float16)
+    _, _, mask, _ = synthetic_inputs(cfg, 0.05, seed=0)
+    masks = downsample_mask(mask.to(DEV), min_res=8)
+    with torch.no_grad():
+        model.set_masks(masks)
+        a = model(x1, t)
+        step, stamp, launches = model.fused_step, model.timestamp, ops.launch_count
+        model.set_masks(masks)
+        assert model.timestamp == stamp and ops.launch_count == launches
+        b = model(x1, t)
+        assert model.fused_step is step and torch.equal(a, b)
+        masks2 = {k: v.clone() for k, v in masks.items()}           # new tensors: a real set_masks (one sync for all geometries)
+        model.set_masks(masks2)
+        assert model.timestamp == stamp + 1
+        c = model(x1, t)
+    assert torch.equal(a, c)

@@ -27,7 +27,6 @@ with torch.no_grad():
     model.set_mode("full"); model(cl(x0), t.to(dev))
     model.set_masks(downsample_mask(mask.to(dev), min_res=8)); model.set_mode("sparse")
 lib = _cabi.lib()
-lib.sige_debug_set_trace.argtypes = [ctypes.c_void_p]
 SLOT = 256 * 16
 buf = torch.zeros(200 * SLOT, dtype=torch.int64, device=dev)
 order = {}
