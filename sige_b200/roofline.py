@@ -261,6 +261,6 @@ def measure_in_graph(model, args, options, flush, reps: int = 5):
                    "frac": (tot_flops / (tot_us * 1e-6) / 1e12 / pk["bf16_tflops"]) if tot_us else 0.0},
         "slowest": [{"layer": step.fused[i].name, "us": charged[i], "tiles": step.fused[i].tiles,
                      "GBps": step.fused[i].bytes / (charged[i] * 1e-6) / 1e9} for i in slow],
-        "method": "in-graph %globaltimer stamps (first CTA entry .. last CTA exit per launch), L2 flushed before the replay, "
+        "method": "in-graph %%globaltimer stamps (first CTA entry .. last CTA exit per launch), L2 flushed before the replay, "
                   "overlap with the predecessor (PDL prologue) charged once; median-free mean of %d replays" % reps,
     }
