@@ -813,8 +813,11 @@ struct Plan {
 static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int ksplit_req) {
     Plan pl;
     const long long m_blocks = ceil_div(NT, TILES);
-    // BN = 128 only when that still leaves enough CTAs; small problems want more, narrower CTAs
-    const bool wide = (Cout % 128 == 0) && (m_blocks * (Cout / 128) >= 148);
+    // BN = 128 when that still fills the machine — or when the narrow tiling would need more waves of 148 one-per-SM CTAs
+    // than the wide one (a batch of edits: 64 row blocks x Cout 256 is 256 narrow CTAs = 2 waves, 128 wide CTAs = 1 wave,
+    // and a CTA's gather — the long pole — is the same either way); small problems want more, narrower CTAs
+    const long long narrow_ctas = m_blocks * (Cout / 64), wide_ctas = m_blocks * (Cout / 128);
+    const bool wide = (Cout % 128 == 0) && (wide_ctas >= 148 || (narrow_ctas > 148 && ceil_div(wide_ctas, 148) < ceil_div(narrow_ctas, 148)));
     pl.bn = wide ? 128 : 64;
     const bool split_ok = pl.bn == 64;                       // Cfg::kSplitOk
     const int tps = (taps == 9 && pl.bn == 64) ? 3 : 1;     // Cfg::TPS

@@ -172,7 +172,8 @@ def measure_engine(engine, flush, reps: int = 5):
 def measure_in_graph(model, args, options, flush, reps: int = 5):
     """IN-STEP roofline of the dominant kernel (tc5::tile_conv_tc5_kernel): a second fused step is built whose tcgen05
     launches stamp %globaltimer per CTA into a trace buffer (pointer baked into the captured kernel parameters), the
-    CUDA graph is replayed after an L2 flush, and per launch  start = first CTA's entry, end = last CTA's exit.
+    CUDA graph is replayed after an L2 flush, and per launch  start = the first CTA whose dependency resolved
+    (griddepcontrol.wait returned), end = last CTA's exit.
     Programmatic dependent launch lets a layer's prologue overlap its predecessor, so the time CHARGED to launch i is its
     exclusive part  end_i - max(start_i, end_{i-1})  — the charges add up to the union of the kernel's intervals, which is
     <= the step time by construction.  achieved = sum(algorithmic bytes of those launches) / sum(charged time)."""
@@ -231,7 +232,10 @@ def measure_in_graph(model, args, options, flush, reps: int = 5):
             if ctas[i] == 0:
                 continue
             t = host[offs[i]:offs[i] + ctas[i] * 16].view(ctas[i], 16)
-            st, en = t[:, 0][t[:, 0] > 0], t[:, 11][t[:, 11] > 0]
+            # slot 3 = this CTA's dependency has resolved (griddepcontrol.wait returned) and its gather loads are issued: the
+            # prologue before it (barrier init, TMEM alloc, weight prefetch) overlaps the PREDECESSOR under PDL and is not
+            # charged; slot 11 = CTA exit
+            st, en = t[:, 3][t[:, 3] > 0], t[:, 11][t[:, 11] > 0]
             if st.numel() and en.numel():
                 iv.append((int(st.min()), int(en.max()), i))
         iv.sort()
@@ -261,6 +265,6 @@ def measure_in_graph(model, args, options, flush, reps: int = 5):
                    "frac": (tot_flops / (tot_us * 1e-6) / 1e12 / pk["bf16_tflops"]) if tot_us else 0.0},
         "slowest": [{"layer": step.fused[i].name, "us": charged[i], "tiles": step.fused[i].tiles,
                      "GBps": step.fused[i].bytes / (charged[i] * 1e-6) / 1e9} for i in slow],
-        "method": "in-graph %%globaltimer stamps (first CTA entry .. last CTA exit per launch), L2 flushed before the replay, "
+        "method": "in-graph %%globaltimer stamps (first CTA past its dependency .. last CTA exit per launch), L2 flushed before the replay, "
                   "overlap with the predecessor (PDL prologue) charged once; median-free mean of %d replays" % reps,
     }
