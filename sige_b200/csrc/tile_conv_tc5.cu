@@ -834,6 +834,12 @@ static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int kspl
         while (split_ok && ks < 8 && base * (ks * 2) <= kMaxCtas[ks * 2] && (J * tps) / (ks * 2) >= min_taps) ks *= 2;
     }
     if (ks > J || !split_ok) ks = 1;
+    // Two consecutive layers are co-resident under programmatic dependent launch (the successor's prologue overlaps this
+    // layer).  A B200 holds 15 clusters of 8 (ncu: Max Active Clusters) — two layers of 8 clusters each do not fit and the 16th
+    // cluster starts, cold, only when a cluster of the predecessor exits (measured: +3 us on every second layer of the dense
+    // 8x8 / 16x16 blocks, profiles/r02_graph_timeline_spread.txt).  A/B knob: fall back to clusters of 4 (33 fit) there.
+    static int pair_fit = getenv("SIGE_TC5_PAIR_FIT") ? atoi(getenv("SIGE_TC5_PAIR_FIT")) : 0;
+    if (pair_fit && ksplit_req <= 0 && ks == 8 && base > 7) ks = 4;
     pl.ksplit = ks;
     static int deep_env = getenv("SIGE_TC5_DEEP") ? atoi(getenv("SIGE_TC5_DEEP")) : 1;   // A/B knob
     pl.deep = (pl.bn == 64 && taps == 9 && ks > 1 && deep_env) ? 1 : 0;

@@ -89,4 +89,17 @@ if "--detail" in sys.argv:
                     (names[i], t_.shape[0], (int(t_[:, 0].min()) - t0) / 1e3, med(3), med(4), med(6), med(7), med(8), mx(10), mx(11))))
     for _, line in sorted(det):
         print(line)
+if "--spread" in sys.argv:
+    print("--- per-launch spread over CTAs (us after the first kernel start): released min/med/max | acc ready min/med/max | exchange done min/med/max | stored min/med/max")
+    for i in sorted(names):
+        t_ = tt[i]; t_ = t_[t_[:, 0] > 0]
+        if t_.shape[0] == 0:
+            continue
+        def mmm(k):
+            v = t_[:, k][t_[:, k] > 0]
+            if not v.numel():
+                return "   nan    nan    nan"
+            v = (v - t0).double() / 1e3
+            return "%7.2f %7.2f %7.2f" % (float(v.min()), float(v.median()), float(v.max()))
+        print("%-28s n%3d | %s | %s | %s | %s" % (names[i], t_.shape[0], mmm(3), mmm(7), mmm(8), mmm(10)))
 print("first start -> last end: %.1f us; sum of kernel durations %.1f us over %d traced launches" % ((prev_end - t0) / 1e3, busy / 1e3, len(rows)))
