@@ -231,6 +231,14 @@ typedef struct {
 /* Fused gather -> (affine+SiLU) -> conv (+bias) -> (+residual) -> scatter, one launch. */
 int sige_tile_conv(const sige_tile_conv_t *p, sige_stream_t stream);
 
+/* Residual block: conv1 -> conv2 of one block (reference diffusion/models/ddpm_arch/sige_fused_unet.py:100-131: main_gather ->
+ * conv1 -> scatter_gather -> conv2 -> scatter[_with_block_residual]) as ONE call.  `conv2` gathers from the buffer `conv1`
+ * scatters into (conv1->dst or one of its aux views must be conv2's source); its fused 1x1 shortcut / residual fields carry
+ * the block's skip path.  The two launches are chained by programmatic dependent launch (SIGE_CONV_PDL is forced on the
+ * second): conv2's prologue and weight prefetch overlap conv1, its gather waits for conv1's tiles.  Returns the first
+ * non-zero status. */
+int sige_resblock(const sige_tile_conv_t *conv1, const sige_tile_conv_t *conv2, sige_stream_t stream);
+
 /* Generic (any dtype incl. fp32, any channel count, groups, dilation) tile convolution on a
  * stack: x (M, Cin, R, S) -> out (M, Cout, Ro, So); w OIHW in `dtype`; fp32 accumulate. */
 int sige_tile_conv_generic(const void *x, const void *w, const void *bias, void *out, int dtype,

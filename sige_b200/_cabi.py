@@ -97,6 +97,7 @@ PROTOTYPES = {
     "sige_scatter_gather": (_I, [_P, _P] + [_I] * 10 + [_P, _I, _P, _BP, _BP, _I, _I, _P, _P]),
     "sige_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "sige_tile_conv": (_I, [POINTER(TileConv), _P]),
+    "sige_resblock": (_I, [POINTER(TileConv), POINTER(TileConv), _P]),
     "sige_tile_conv_generic": (_I, [_P, _P, _P, _P] + [_I] * 14 + [_P]),
     "sige_tile_conv_plan": (_I, [_P, _P]),
     "sige_conv_in_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -602,3 +602,21 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     if (a->dtype == SIGE_F16) return launch_tile_conv<__half>(p, (cudaStream_t)stream);
     return launch_tile_conv<__nv_bfloat16>(p, (cudaStream_t)stream);
 }
+
+// conv1 -> conv2 of one residual block as one call (see include/sige_b200.h).
+extern "C" int sige_resblock(const sige_tile_conv_t *conv1, const sige_tile_conv_t *conv2, sige_stream_t stream) {
+    using namespace sige;
+    SIGE_REQUIRE(conv1 && conv2, "sige_resblock: null descriptor");
+    bool chained = false;       // conv2 must read what conv1 writes
+    for (int s = 0; s < conv2->n_src; ++s) {
+        if (conv1->dst && conv2->src[s].ptr == conv1->dst) chained = true;
+        for (int a = 0; a < conv1->n_aux; ++a)
+            if (conv2->src[s].ptr == conv1->aux[a].ptr) chained = true;
+    }
+    SIGE_REQUIRE(chained, "sige_resblock: conv2 does not gather from conv1's destination (or one of its aux views)");
+    int rc = sige_tile_conv(conv1, stream);
+    if (rc != 0) return rc;
+    sige_tile_conv_t second = *conv2;
+    second.flags |= SIGE_CONV_PDL;
+    return sige_tile_conv(&second, stream);
+}

@@ -256,3 +256,78 @@ def test_set_masks_again_with_the_same_masks_is_free():
         assert model.timestamp == stamp + 1
         c = model(x1, t)
     assert torch.equal(a, c)
+
+
+def test_multi_step_cached_flow_on_the_fused_path():
+    """The all-steps cache protocol (reference diffusion_demo/samplers/ddim_ddpm_sampler.py:60-66): dense passes fill
+    original_outputs[step] for every step id once; an edit then runs sparse for all steps with no dense pass.  On the fused
+    path every step id gets its own compiled step (own buffers, initialised from that id's caches) which later edits with
+    the same masks reuse."""
+    from sige.utils import downsample_mask
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
+
+    cfg = DDPMConfig.small()
+    model = _model("intree", cfg).to(DEV)
+    x0, x1, mask, t = synthetic_inputs(cfg, 0.05, seed=0)
+    x0, x1, t = x0.to(DEV), x1.to(DEV), t.to(DEV)
+    ids = [0, 1, 2]
+    with torch.no_grad():
+        model.set_mode("full")
+        for s in ids:
+            model.set_cache_id(s)
+            model(x0 * (1 + 0.1 * s), t + 10 * s)
+        model.set_masks(downsample_mask(mask.to(DEV), min_res=8))
+        model.set_mode("sparse")
+        eager, fused, steps = [], [], []
+        model.set_fused(False)
+        for s in ids:
+            model.set_cache_id(s)
+            eager.append(model(x1 * (1 + 0.1 * s), t + 10 * s))
+        model.set_fused(True, dtype=torch.float16)
+        for rnd in range(2):
+            for s in ids:
+                model.set_cache_id(s)
+                out = model(x1 * (1 + 0.1 * s), t + 10 * s)
+                if rnd == 0:
+                    fused.append(out)
+                    steps.append(model.fused_step)
+                else:
+                    assert model.fused_step is steps[s], "the step compiled for cache id %d is reused" % s
+                    assert torch.equal(out, fused[s])
+    assert len({id(s) for s in steps}) == 3
+    for s in ids:
+        e = float((fused[s] - eager[s]).abs().max() / eager[s].abs().max())
+        assert e <= TOL_MAX, "cache id %d: fused vs eager %g" % (s, e)
+    assert float((eager[0] - eager[1]).abs().max()) > 1e-3, "the step ids really hold different caches"
+
+
+def test_resblock_entry_point_equals_its_two_launches():
+    """sige_resblock (C-ABI): conv1 -> conv2 of one residual block as one call == the two sige_tile_conv launches."""
+    import ctypes
+
+    from sige_b200 import _cabi
+    from sige_b200.fused import FusedStep
+    from sige_b200.workloads.ddpm import DDPMConfig
+
+    model, x1, t = _prepared("intree", DDPMConfig.small(), 0.05, torch.float16)
+    with torch.no_grad():
+        step = FusedStep(model, x1, t, use_graph=False)
+    by_name = {f.name: f for f in step.fused}
+    c1, c2 = by_name["down.0.block.0.scatter_gather"], by_name["down.0.block.0.scatter"]
+    dst = c2.spec.dst.raw
+    step.run_eager()
+    torch.cuda.synchronize()
+    want = dst.clone()
+    dst.zero_()
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = _cabi.lib().sige_resblock(ctypes.byref(c1.desc), ctypes.byref(c2.desc), stream)
+    assert rc == 0, _cabi.last_error()
+    torch.cuda.synchronize()
+    idx = c2.spec.idx.long()
+    # the call rewrites exactly the active output tiles
+    for (iy, ix) in idx.tolist()[:8]:
+        oy, ox = iy + c2.spec.off, ix + c2.spec.off
+        assert torch.equal(dst[:, :, oy:oy + 4, ox:ox + 4], want[:, :, oy:oy + 4, ox:ox + 4])
+    # a conv2 that does not read conv1's output is refused
+    other = by_name["down.1.block.0.scatter"]
+    assert _cabi.lib().sige_resblock(ctypes.byref(c1.desc), ctypes.byref(other.desc), stream) != 0
