@@ -21,13 +21,32 @@ ratio = 0.012
 for a in sys.argv[1:]:
     if a.startswith("--ratio="):
         ratio = float(a.split("=")[1])
-x0, x1, mask, t = synthetic_inputs(cfg, ratio, seed=0)
+n_edits = 1
+for a in sys.argv[1:]:
+    if a.startswith("--edits="):
+        n_edits = int(a.split("=")[1])
+edit_x, edit_masks = [], []
+for e in range(n_edits):            # the batch of bench.py --edits N
+    x0, x1e, mask_e, t = synthetic_inputs(cfg, ratio, seed=0, edit_seed=e)
+    if e > 0:
+        g = torch.Generator().manual_seed(1000 + e)
+        shift = tuple(int(v) for v in torch.randint(-96, 97, (2,), generator=g))
+        mask_e = torch.roll(mask_e, shift, (0, 1))
+        x1e = x0 + torch.roll(x1e - x0, shift, (2, 3))
+    edit_x.append(x1e)
+    edit_masks.append(mask_e)
+x1 = torch.cat(edit_x, 0)
 cl = lambda a: a.to(dev)
 with torch.no_grad():
     model.set_mode("full"); model(cl(x0), t.to(dev))
-    model.set_masks(downsample_mask(mask.to(dev), min_res=8)); model.set_mode("sparse")
+    if n_edits == 1:
+        model.set_masks(downsample_mask(edit_masks[0].to(dev), min_res=8))
+    else:
+        from sige_b200.masks import stack_mask_pyramids
+        model.set_masks(stack_mask_pyramids([downsample_mask(m.to(dev), min_res=8) for m in edit_masks]))
+    model.set_mode("sparse")
 lib = _cabi.lib()
-SLOT = 256 * 16
+SLOT = 1024 * 16
 buf = torch.zeros(200 * SLOT, dtype=torch.int64, device=dev)
 order = {}
 def hook(fc):
@@ -43,7 +62,7 @@ for _ in range(3):
 buf.zero_(); flush.fill_(2); torch.cuda.synchronize()
 eng.replay(); torch.cuda.synchronize()
 names = {order[id(f)]: f.name for f in eng.fused if id(f) in order}
-tt = buf.view(200, 256, 16).cpu()
+tt = buf.view(200, 1024, 16).cpu()
 rows = []
 for i in sorted(names):
     t_ = tt[i]; t_ = t_[t_[:, 0] > 0]
