@@ -173,6 +173,15 @@ __device__ __forceinline__ void st_async16(uint32_t remote_addr, uint32_t a, uin
                  "r"(b), "r"(c), "r"(d), "r"(remote_bar)
                  : "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register staging, so several chunks can be in flight per CTA;
+// src_bytes = 0 zero-fills the destination (outside the image / missing tile) without reading
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// this thread's arrival on `bar` fires once all of its cp.async issued so far have landed (one of the barrier's expected arrivals)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -276,7 +285,8 @@ __device__ __forceinline__ long long gtime() {
         if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); \
     } while (0)
 
-template <typename T, int BN, int TAPS, bool DEEP>
+// ASYNC: the gather is a pure copy (no pre-op: the producer of the source already applied it) and is done with cp.async.
+template <typename T, int BN, int TAPS, bool DEEP, bool ASYNC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap,
                      const __grid_constant__ CUtensorMap wmap2) {
@@ -435,6 +445,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 if (is_sc) st = 0;
                 if (j == j_begin || st == 0) {                        // a new chunk starts: wait for its halo buffer
                     mbar_wait(A_FULL(ab), (ause / NAB) & 1);
+                    if (ASYNC) fence_proxy_async();      // cp.async (generic proxy) writes -> visible to the tensor core's async proxy
                     if (j == j_begin && lane == 0) SIGE_TRACE(5);
                 }
                 mbar_wait(B_FULL(s), k & 1);
@@ -617,6 +628,83 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             }
         };
         auto issue_any = [&](int c) { if (c < NC) issue(c); else issue2(c - NC); };
+        if (ASYNC) {
+            // ---- pure-copy gather with cp.async: every unit goes straight from global/L2 to its (up to three) swizzled
+            //      destinations; the thread's arrival on A_FULL fires when its copies have landed, so the producer never
+            //      waits for data and keeps NAB chunks in flight (register staging kept exactly one in flight)
+            auto copy_chunk = [&](int c, unsigned char *abuf, uint32_t full_bar) {
+                const uint32_t abase = s32(abuf);
+                if (c < NC) {
+                    const int cbase = c * KC;
+                    const int sg = cbase >= p.C0 ? 1 : 0;
+                    const Seg &seg = p.seg[sg];
+                    const int cl = cbase - (sg ? p.C0 : 0);
+                    if (sg != g_sg) resolve(sg);
+#pragma unroll
+                    for (int k = 0; k < LOADS; ++k) {
+                        if (g_off[k] == -2) continue;
+                        const bool ok = g_off[k] >= 0;
+                        const T *src = reinterpret_cast<const T *>(seg.ptr) + (ok ? g_off[k] + cl : 0);
+                        const uint32_t nb = ok ? 16u : 0u;
+                        const int u = (ptid + k * NPROD) & 7;
+                        const int x = g_xyt[k] & 15, y = (g_xyt[k] >> 4) & 15, tl = g_xyt[k] >> 8;
+                        if (TAPS == 9) {
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int xp = x - kx;
+                                if (xp >= 0 && xp < 4) {
+                                    const int row = y * 32 + tl * 4 + xp;
+                                    cp_async16(abase + kx * A_COPY_BYTES + row * 128 + ((u ^ (row & 7)) << 4), src, nb);
+                                }
+                            }
+                        } else {
+                            const int row = tl * 16 + y * 4 + x;
+                            cp_async16(abase + row * 128 + ((u ^ (row & 7)) << 4), src, nb);
+                        }
+                    }
+                } else {
+                    // fused shortcut chunk: the 4x4 centre of each halo tile from the RAW block input into copy kx = 1
+                    const int cbase = (c - NC) * KC;
+                    const int sg = cbase >= p.C0_2 ? 1 : 0;
+                    const Seg &seg = p.seg2[sg];
+                    const int cl = cbase - (sg ? p.C0_2 : 0);
+                    const int Hs = p.H >> seg.up, Ws = p.W >> seg.up;
+#pragma unroll
+                    for (int k = 0; k < LOADS2; ++k) {
+                        const int q = ptid + k * NPROD;
+                        if (q >= TILES * 16 * 8) continue;
+                        const int pix = q >> 3, u = q & 7;
+                        const int tl = pix >> 4, rem = pix & 15;
+                        const int y = 1 + (rem >> 2), xx = 1 + (rem & 3);
+                        const int t = tile0 + tl;
+                        const T *src = reinterpret_cast<const T *>(seg.ptr);
+                        uint32_t nb = 0;
+                        if (t < p.NT && s_flags[tl]) {
+                            int b = 0;
+                            if (p.NT != p.N) b = t / p.N;
+                            const int hh = y + s_idx[2 * tl], ww = xx + s_idx[2 * tl + 1];
+                            if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) {
+                                src += (((long long)b * Hs + (hh >> seg.up)) * Ws + (ww >> seg.up)) * seg.C + cl + u * 8;
+                                nb = 16;
+                            }
+                        }
+                        const int row = (1 + (rem >> 2)) * 32 + tl * 4 + (rem & 3);
+                        cp_async16(abase + A_COPY_BYTES + row * 128 + ((u ^ (row & 7)) << 4), src, nb);
+                    }
+                }
+                cp_async_arrive(full_bar);
+            };
+            if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");   // activations of the previous layer are complete
+            int ab = 0, ause = 0;
+            for (int c = c_first; c <= c_last; ++c) {
+                mbar_wait(A_EMPTY(ab), ((ause / NAB) & 1) ^ 1);           // the MMAs that read this buffer have retired
+                if (ptid == 0 && c == c_first) SIGE_TRACE(3);
+                copy_chunk(c, smem + C::OFF_A + ab * A_BUF_BYTES, A_FULL(ab));
+                if (ptid == 0 && c == c_first) SIGE_TRACE(4);
+                ++ause;
+                ab = ause % NAB;
+            }
+        } else {
         if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");   // activations of the previous layer are complete
         issue_any(c_first);
         int ab = 0, ause = 0;
@@ -630,6 +718,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             if (c < c_last) issue_any(c + 1);
             ++ause;
             ab = ause % NAB;
+        }
         }
     }
 
@@ -846,8 +935,8 @@ static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int kspl
     return pl;
 }
 
-template <typename T, int BN, int TAPS, bool DEEP = false>
-static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaStream_t st) {
+template <typename T, int BN, int TAPS, bool DEEP, bool ASYNC>
+static int launch_v(Params &p, const void *w_packed, const void *w2_packed, cudaStream_t st) {
     using C = Cfg<BN, TAPS, DEEP>;
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
@@ -877,7 +966,7 @@ static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaSt
             return 2;
         }
     }
-    auto kern = tile_conv_tc5_kernel<T, BN, TAPS, DEEP>;
+    auto kern = tile_conv_tc5_kernel<T, BN, TAPS, DEEP, ASYNC>;
     static int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -918,6 +1007,15 @@ static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaSt
         return 2;
     }
     return 0;
+}
+
+// pure-copy gathers (no pre-op in the gather stage) take the cp.async variant
+template <typename T, int BN, int TAPS, bool DEEP = false>
+static int launch(Params &p, const void *w_packed, const void *w2_packed, cudaStream_t st) {
+    static int async_env = getenv("SIGE_TC5_ASYNC_GATHER") ? atoi(getenv("SIGE_TC5_ASYNC_GATHER")) : 1;      // A/B knob
+    const bool pure_copy = p.scale == nullptr && p.shift == nullptr && p.act == SIGE_ACT_IDENTITY;
+    if (pure_copy && async_env) return launch_v<T, BN, TAPS, DEEP, true>(p, w_packed, w2_packed, st);
+    return launch_v<T, BN, TAPS, DEEP, false>(p, w_packed, w2_packed, st);
 }
 
 }  // namespace tc5
