@@ -64,6 +64,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--ratio", type=float, default=0.012)
+    ap.add_argument("--workload", default="ddpm", choices=["ddpm", "sd", "gaugan"],
+                    help="ddpm = BASELINE.json's metric (default).  sd / gaugan = the reference's secondary consumers at full size "
+                         "(configs[2]: SD v1 U-Net, 64x64 latent, B = 2, 15 %% mask; configs[3]: SPADE generator 512x1024, 3 %% label edit), "
+                         "the reference's own unmodified model files on this repo's sige.nn: a secondary line, one GPU")
     ap.add_argument("--edits", type=int, default=1, help="independent edits of the same original image per GPU, batched in one fused step "
                                                          "(each with its own mask; weights are read once per step)")
     ap.add_argument("--total-edits", type=int, default=0, help="BASELINE.json configs[4]: a FIXED batch of edits sharded over the GPUs "
@@ -159,7 +163,7 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def _reference_child(backend: str, ratio: float, steps: int, warmup: int, threads: int, timeout: float):
+def _reference_child(backend: str, ratio: float, steps: int, warmup: int, threads: int, timeout: float, extra=()):
     """One run of baseline/run_reference.py (the reference's own python + native backend) in a clean child process."""
     import subprocess
 
@@ -172,7 +176,7 @@ def _reference_child(backend: str, ratio: float, steps: int, warmup: int, thread
         if host_cores() > 32:   # many-core host: keep torch's and the reference kernels' OpenMP runtimes from spinning against each other
             env.update(OMP_WAIT_POLICY="PASSIVE", GOMP_SPINCOUNT="0")
     cmd = [sys.executable, os.path.join(REPO, "baseline", "run_reference.py"), "--backend", backend, "--steps", str(steps), "--warmup", str(warmup),
-           "--ratio", str(ratio)] + (["--threads", str(threads)] if threads else [])
+           "--ratio", str(ratio)] + (["--threads", str(threads)] if threads else []) + list(extra)
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
     if out.returncode != 0:
         raise RuntimeError("reference child failed: %s" % out.stderr.strip().splitlines()[-1:] )
@@ -540,8 +544,91 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_consumer(args):
+    """Secondary line: the reference's SD U-Net / GauGAN generator (unmodified model files, full size) — the reference's own
+    CUDA path, this repo's exact fp32 operator modules and the fused fp16 step, on the same GPU, same inputs, with the
+    parity of the two latter against the former."""
+    import tempfile
+
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.join(REPO, "baseline"))
+    import consumers
+    import loader
+    from sige.utils import dilate_mask, downsample_mask
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    ref = None
+    if loader.available(cuda=True):
+        dump = os.path.join(tempfile.mkdtemp(prefix="sige_ref_"), "ref.npz")
+        r = _reference_child("cuda", args.ratio, max(1, min(args.steps, 20)), 3, 0, 900, extra=["--workload", args.workload])      # stock settings (TF32 convs): the timing
+        _reference_child("cuda", args.ratio, 1, 1, 0, 900, extra=["--workload", args.workload, "--no-tf32", "--dump", dump])         # exact fp32: the parity target
+        ref = (r, np.load(dump))
+        log("reference CUDA path: %.2f ms/step" % r["ms_per_step"])
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False      # our dense pass: exact fp32, like the parity target
+    net = (consumers.build_sd("full") if args.workload == "sd" else consumers.build_gaugan("full")).to(dev)
+    run = (lambda fused: consumers.run_sd(net, downsample_mask, device=dev, fused=fused, size="full")) if args.workload == "sd" else \
+          (lambda fused: consumers.run_gaugan(net, downsample_mask, dilate_mask, device=dev, fused=fused, size="full"))
+    full0, out_mod = run(lambda n: n.set_fused(False))
+    sparse_args = tuple(v.to(dev) for v in (consumers.sd_inputs("full") if args.workload == "sd" else consumers.gaugan_inputs("full")))
+    sparse_args = (sparse_args[1], sparse_args[3], sparse_args[4]) if args.workload == "sd" else (sparse_args[1],)
+
+    def timed(k):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        with torch.no_grad():
+            for i in range(k):
+                evs[i][0].record()
+                out = net(*sparse_args)
+                evs[i][1].record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / k, out
+
+    timed(3)
+    ms_mod, out_mod = timed(max(3, min(args.steps, 20)))
+    net.set_fused(True, dtype=dtype)
+    t0 = time.time()
+    with torch.no_grad():
+        net(*sparse_args)
+    compile_s = time.time() - t0
+    step = net.fused_step
+    timed(3)
+    ms_fused, out_fused = timed(max(5, min(args.steps, 50)))
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / np.abs(b).max())
+
+    parity = None
+    if ref is not None:
+        want = ref[1]["sparse_out"]
+        parity = {"dense_pass_vs_reference_cuda": rel(full0.float().cpu().numpy(), ref[1]["full0_out"]),
+                  "fp32_modules_vs_reference_cuda": rel(out_mod.float().cpu().numpy(), want),
+                  "fused_%s_vs_reference_cuda" % args.dtype: rel(out_fused.float().cpu().numpy(), want)}
+    from collections import Counter
+
+    name = {"sd": "Stable Diffusion v1 U-Net (859.5 M params), 64x64 latent (512x512 image), B = 2, 15 % square mask",
+            "gaugan": "GauGAN SPADE generator (ngf 64, 'more' up-sampling), 512x1024, 2.98 % label edit"}[args.workload]
+    line = {
+        "metric": "%s sparse steps/sec" % args.workload, "value": 1e3 / ms_fused, "unit": "steps/s", "n_gpus": 1, "ms_per_step": ms_fused,
+        "higher_is_better": True, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic (random-init weights)",
+        "config": {"workload": name, "model_file": "the reference's unmodified model file (baseline/_ref) on this repo's sige.nn",
+                   "path": "model(...) as a fused step: %d fused conv launches + %d recorded torch calls in one CUDA graph" % (len(step.fused), len(step.eager_nodes)) if step else "eager"},
+        "eager_fp32_modules_ms_per_step": ms_mod,
+        "reference_cuda_ms_per_step": None if ref is None else ref[0]["ms_per_step"],
+        "speedup_vs_reference_cuda": None if ref is None else ref[0]["ms_per_step"] / ms_fused,
+        "parity": parity, "compile_seconds": compile_s,
+        "eager_node_kinds": dict(Counter(step.eager_nodes).most_common(12)) if step else None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload != "ddpm" and args.impl == "ours":
+        run_consumer(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference-cuda":

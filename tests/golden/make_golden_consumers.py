@@ -4,7 +4,7 @@
 
 In the child process `import sige` is the reference's package from baseline/_ref (its python + its sige.cpu kernels); the
 models are the reference's own SIGEUNetModel (Stable Diffusion) and SIGEFusedSPADEGenerator (GauGAN) in miniature
-(tests/consumers.py).  Writes tests/golden/sd_mini_golden.npz and gaugan_mini_golden.npz.
+(baseline/consumers.py).  Writes tests/golden/sd_mini_golden.npz and gaugan_mini_golden.npz.
 """
 import os
 import subprocess
@@ -23,7 +23,7 @@ def child():
     assert os.path.realpath(sige.__file__).startswith(os.path.realpath(os.path.join(REPO, "baseline", "_ref"))), sige.__file__
     from sige.utils import dilate_mask, downsample_mask
 
-    sys.path.insert(0, os.path.join(REPO, "tests"))
+    sys.path.insert(0, os.path.join(REPO, "baseline"))
     import consumers
 
     torch.set_num_threads(8)

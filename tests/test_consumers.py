@@ -14,6 +14,7 @@ import torch
 from conftest import REPO, golden
 
 sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.path.insert(0, os.path.join(REPO, "baseline"))
 import consumers  # noqa: E402
 
 needs_ref = pytest.mark.skipif(not consumers.available(), reason="baseline/_ref absent (python baseline/build_ref.py)")
