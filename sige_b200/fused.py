@@ -369,6 +369,12 @@ class CudaExecutor:
     def attention_supported(self, n_tokens: int, channels: int) -> bool:
         return self.ops.attention_tokens_supported(n_tokens, channels, self.dtype)
 
+    def tail_supported(self, channels: int, cout: int) -> bool:
+        """sige_conv_out_nhwc stages a 10 x 34 pixel halo tile and the weights of all channels in shared memory (<= 227 KB)."""
+        pitch = channels * 2 + 16
+        smem = ((10 * 34 * pitch + 15) & ~15) + 8 * (9 * channels * 2 + 16)      # (CO_TH + 2) x (CO_TW + 2) = 10 x 34 pixels
+        return cout <= 8 and channels % 16 == 0 and channels <= 1024 and smem <= 227 * 1024
+
     def prepare_attention(self, qkv_tokens: torch.Tensor, out_tokens: torch.Tensor, pdl: bool):
         ops = self.ops
         from ._cabi import CONV_PDL
@@ -999,7 +1005,7 @@ class Lowering:
         out = node.outs[0]
         v = self.sym(x)
         if isinstance(v, GNVal):
-            if k == 3 and s == 1 and p == 1 and cout <= 8 and cin % 16 == 0 and v.act in (None, "swish"):
+            if k == 3 and s == 1 and p == 1 and cout <= 8 and cin % 16 == 0 and v.act in (None, "swish") and self.ex.tail_supported(cin, cout):
                 res = torch.empty((v.src.shape[0], cout, v.src.shape[2], v.src.shape[3]), dtype=self.dtype, device=self.dev)
                 v.src.readers.append(None)
                 x_raw = v.src.raw

@@ -157,6 +157,9 @@ class SimExecutor:
     def attention_supported(self, n_tokens, channels):
         return True
 
+    def tail_supported(self, channels, cout):
+        return True
+
     def prepare_attention(self, qkv_tokens, out_tokens, pdl):
         def run(_stream):
             self.launches += 1
