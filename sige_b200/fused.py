@@ -941,29 +941,45 @@ class Lowering:
             with torch._C.DisableTorchFunctionSubclass():
                 st = tuple(o.stride())
             # the recorded memory layout: later `view`s of this value were validated against exactly these strides
-            outs.append(torch.empty_strided(tuple(o.shape), st, dtype=self.dtype if o.dtype.is_floating_point else o.dtype, device=self.dev))
+            act_like = o.dtype.is_floating_point and o.dim() >= 3
+            outs.append(torch.empty_strided(tuple(o.shape), st, dtype=self.dtype if act_like else o.dtype, device=self.dev))
+
+        # Precision of a recorded call (mixed-precision steps: fp32 model, fp16/bf16 step): it runs under autocast — GEMM-like
+        # ops on the tensor cores in the step's dtype, softmax / norms / transcendental math in fp32 — on the tensors as they
+        # are stored: activation-like values (>= 3-D) in the step's dtype, small ones (time embeddings, statistics) in the
+        # dtype the model computed them in.  Constant fp32 operands of GEMM-like ops (weights) are converted once, here.
+        is_module_call = isinstance(node.op, str)
+        gemm_like = node.name in ("linear", "bmm", "matmul", "conv2d", "conv1d", "baddbmm", "addmm", "mm", "einsum")
+        half_consts: Dict[int, torch.Tensor] = {}
 
         def sub(o):
             if not isinstance(o, LazyTensor):
+                if gemm_like and _is_const(o) and o.dtype == torch.float32 and self.dtype != torch.float32:
+                    if id(o) not in half_consts:
+                        half_consts[id(o)] = o.detach().to(self.dtype)
+                    return half_consts[id(o)]
                 return o
             g = getters[id(o)]
-            if g.dtype != o.dtype:
-                g = g.to(o.dtype)                 # mixed precision: the recorded call saw the model's dtype
+            if is_module_call and g.dtype != o.dtype:
+                g = g.to(o.dtype)          # an operator module falling back to its eager kernels works in the MODEL's dtype (its caches are)
             want = lazy_strides[id(o)]
             if g.dim() >= 2 and tuple(g.stride()) != want and g.numel() > 0:
-                # ... and the model's memory layout (NHWC buffers vs the strides `view` was recorded on)
+                # the model's memory layout (NHWC buffers vs the strides `view` was recorded on)
                 g = torch.empty_strided(tuple(g.shape), want, dtype=g.dtype, device=g.device).copy_(g)
             return g
 
         op, module, multi = node.op, node.module, node.multi
+        use_autocast = self.dev.type == "cuda" and self.dtype in (torch.float16, torch.bfloat16) and not is_module_call
+        dev_type, ac_dtype = self.dev.type, self.dtype
 
         def run(_stream):
             args = lazy._tree_map(sub, node.args)
             kwargs = lazy._tree_map(sub, node.kwargs)
-            if isinstance(op, str):
-                res = module(*args)
-            else:
-                res = op(*args, **kwargs)
+            with torch.autocast(device_type=dev_type, dtype=ac_dtype, enabled=use_autocast):
+                if isinstance(op, str):
+                    res = module(*args)
+                else:
+                    res = op(*args, **kwargs)
             res = list(res) if multi else [res]
             for dst, r in zip(outs, [r for r in res if isinstance(r, torch.Tensor)]):
                 dst.copy_(r)
@@ -1349,17 +1365,21 @@ class Lowering:
         return (not a["training"] or a["p"] == 0) and not a["inplace"] and self._alias(node, a["input"])
 
     def _h_float(self, node: Node):        # GroupNorm32 of the SD code: `super().forward(x.float()).type(x.dtype)`
-        return self._alias(node, node.args[0])
+        x = node.args[0]
+        return isinstance(x, LazyTensor) and x.dtype.is_floating_point and self._alias(node, x)
 
     _h_half = _h_float
     _h_contiguous = _h_float
 
     def _h_type(self, node: Node):
         a = self._bind(node, ("input", "dtype"), {"dtype": None})
-        return isinstance(a["dtype"], torch.dtype) and a["dtype"].is_floating_point and self._alias(node, a["input"])
+        x = a["input"]
+        return (isinstance(a["dtype"], torch.dtype) and a["dtype"].is_floating_point and isinstance(x, LazyTensor) and x.dtype.is_floating_point
+                and self._alias(node, x))
 
     def _h_to(self, node: Node):
-        if len(node.args) == 2 and isinstance(node.args[1], torch.dtype) and node.args[1].is_floating_point and not node.kwargs:
+        if (len(node.args) == 2 and isinstance(node.args[1], torch.dtype) and node.args[1].is_floating_point and not node.kwargs
+                and isinstance(node.args[0], LazyTensor) and node.args[0].dtype.is_floating_point):
             return self._alias(node, node.args[0])
         return False
 
