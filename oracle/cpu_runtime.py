@@ -107,6 +107,10 @@ def reference_cpu_runtime():
     saved_ops, saved_conv = modules.ops, modules.SIGEConv2d._sparse_forward
 
     def conv_sparse(self, x):  # reference sige/nn/base.py:88-89
+        from sige_b200 import lazy
+
+        if lazy.is_lazy(x):           # a trace in progress (sige_b200.fused): record the operator-module call as the product does
+            return saved_conv(self, x)
         return F.conv2d(x, self.weight, self.bias, self.stride, (0, 0), self.dilation, self.groups)
 
     modules.ops = cpu_ops

@@ -501,7 +501,17 @@ class AttnOut:
         self.s, self.v = s, v
 
 
+class GScores:
+    """q @ k^T (* scale) of generic (batch*heads, tokens, dim) operands — the attention core of the SD transformer blocks
+    (reference stable-diffusion/ldm/modules/sige_attention.py:46-60, attention.py CrossAttention)."""
+
+    def __init__(self, q: LazyTensor, k: LazyTensor, scale: float = 1.0, probs: bool = False):
+        self.q, self.k, self.scale, self.probs = q, k, scale, probs
+
+
 _MATERIAL = (Full, Stack, RealStack, ConvOut, RealT)
+_VIEW_OPS = {"reshape", "view", "permute", "transpose", "chunk", "split", "__getitem__", "unsqueeze", "squeeze", "flatten", "unflatten",
+             "expand", "narrow", "select", "unbind", "t", "movedim", "swapaxes", "view_as", "reshape_as", "T.__get__", "mT.__get__"}
 
 
 def _is_const(o) -> bool:
@@ -529,6 +539,7 @@ class Lowering:
         self.fused: List[FusedConv] = []
         self.conv_ins: List[ConvInRec] = []
         self.eager_nodes: List[str] = []
+        self.view_nodes = 0              # view ops resolved at build time (no run-time work)
         self._all_idx: Dict = {}
         self._vecs: Dict = {}
         self._pending_prepare: List[Callable[[], None]] = []
@@ -936,6 +947,9 @@ class Lowering:
 
         lazy._tree_map(bind, node.args)
         lazy._tree_map(bind, node.kwargs)
+        is_module_call = isinstance(node.op, str)
+        if not is_module_call and node.name in _VIEW_OPS and self._static_view(node, getters):
+            return
         outs = []
         for o in node.outs:
             with torch._C.DisableTorchFunctionSubclass():
@@ -948,7 +962,6 @@ class Lowering:
         # ops on the tensor cores in the step's dtype, softmax / norms / transcendental math in fp32 — on the tensors as they
         # are stored: activation-like values (>= 3-D) in the step's dtype, small ones (time embeddings, statistics) in the
         # dtype the model computed them in.  Constant fp32 operands of GEMM-like ops (weights) are converted once, here.
-        is_module_call = isinstance(node.op, str)
         gemm_like = node.name in ("linear", "bmm", "matmul", "conv2d", "conv1d", "baddbmm", "addmm", "mm", "einsum")
         half_consts: Dict[int, torch.Tensor] = {}
 
@@ -963,11 +976,12 @@ class Lowering:
             if is_module_call and g.dtype != o.dtype:
                 g = g.to(o.dtype)          # an operator module falling back to its eager kernels works in the MODEL's dtype (its caches are)
             want = lazy_strides[id(o)]
-            if g.dim() >= 2 and tuple(g.stride()) != want and g.numel() > 0:
-                # the model's memory layout (NHWC buffers vs the strides `view` was recorded on)
+            if stride_sensitive and g.dim() >= 2 and tuple(g.stride()) != want and g.numel() > 0:
+                # `view` was validated against the model's memory layout (NCHW tensors), the buffers are NHWC
                 g = torch.empty_strided(tuple(g.shape), want, dtype=g.dtype, device=g.device).copy_(g)
             return g
 
+        stride_sensitive = is_module_call or node.name in ("view", "view_as", "as_strided")
         op, module, multi = node.op, node.module, node.multi
         use_autocast = self.dev.type == "cuda" and self.dtype in (torch.float16, torch.bfloat16) and not is_module_call
         dev_type, ac_dtype = self.dev.type, self.dtype
@@ -990,6 +1004,28 @@ class Lowering:
         for o, t in zip(node.outs, outs):
             # pointwise math on a tile stack yields a tile stack (GauGAN's SPADE modulation between Gather and the conv)
             self.env[id(o)] = RealStack(t) if (is_stack_op or (not isinstance(node.op, str) and tuple(o.shape) in stack_shapes)) else RealT(t)
+
+    def _static_view(self, node: Node, getters: Dict[int, torch.Tensor]) -> bool:
+        """A pure view op (reshape / permute / split / indexing ...) of persistent tensors is evaluated ONCE, here: its result
+        aliases the persistent buffer, which every replay refreshes in place — no kernel, no copy at run time."""
+        def sub(o):
+            return getters[id(o)] if isinstance(o, LazyTensor) else o
+
+        try:
+            with torch.no_grad():
+                res = node.op(*lazy._tree_map(sub, node.args), **lazy._tree_map(sub, node.kwargs))
+        except Exception:  # noqa: BLE001  (e.g. `view` on a layout it was not recorded on: the run-time path fixes the strides)
+            return False
+        res = list(res) if node.multi else [res]
+        tensors = [r for r in res if isinstance(r, torch.Tensor)]
+        bases = {g.untyped_storage().data_ptr() for g in getters.values()}
+        if len(tensors) != len(node.outs) or not all(r.untyped_storage().data_ptr() in bases and tuple(r.shape) == tuple(o.shape)
+                                                     for r, o in zip(tensors, node.outs)):
+            return False           # the op had to copy (or is not a view): evaluate it at run time
+        for o, r in zip(node.outs, tensors):
+            self.env[id(o)] = RealT(r)
+        self.view_nodes += 1
+        return True
 
     # ------------------------------------------------------------------ node handlers
     def _lower(self, node: Node) -> None:
@@ -1132,8 +1168,10 @@ class Lowering:
         x, residual = node.args
         m = node.module
         co = self.sym(x)
-        if not (isinstance(co, ConvOut) and co.on_tiles and self.n_uses(x) == 1):
+        if not (isinstance(co, ConvOut) and co.on_tiles):
             return False
+        # (a conv output that is ALSO consumed as a stack — SD's transformer scatters proj_in's tiles and keeps them as
+        #  tokens, sige_attention.py:153-160 — is launched once per form: scatter form here, stack form at its other consumer)
         g = m.gather.module
         if isinstance(co.src, Stack) and not self._same_gather(co.src.gather, g):
             return False
@@ -1158,15 +1196,17 @@ class Lowering:
         x, scale, shift = node.args
         m = node.module
         co = self.sym(x)
-        if not (isinstance(co, ConvOut) and co.on_tiles and isinstance(co.src, Stack) and self.n_uses(x) == 1):
+        if not (isinstance(co, ConvOut) and co.on_tiles and self.n_uses(x) == 1):
             return False
         if not (scale is None or _is_const(scale)) or not (shift is None or _is_const(shift)):
             return False
         g = m.gather.module
-        if not self._same_gather(co.src.gather, g):
+        if isinstance(co.src, Stack) and not self._same_gather(co.src.gather, g):
             return False
+        if isinstance(co.src, RealStack) and (int(co.src.tensor.shape[2]) != int(g.block_size[0]) or g.block_size[0] != g.block_size[1] or g.tile_images is not None):
+            return False          # (a materialised stack — GauGAN's SPADE convs read torch math on the tiles — scatters through g's tile set)
         dst = self.cached(m.original_outputs[m.cache_id], g.num_edits)
-        self._tile_emit(node, co, dst, name=self._module_name(node))
+        self._tile_emit(node, co, dst, name=self._module_name(node), gather=g)
 
         class _G:        # the second gather re-uses the paired gather's geometry with this module's activation
             pass
@@ -1276,6 +1316,9 @@ class Lowering:
         for x, c in ((sa, b), (sb, a)):
             if isinstance(x, Scores) and isinstance(c, (int, float)):
                 self.env[id(out)] = Scores(x.q, x.k, x.scale * float(c))
+                return True
+            if isinstance(x, GScores) and not x.probs and isinstance(c, (int, float)):
+                self.env[id(out)] = GScores(x.q, x.k, x.scale * float(c))
                 return True
         r = self._affine(node, a, b, True)
         if r is None:
@@ -1493,13 +1536,54 @@ class Lowering:
         if isinstance(a, Tok) and a.layout == "bcn" and isinstance(b, Probs) and b.transposed:
             self.env[id(node.outs[0])] = AttnOut(b.s, a.sl)
             return True
+        # generic core: bmm(q, k.permute(0, 2, 1)) [* scale] -> softmax(-1) -> bmm(., v)  ==  one fused attention call
+        qa, kb = node.args[0], node.args[1]
+        if (a is None and isinstance(kb, LazyTensor) and kb.node is not None and kb.node.name in ("permute", "transpose") and self.n_uses(kb) == 1
+                and qa.dim() == 3 and kb.dim() == 3):
+            pn = kb.node
+            dims = tuple(pn.args[1:]) if not isinstance(pn.args[1], (tuple, list)) else tuple(pn.args[1])
+            if (pn.name == "permute" and dims == (0, 2, 1)) or (pn.name == "transpose" and set(int(d) % 3 for d in dims) == {1, 2}):
+                self.env[id(node.outs[0])] = GScores(qa, pn.args[0])
+                return True
+        if a is None and isinstance(qa, LazyTensor) and _is_const(kb) and qa.dim() == 3 and kb.dim() == 3:
+            # cross-attention against CACHED keys (sige_attention.py:35-42): k^T is a constant computed in the dense pass
+            self.env[id(node.outs[0])] = GScores(qa, kb.transpose(1, 2))
+            return True
+        if isinstance(a, GScores) and a.probs and self.n_uses(node.args[0]) == 1 and node.args[1].dim() == 3:
+            return self._emit_sdpa(node, a, node.args[1])
         return False
+
+    def _emit_sdpa(self, node: Node, g: GScores, v: LazyTensor) -> bool:
+        def rt(t):
+            if isinstance(t, LazyTensor):
+                return self.runtime_tensor(t)
+            c = t.detach().to(self.dev).to(self.dtype).contiguous()       # cached keys / values: constants of this step
+            self._keepalive.append(c)
+            return c
+
+        q, k, vv = rt(g.q), rt(g.k), rt(v)
+        o = node.outs[0]
+        if not (q.dtype == k.dtype == vv.dtype and q.dim() == 3):
+            return False
+        out = torch.empty(tuple(o.shape), dtype=q.dtype, device=self.dev)
+        scale = float(g.scale)
+
+        def run(_stream):
+            out.copy_(F.scaled_dot_product_attention(q, k, vv, scale=scale))
+
+        self.steps.append(("eager", run))
+        self.eager_nodes.append("sdpa")
+        self.env[id(o)] = RealT(out)
+        return True
 
     def _h_softmax(self, node: Node):
         a = self._bind(node, ("input", "dim"), {"dim": None})
         v = self.sym(a["input"])
         if isinstance(v, Scores) and a["dim"] in (2, -1) and a.get("dtype") is None:
             self.env[id(node.outs[0])] = Probs(v)
+            return True
+        if isinstance(v, GScores) and not v.probs and a["dim"] in (2, -1) and a.get("dtype") is None and self.n_uses(a["input"]) == 1:
+            self.env[id(node.outs[0])] = GScores(v.q, v.k, v.scale, probs=True)
             return True
         return False
 
