@@ -973,8 +973,8 @@ class Lowering:
                     return half_consts[id(o)]
                 return o
             g = getters[id(o)]
-            if is_module_call and g.dtype != o.dtype:
-                g = g.to(o.dtype)          # an operator module falling back to its eager kernels works in the MODEL's dtype (its caches are)
+            if casts_to_model_dtype and g.dtype != o.dtype:
+                g = g.to(o.dtype)          # an operator module that reads its caches falls back to its eager kernels in the MODEL's dtype
             want = lazy_strides[id(o)]
             if stride_sensitive and g.dim() >= 2 and tuple(g.stride()) != want and g.numel() > 0:
                 # `view` was validated against the model's memory layout (NCHW tensors), the buffers are NHWC
@@ -982,6 +982,7 @@ class Lowering:
             return g
 
         stride_sensitive = is_module_call or node.name in ("view", "view_as", "as_strided")
+        casts_to_model_dtype = is_module_call and node.name not in ("sige.conv", "sige.gather")     # these two read no cache: the step's dtype
         op, module, multi = node.op, node.module, node.multi
         use_autocast = self.dev.type == "cuda" and self.dtype in (torch.float16, torch.bfloat16) and not is_module_call
         dev_type, ac_dtype = self.dev.type, self.dtype
