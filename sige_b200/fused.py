@@ -1569,8 +1569,10 @@ class Lowering:
         out = torch.empty(tuple(o.shape), dtype=q.dtype, device=self.dev)
         scale = float(g.scale)
 
+        q4, k4, v4 = q.unsqueeze(0), k.unsqueeze(0), vv.unsqueeze(0)      # 4-D: with 3-D operands torch falls to its fp32 math path (40x slower)
+
         def run(_stream):
-            out.copy_(F.scaled_dot_product_attention(q, k, vv, scale=scale))
+            out.copy_(F.scaled_dot_product_attention(q4, k4, v4, scale=scale)[0])
 
         self.steps.append(("eager", run))
         self.eager_nodes.append("sdpa")
