@@ -64,11 +64,15 @@ class SIGEConv2d(nn.Conv2d, SIGEModule):
         SIGEModule.__init__(self, call_super=False)
         self._packed = None  # (key, packed weight [taps, Cout, Cin], fp32 bias)
 
-    def _packed_weight(self, dtype: torch.dtype):
-        key = (self.weight.data_ptr(), self.weight._version, dtype, self.weight.device,
+    def _packed_weight(self, dtype: torch.dtype, pad_cin: int = 0):
+        """Packed weights for the tensor-core kernels; ``pad_cin`` > Cin appends zero input channels (exact)."""
+        key = (self.weight.data_ptr(), self.weight._version, dtype, self.weight.device, pad_cin,
                None if self.bias is None else (self.bias.data_ptr(), self.bias._version))
         if self._packed is None or self._packed[0] != key:
-            wp = ops.pack_conv_weight(self.weight, dtype)
+            w = self.weight
+            if pad_cin > w.shape[1]:
+                w = F.pad(w.detach(), (0, 0, 0, 0, 0, pad_cin - w.shape[1]))
+            wp = ops.pack_conv_weight(w, dtype)
             b32 = None if self.bias is None else self.bias.detach().float().contiguous()
             self._packed = (key, wp, b32)
         return self._packed[1], self._packed[2]
@@ -90,6 +94,18 @@ class SIGEConv2d(nn.Conv2d, SIGEModule):
             wp, b32 = self._packed_weight(x.dtype)
             was_nchw = ops.layout_of(x) != ops.NHWC
             out = ops.tile_conv_stack(x, wp, b32, self.kernel_size, self.stride[0])
+            return out.contiguous() if was_nchw else out
+        cin = self.weight.shape[1]
+        if (x.dtype in (torch.float16, torch.bfloat16) and self.groups == 1 and cin % 64 != 0 and cin >= 8
+                and ops.tile_conv_tc_supported(x, self.weight, self.stride, self.dilation, self.groups, ignore_cin=True)):
+            # few-channel inputs on the tensor cores (GauGAN's 36-channel label maps, gaugan/models/sige_normalization.py): zero
+            # channels are appended to the stack and to the weights — exact, and ~15x faster than the CUDA-core kernel
+            cpad = (cin + 63) // 64 * 64
+            wp, b32 = self._packed_weight(x.dtype, pad_cin=cpad)
+            was_nchw = ops.layout_of(x) != ops.NHWC
+            xp = torch.zeros((x.shape[0], cpad, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+            xp[:, :cin].copy_(x)
+            out = ops.tile_conv_stack(xp, wp, b32, self.kernel_size, self.stride[0])
             return out.contiguous() if was_nchw else out
         return ops.tile_conv_generic(x, self.weight, self.bias, self.stride, self.dilation, self.groups)
 

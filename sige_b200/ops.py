@@ -319,7 +319,7 @@ def pack_conv_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def tile_conv_tc_supported(x: torch.Tensor, weight: torch.Tensor, stride, dilation, groups) -> bool:
+def tile_conv_tc_supported(x: torch.Tensor, weight: torch.Tensor, stride, dilation, groups, ignore_cin: bool = False) -> bool:
     """Can the tensor-core kernel take this stack convolution?  (north-star: tensor cores where
     channels >= 64, CUDA-core kernel otherwise.)"""
     return (
@@ -327,7 +327,7 @@ def tile_conv_tc_supported(x: torch.Tensor, weight: torch.Tensor, stride, dilati
         and groups == 1
         and tuple(dilation) == (1, 1)
         and stride[0] == stride[1]
-        and weight.shape[1] % 64 == 0
+        and (ignore_cin or weight.shape[1] % 64 == 0)
         and weight.shape[0] % 8 == 0
         and x.shape[2] >= weight.shape[2] and x.shape[3] >= weight.shape[3]
         and ((x.shape[2] - weight.shape[2]) // stride[0] + 1) * ((x.shape[3] - weight.shape[3]) // stride[1] + 1) <= 128

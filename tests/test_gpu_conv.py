@@ -379,3 +379,27 @@ def test_tc5_fused_shortcut_matches_block_residual_semantics(oracle):
         d.flags = 0                                   # the mma.sync kernel does not implement it: loud error, not a wrong result
         with pytest.raises(Exception, match="tcgen05"):
             ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("cl", [False, True])
+def test_few_channel_stacks_take_the_tensor_cores(oracle, dtype, cl):
+    """SIGEConv2d on a stack whose channel count is not a multiple of 64 (GauGAN's 36-channel label maps,
+    reference gaugan/models/sige_normalization.py): zero channels are appended to stack and weights — exact."""
+    from sige_b200 import ops
+    from sige_b200.nn import SIGEConv2d
+
+    rng = np.random.default_rng(11)
+    for (M, Ci, Co, R, k) in [(37, 36, 128, 6, 3), (16, 8, 64, 4, 1), (9, 100, 72, 6, 3)]:
+        conv = SIGEConv2d(Ci, Co, k, padding=k // 2).to(DEV).to(dtype)
+        conv.set_mode("sparse")
+        x = _round(rng.standard_normal((M, Ci, R, R)).astype(np.float32), dtype)
+        w = conv.weight.detach().float().cpu().numpy()
+        b = conv.bias.detach().float().cpu().numpy()
+        want = oracle.conv2d_tiles(x, w, b, (1, 1))
+        before = ops.launch_count
+        got = conv(T(x, dtype, cl=cl))
+        assert got.shape == want.shape
+        e = rel_err(got, want)
+        assert e <= TOL[dtype], "case %s: rel err %g" % ((M, Ci, Co, R, k), e)
+        assert ops.launch_count - before <= 2, "one weight pack + one tensor-core launch"
