@@ -103,8 +103,9 @@ class SIGEConv2d(nn.Conv2d, SIGEModule):
             cpad = (cin + 63) // 64 * 64
             wp, b32 = self._packed_weight(x.dtype, pad_cin=cpad)
             was_nchw = ops.layout_of(x) != ops.NHWC
-            xp = torch.zeros((x.shape[0], cpad, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+            xp = torch.empty((x.shape[0], cpad, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
             xp[:, :cin].copy_(x)
+            xp[:, cin:].zero_()
             out = ops.tile_conv_stack(xp, wp, b32, self.kernel_size, self.stride[0])
             return out.contiguous() if was_nchw else out
         return ops.tile_conv_generic(x, self.weight, self.bias, self.stride, self.dilation, self.groups)
