@@ -90,6 +90,13 @@ int sige_reduce_mask_capacity(int H, int W, int R, int S, int strideH, int strid
 int sige_gather(const void *x, int dtype, int layout, int B, int C, int H, int W, int R, int S,
                 const int32_t *idx, int N, const sige_bcast_t *scale, const sige_bcast_t *shift,
                 int act, int act_first, void *out, sige_stream_t stream);
+/* The same gather from a source that holds (H/2, W/2) pixels, read through nearest-neighbour x2 up-sampling (up = 1): what
+ * `Gather(F.interpolate(x, scale_factor=2))` produces (reference diffusion/models/ddpm_arch/sige_fused_unet.py:223,
+ * gaugan/models/spade_generators/sige_fused_spade_generator.py:237-249) without materialising the up-sampled tensor.
+ * H, W are the up-sampled extents the tile origins refer to; up = 0 is sige_gather. */
+int sige_gather_upsampled(const void *x, int dtype, int layout, int B, int C, int H, int W, int up, int R, int S,
+                          const int32_t *idx, int N, const sige_bcast_t *scale, const sige_bcast_t *shift,
+                          int act, int act_first, void *out, sige_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* a6: scatter                (reference sige/cuda/scatter_kernel.cu:8-44,76-117) */

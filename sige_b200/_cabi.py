@@ -91,6 +91,7 @@ PROTOTYPES = {
     "sige_reduce_mask": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "sige_reduce_mask_capacity": (_I, [_I] * 8),
     "sige_gather": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _BP, _BP, _I, _I, _P, _P]),
+    "sige_gather_upsampled": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _BP, _BP, _I, _I, _P, _P]),
     "sige_scatter": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _BP, _P]),
     "sige_scatter_with_block_residual": (_I, [_P, _P, _P, _P, _P] + [_I] * 14 + [_P, _I, _P, _I, _P]),
     "sige_get_scatter_map": (_I, [_I] * 10 + [_P, _I, _P, _P]),

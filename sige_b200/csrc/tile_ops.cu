@@ -21,6 +21,7 @@ struct TileGeom {
     int B, C, H, W;  // full tensor extent
     int N;           // tiles per batch element
     int R, S;        // tile extent (of the stack being read or written)
+    int up;          // gather only: 1 = the source holds (H/2, W/2) pixels, read through nearest x2 up-sampling
 };
 
 // ----------------------------------------------------------------------------
@@ -40,7 +41,7 @@ __global__ void gather_nchw_kernel(long long total, TileGeom g, const T *__restr
     const int hh = __ldg(idx + 2 * n) + r, ww = __ldg(idx + 2 * n + 1) + s;
     float z = 0.f;
     if (hh >= 0 && hh < g.H && ww >= 0 && ww < g.W) {
-        z = DT<T>::to_f(x[(((long long)b * g.C + c) * g.H + hh) * g.W + ww]);
+        z = DT<T>::to_f(x[(((long long)b * g.C + c) * (g.H >> g.up) + (hh >> g.up)) * (g.W >> g.up) + (ww >> g.up)]);
         z = affine_act<kFast>(z, scale, shift, act, act_first, b, c, hh, ww);
     }
     out[i] = DT<T>::from_f(z);
@@ -63,7 +64,7 @@ __global__ void gather_nhwc_kernel(long long total, TileGeom g, const T *__restr
     const int c0 = cv * V;
     T res[V];
     if (hh >= 0 && hh < g.H && ww >= 0 && ww < g.W) {
-        const T *src = x + (((long long)b * g.H + hh) * g.W + ww) * g.C + c0;
+        const T *src = x + (((long long)b * (g.H >> g.up) + (hh >> g.up)) * (g.W >> g.up) + (ww >> g.up)) * g.C + c0;
         if (V == DT<T>::vec) {
             *reinterpret_cast<Vec16<T> *>(res) = *reinterpret_cast<const Vec16<T> *>(src);
         } else {
@@ -467,14 +468,21 @@ int sige_reduce_mask(const uint8_t *mask, int H, int W, int R, int S, int stride
 int sige_gather(const void *x, int dtype, int layout, int B, int C, int H, int W, int R, int S, const int32_t *idx,
                 int N, const sige_bcast_t *scale, const sige_bcast_t *shift, int act, int act_first, void *out,
                 sige_stream_t stream) {
+    return sige_gather_upsampled(x, dtype, layout, B, C, H, W, 0, R, S, idx, N, scale, shift, act, act_first, out, stream);
+}
+
+int sige_gather_upsampled(const void *x, int dtype, int layout, int B, int C, int H, int W, int up, int R, int S,
+                          const int32_t *idx, int N, const sige_bcast_t *scale, const sige_bcast_t *shift, int act,
+                          int act_first, void *out, sige_stream_t stream) {
     SIGE_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && R > 0 && S > 0 && N >= 0, "sige_gather: bad shape");
+    SIGE_REQUIRE(up == 0 || (up == 1 && H % 2 == 0 && W % 2 == 0), "sige_gather_upsampled: up must be 0 or 1 (even H, W)");
     SIGE_REQUIRE(layout == SIGE_NCHW || layout == SIGE_NHWC, "sige_gather: bad layout %d", layout);
     SIGE_REQUIRE(act == SIGE_ACT_IDENTITY || act == SIGE_ACT_SWISH, "sige_gather: unknown activation %d", act);
     if (N == 0) return 0;
     SIGE_REQUIRE(x && out && idx, "sige_gather: null pointer");
     Bcast sc, sh;
     if (make_bcast(scale, B, C, H, W, "scale", &sc) || make_bcast(shift, B, C, H, W, "shift", &sh)) return 1;
-    TileGeom g{B, C, H, W, N, R, S};
+    TileGeom g{B, C, H, W, N, R, S, up};
     SIGE_DISPATCH_DTYPE(dtype, return launch_gather<T>(x, layout, g, idx, sc, sh, act, act_first, out,
                                                        (cudaStream_t)stream));
 }
@@ -496,7 +504,7 @@ int sige_scatter(const void *x, const void *y, void *out, int dtype, int layout,
     SIGE_REQUIRE(x && idx, "sige_scatter: null pointer");
     Bcast res;
     if (make_bcast(residual, B, C, H, W, "residual", &res)) return 1;
-    TileGeom g{B, C, H, W, N, Ro, So};
+    TileGeom g{B, C, H, W, N, Ro, So, 0};
     SIGE_DISPATCH_DTYPE(dtype, return launch_scatter<T>(x, out, layout, g, offH, offW, strideH, strideW, idx, res,
                                                         (cudaStream_t)stream));
 }
@@ -520,7 +528,7 @@ int sige_scatter_with_block_residual(const void *x0, const void *y0, const void 
         return 1;
     if (N1 == 0) return 0;
     SIGE_REQUIRE(x1 && idx1, "sige_scatter_with_block_residual: null pointer");
-    TileGeom g{B, C, H, W, N1, R1, S1};
+    TileGeom g{B, C, H, W, N1, R1, S1, 0};
     SIGE_DISPATCH_DTYPE(dtype, return launch_calibrate<T>(x1, y1, out, layout, g, idx1, (cudaStream_t)stream));
 }
 
@@ -552,7 +560,7 @@ int sige_scatter_gather(const void *x, const void *y, int dtype, int layout, int
     SIGE_REQUIRE(x && y && out && idx && scatter_map, "sige_scatter_gather: null pointer");
     Bcast sc, sh;
     if (make_bcast(scale, B, C, H, W, "scale", &sc) || make_bcast(shift, B, C, H, W, "shift", &sh)) return 1;
-    TileGeom g{B, C, H, W, N, R, S};
+    TileGeom g{B, C, H, W, N, R, S, 0};
     SIGE_DISPATCH_DTYPE(dtype, return launch_scatter_gather<T>(x, y, layout, g, Rx, Sx, idx, scatter_map, sc, sh, act,
                                                                act_first, out, (cudaStream_t)stream));
 }

@@ -386,8 +386,8 @@ class CudaExecutor:
 
         return run
 
-    def gather(self, x, block, idx, scale, shift, act, act_first):
-        return self.ops.gather(x, block[0], block[1], idx, scale, shift, act, act_first)
+    def gather(self, x, block, idx, scale, shift, act, act_first, up=0):
+        return self.ops.gather(x, block[0], block[1], idx, scale, shift, act, act_first, up=up)
 
     def launch_counter(self) -> int:
         return self.ops.launch_count
@@ -890,10 +890,15 @@ class Lowering:
         return out
 
     def materialize_stack(self, lt: LazyTensor, st: Stack) -> torch.Tensor:
-        src = self.plain_of_full(st.src)
         g = st.gather
         if getattr(g, "tile_images", None) is not None:
             raise TraceUnsupported("foreign ops on the tile stack of a batch of independent edits")
+        f = st.src
+        up = 0
+        if f.pre is None and f.pad is None and len(f.segs) == 1 and f.segs[0][1] == 1:
+            src, up = f.segs[0][0], 1        # Gather(F.interpolate(x, x2)): read the half-resolution tensor, never materialise the big one
+        else:
+            src = self.plain_of_full(f)
         src.readers.append(None)
         x = src.raw
         idx = g.active_indices.to(self.dev)
@@ -902,7 +907,7 @@ class Lowering:
         ex, scale, shift = self.ex, st.scale, st.shift
 
         def run(_stream):
-            out.copy_(ex.gather(x, g.block_size, idx, scale, shift, g.activation_name, g.activation_first))
+            out.copy_(ex.gather(x, g.block_size, idx, scale, shift, g.activation_name, g.activation_first, up))
 
         self.steps.append(("eager", run))
         self.eager_nodes.append("gather(n%d)" % lt.node.index)

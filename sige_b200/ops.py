@@ -158,11 +158,13 @@ def reduce_mask_cuda(mask: torch.Tensor, block_size, stride, padding) -> torch.T
 # a2: gather                          (reference sige/cuda/gather_kernel.cu:69-124)
 # --------------------------------------------------------------------------------------
 def gather(x, bsize_h: int, bsize_w: int, active_indices, scale=None, shift=None, activation_name: str = "identity",
-           activation_first: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           activation_first: bool = False, out: Optional[torch.Tensor] = None, up: int = 0) -> torch.Tensor:
+    """``up=1``: x holds (H/2, W/2) pixels and is read through nearest x2 up-sampling (tile origins refer to (H, W))."""
     _require_cuda(x, active_indices, scale, shift)
     x, layout = _dense(x)
     idx = _idx(active_indices)
     B, C, H, W = x.shape
+    H, W = H << up, W << up
     N = idx.shape[0]
     if out is None:
         out = _empty_like_layout((B * N, C, bsize_h, bsize_w), x, layout)
@@ -171,8 +173,8 @@ def gather(x, bsize_h: int, bsize_w: int, active_indices, scale=None, shift=None
     sc, sh = _bcast(scale), _bcast(shift)
     with torch.cuda.device(x.device):
         _cabi.check(
-            _cabi.lib().sige_gather(x.data_ptr(), _dt(x), layout, B, C, H, W, bsize_h, bsize_w, idx.data_ptr(), N, _bref(sc),
-                                    _bref(sh), _act(activation_name), int(activation_first), out.data_ptr(), _stream(x)),
+            _cabi.lib().sige_gather_upsampled(x.data_ptr(), _dt(x), layout, B, C, H, W, int(up), bsize_h, bsize_w, idx.data_ptr(), N,
+                                              _bref(sc), _bref(sh), _act(activation_name), int(activation_first), out.data_ptr(), _stream(x)),
             "sige_gather",
         )
     _bump()

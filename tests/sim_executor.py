@@ -170,7 +170,9 @@ class SimExecutor:
 
         return run
 
-    def gather(self, x, block, idx, scale, shift, act, act_first):
+    def gather(self, x, block, idx, scale, shift, act, act_first, up=0):
+        if up:
+            x = F.interpolate(x.float(), scale_factor=2.0, mode="nearest")
         B, C, H, W = x.shape
         z = x.float()
         if not act_first:

@@ -227,3 +227,27 @@ def test_errors_are_loud():
         ops.gather(x, 6, 6, idx, scale=torch.zeros(1, 3, 1, 1, device=DEV))
     with pytest.raises(NotImplementedError):
         ops.gather(x.double(), 6, 6, idx)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("cl", [False, True])
+def test_gather_through_nearest_upsampling(dtype, cl):
+    """sige_gather_upsampled: Gather(F.interpolate(x, scale_factor=2)) read from the half-resolution tensor — bit-identical to
+    gathering the materialised up-sampled tensor (nearest up-sampling copies values)."""
+    from sige_b200 import ops
+
+    rng = np.random.default_rng(21)
+    B, C, h, w = 2, 16, 9, 13
+    x = torch.from_numpy(rng.standard_normal((B, C, h, w)).astype(np.float32)).to(DEV).to(dtype)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    big = torch.nn.functional.interpolate(x, scale_factor=2.0, mode="nearest")
+    if cl:
+        big = big.contiguous(memory_format=torch.channels_last)
+    idx = torch.tensor([[-1, -1], [3, 7], [11, 19], [13, 21], [15, 23]], dtype=torch.int32, device=DEV)
+    scale = torch.from_numpy(rng.standard_normal((1, C, 1, 1)).astype(np.float32)).to(DEV)
+    shift = torch.from_numpy(rng.standard_normal((B, C, 1, 1)).astype(np.float32)).to(DEV)
+    for args in [(None, None, "identity"), (scale, shift, "swish")]:
+        a = ops.gather(x, 6, 6, idx, args[0], args[1], args[2], False, up=1)
+        b = ops.gather(big, 6, 6, idx, args[0], args[1], args[2], False)
+        assert a.shape == b.shape == (B * 5, C, 6, 6) and torch.equal(a, b)
