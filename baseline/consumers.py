@@ -95,7 +95,7 @@ def run_sd(net, downsample_mask, device="cpu", fused=None, size="mini"):
         net.set_mode("sparse")
         if fused is not None:
             fused(net)
-        sparse1 = net(x1, ts, ctx)
+        sparse1 = net(x1, ts, context=ctx)        # keyword argument, as the reference's sampler passes it (ldm/models/diffusion/ddpm.py)
     return full0, sparse1
 
 

@@ -82,6 +82,7 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the reference's own CUDA path (sige.cuda for sm_100a + cuDNN) timed beside ours on GPU 0")
     ap.add_argument("--threads", type=int, default=0, help="(reference arm) torch/OpenMP threads; 0 = sweep")
     ap.add_argument("--_cpu-child", dest="_cpu_child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-tc5", action="store_true", help="engine: use the mma.sync kernel everywhere (default: tcgen05/TMEM/TMA kernel where the geometry allows)")
@@ -513,6 +514,23 @@ def run_ours(args):
 
             roof = {"error": repr(e), "trace": traceback.format_exc()[-1500:]}
         log("roofline done")
+        ref_cuda = None
+        if world == 1 and n_edits == 1 and not args.no_reference_cuda:
+            # the reference's OWN CUDA path on this GPU, same inputs (after our timed regions: the GPU is idle)
+            try:
+                sys.path.insert(0, os.path.join(REPO, "baseline"))
+                import loader
+
+                if loader.available(cuda=True):
+                    r = _reference_child("cuda", args.ratio, 50, 10, 0, 300)
+                    ref_cuda = {"value": r["steps_per_s"], "unit": "steps/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"], "warmup": r["warmup"],
+                                "what": "the reference's unmodified python + sige.cuda (its kernels rebuilt for sm_100a) + cuDNN, fp32 (TF32 convs: torch default), "
+                                        "eager, its Runner.profile protocol (synchronize after every forward)",
+                                "speedup_of_this_line": value / r["steps_per_s"]}
+                else:
+                    ref_cuda = {"unavailable": "baseline/_ref/sige/cuda.so absent"}
+            except Exception as e:  # noqa: BLE001
+                ref_cuda = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cpu = cpu_reference_subprocess(args.ratio, args.cpu_steps, 2)
@@ -537,6 +555,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "reference_cuda": ref_cuda,
         }
         print(json.dumps(line), flush=True)
     if distributed:

@@ -1652,12 +1652,18 @@ class FusedStep:
     ``step(*args)`` copies the tensor arguments into the static inputs, replays the program and returns the static
     output tensor(s) (valid until the next call).  ``replay()`` skips the input copy."""
 
-    def __init__(self, model: nn.Module, *args, use_graph: bool = True, executor=None, dtype: Optional[torch.dtype] = None, **options):
+    def __init__(self, model: nn.Module, *args, use_graph: bool = True, executor=None, dtype: Optional[torch.dtype] = None,
+                 call_kwargs: Optional[Dict[str, Any]] = None, **options):
         """``dtype``: arithmetic / storage type of the fused step (fp16 or bf16).  Defaults to the input's dtype; an fp32
         model (the reference's own precision: its dense pass then stays exactly the reference's) runs its sparse steps on
         the tensor cores with ``dtype=torch.float16`` — activations, caches and weights are converted once at build."""
         if getattr(model, "mode", "sparse") != "sparse":
             raise RuntimeError("FusedStep: run the dense pass, set_masks() and set_mode('sparse') first")
+        call_kwargs = dict(call_kwargs or {})         # keyword arguments of the model call (SD: model(x, t, context=c))
+        self._kw_names = sorted(call_kwargs)
+        kw_values = [call_kwargs[k] for k in self._kw_names]
+        self._n_pos = len(args)
+        args = tuple(args) + tuple(kw_values)
         tensors = [a for a in args if isinstance(a, torch.Tensor)]
         if not tensors:
             raise TraceUnsupported("no tensor argument")
@@ -1684,7 +1690,7 @@ class FusedStep:
         with torch.no_grad(), lazy.tracing() as tape:
             it = iter(lazy.make_input(s, tape, dtype=dt) for s, dt in zip(self.static_inputs, self._arg_dtypes))
             largs = [next(it) if a is None else a for a in self._arg_template]
-            outs = nn.Module.__call__(model, *largs)
+            outs = nn.Module.__call__(model, *largs[:self._n_pos], **dict(zip(self._kw_names, largs[self._n_pos:])))
         self.tape = tape
         with torch.no_grad():
             self.low = Lowering(tape, outs, self.static_inputs, executor, self.dtype, self.dev, module_names=names, **options)
@@ -1731,7 +1737,8 @@ class FusedStep:
             return self.outputs
         return self.run_eager()
 
-    def __call__(self, *args):
+    def __call__(self, *args, **kwargs):
+        args = tuple(args) + tuple(kwargs[k] for k in self._kw_names)
         tensors = [a for a in args if isinstance(a, torch.Tensor)]
         for s, t in zip(self.static_inputs, tensors):
             s.copy_(t, non_blocking=True)

@@ -191,7 +191,7 @@ class SIGEModel(nn.Module):
         self.__dict__.setdefault("_fused_steps", {}).clear()
         return self
 
-    def _fused_lookup(self, args):
+    def _fused_lookup(self, args, kwargs=None):
         d = self.__dict__
         if not d.get("_fused_enabled", False) or d.get("mode") != "sparse" or d.get("_sige_sparse_update", False) or torch.is_grad_enabled():
             return None
@@ -203,7 +203,9 @@ class SIGEModel(nn.Module):
 
         if isinstance(x, lazy.LazyTensor):
             return None
-        sig = tuple((tuple(a.shape), a.dtype, str(a.device)) if isinstance(a, torch.Tensor) else ("v", a) for a in args)
+        kwargs = kwargs or {}
+        flat = list(args) + [("kw", k) for k in sorted(kwargs)] + [kwargs[k] for k in sorted(kwargs)]
+        sig = tuple((tuple(a.shape), a.dtype, str(a.device)) if isinstance(a, torch.Tensor) else ("v", a) for a in flat)
         try:
             hash(sig)
         except TypeError:
@@ -216,7 +218,7 @@ class SIGEModel(nn.Module):
             from ..fused import FusedStep
 
             try:
-                steps[key] = FusedStep(self, *args, **d.get("_fused_options", {}))
+                steps[key] = FusedStep(self, *args, call_kwargs=kwargs, **d.get("_fused_options", {}))
             except lazy.TraceUnsupported as e:
                 import warnings
 
@@ -225,11 +227,11 @@ class SIGEModel(nn.Module):
         return steps[key]
 
     def __call__(self, *args, **kwargs):
-        step = None if kwargs else self._fused_lookup(args)
+        step = self._fused_lookup(args, kwargs)
         if step is None:
             return super().__call__(*args, **kwargs)
         self.__dict__["fused_step"] = step
-        out = step(*args)
+        out = step(*args, **kwargs)
         like = args[0].dtype      # results are fresh tensors in the caller's dtype (the static buffers are reused by the next call)
 
         def fresh(o):
