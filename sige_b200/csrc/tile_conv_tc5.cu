@@ -931,7 +931,9 @@ static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int kspl
     if (pair_fit && ksplit_req <= 0 && ks == 8 && base > 7) ks = 4;
     pl.ksplit = ks;
     static int deep_env = getenv("SIGE_TC5_DEEP") ? atoi(getenv("SIGE_TC5_DEEP")) : 1;   // A/B knob
-    pl.deep = (pl.bn == 64 && taps == 9 && ks > 1 && deep_env) ? 1 : 0;
+    // (2 = also for un-split launches: with the cp.async gather a single halo buffer costs 0.65 us of exposed gather per chunk,
+    //  while two weight stages — 48 KB in flight — cap the weight ring at ~1.5 us per chunk; an A/B knob)
+    pl.deep = (pl.bn == 64 && taps == 9 && deep_env && (ks > 1 || deep_env >= 2)) ? 1 : 0;
     return pl;
 }
 

@@ -219,10 +219,15 @@ class SIGEModel(nn.Module):
 
             try:
                 steps[key] = FusedStep(self, *args, call_kwargs=kwargs, **d.get("_fused_options", {}))
-            except lazy.TraceUnsupported as e:
+            except Exception as e:  # noqa: BLE001
+                # TraceUnsupported = the forward needs tensor VALUES at trace time; anything else = a pattern the lowering
+                # mishandled.  Either way the model must keep working: loud warning, eager operator modules from here on
+                # (SIGE_FUSED_STRICT=1 re-raises: the test-suite runs that way).
+                if os.environ.get("SIGE_FUSED_STRICT", "0") == "1" and not isinstance(e, lazy.TraceUnsupported):
+                    raise
                 import warnings
 
-                warnings.warn("sige: this forward cannot run as a fused step (%s); using the eager operator modules" % (e,))
+                warnings.warn("sige: this forward does not run as a fused step (%s: %s); using the eager operator modules" % (type(e).__name__, e))
                 steps[key] = None
         return steps[key]
 

@@ -9,6 +9,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("SIGE_FUSED_STRICT", "1")      # a lowering bug must fail a test, not fall back silently
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
