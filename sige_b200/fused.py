@@ -64,6 +64,7 @@ class Buf:
         self.producers: List = []                             # objects with .can_aux() / .add_aux(view, scale, shift, act)
         self.readers: List = []                               # (idx, block, up) of fused launches reading it; None = a dense read
         self.views: Dict = {}
+        self.view_inits: List = []                            # (view, scale, shift, act) of the views initialised from the cache
 
     @property
     def raw(self) -> torch.Tensor:
@@ -78,6 +79,16 @@ class Buf:
     def has_raw(self) -> bool:
         return self._raw is not None
 
+    def restore(self) -> None:
+        """Back to the cached original values (a new edit starts from them): raw copy and every transformed view."""
+        if self.cached_init is None:
+            return
+        if self._raw is not None:
+            c = self.cached_init.to(self._raw.device)
+            self._raw.copy_(c if c.shape[0] == self.shape[0] else c.expand(self.shape[0], *c.shape[1:]))
+        for (v, sc, sh, act) in self.view_inits:
+            self.owner.init_view(v, self.cached_init, sc, sh, act)
+
 
 class ConvSpec:
     """Everything one fused gather->conv->scatter launch needs, as tensors (the executor turns it into a descriptor)."""
@@ -90,6 +101,7 @@ class ConvSpec:
         self.H = self.W = 0
         self.idx: Optional[torch.Tensor] = None
         self.tile_img: Optional[torch.Tensor] = None         # int32 [N]: a batch of independent edits (idx = concatenated lists)
+        self.slot: Optional["IdxSlot"] = None                # fixed-capacity index buffer (N = capacity, slot.n tiles are real)
         self.N = 0
         self.block = 0
         self.scale: Optional[torch.Tensor] = None            # fp32 [Cin] or [B, Cin]
@@ -148,7 +160,10 @@ class FusedConv:
     # ---- accounting (algorithmic bytes / flops of one fused launch)
     @property
     def tiles(self) -> int:
-        return self.spec.N if self.spec.tile_img is not None else self.spec.B * self.spec.N
+        s = self.spec
+        if s.tile_img is not None:
+            return s.N
+        return s.B * (s.slot.n if s.slot is not None else s.N)
 
     @property
     def out_elems(self) -> int:
@@ -175,6 +190,34 @@ class FusedConv:
         if s.shortcut is not None:
             f += 2 * self.tiles * ro * ro * s.Cout * int(s.shortcut[1].shape[1])
         return f
+
+
+class IdxSlot:
+    """A tile list with a fixed capacity: the launches hold this buffer's address and N = capacity; entries beyond the current
+    count are SIGE_TILE_NONE origins (such a tile reads zeros and writes nothing, include/sige_b200.h).  A new mask whose lists
+    fit is installed by rewriting the buffers in place (`FusedStep.rebind`): no re-trace, no re-capture."""
+
+    def __init__(self, gather, dev):
+        from ._cabi import TILE_NONE
+
+        self.gather = gather
+        idx = gather.active_indices.to(dev)
+        self.n = int(idx.shape[0])
+        self.cap = max(8, (self.n + 7) // 8 * 8)
+        self.buf = torch.full((self.cap, 2), TILE_NONE, dtype=torch.int32, device=dev)
+        self.buf[:self.n] = idx
+        self.none = TILE_NONE
+
+    def fits(self) -> bool:
+        g = self.gather
+        return getattr(g, "tile_images", None) is None and g.active_indices is not None and int(g.active_indices.shape[0]) <= self.cap \
+            and int(g.active_indices.shape[0]) > 0
+
+    def reload(self) -> None:
+        idx = self.gather.active_indices.to(self.buf.device)
+        self.n = int(idx.shape[0])
+        self.buf[:self.n] = idx
+        self.buf[self.n:] = self.none
 
 
 class ConvInRec:
@@ -539,6 +582,9 @@ class Lowering:
         self.fused: List[FusedConv] = []
         self.conv_ins: List[ConvInRec] = []
         self.eager_nodes: List[str] = []
+        self.slots: Dict[int, IdxSlot] = {}
+        self.flag_recipes: List = []       # (flags buffer, main slot, off, shortcut slot, soff) of fused shortcuts
+        self.cached_bufs: List[Buf] = []
         self.view_nodes = 0              # view ops resolved at build time (no run-time work)
         self._all_idx: Dict = {}
         self._vecs: Dict = {}
@@ -573,7 +619,9 @@ class Lowering:
         """A buffer initialised from a module cache; only active tiles are rewritten per step.  The program owns a
         copy (the module's cache stays pristine).  `batch`: number of independent edits sharing the cache."""
         shape = tuple(cache.shape) if batch is None else (batch, *cache.shape[1:])
-        return Buf(self, shape, cached_init=cache.detach())
+        b = Buf(self, shape, cached_init=cache.detach())
+        self.cached_bufs.append(b)
+        return b
 
     def vec(self, v: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         """fp32 contiguous copy of a per-channel vector (kept alive; one copy per distinct source)."""
@@ -624,20 +672,31 @@ class Lowering:
         sh = None if shift is None else shift.contiguous()
         v = self.empty(b, c, h, w)
         if buf.cached_init is not None:
-            z = buf.cached_init.to(self.dev).float()
-            if sc is not None:
-                z = z * sc.view(1, -1, 1, 1)
-            if sh is not None:
-                z = z + sh.view(1, -1, 1, 1)
-            if act == "swish":
-                z = z * torch.sigmoid(z)
-            v.copy_(z)
+            self.init_view(v, buf.cached_init, sc, sh, act)
+            buf.view_inits.append((v, sc, sh, act))
         else:
             v.zero_()
         for pr in buf.producers:
             pr.add_aux(v, sc, sh, act)
         buf.views[key] = (v, sc, sh)
         return v
+
+    def init_view(self, v: torch.Tensor, cached: torch.Tensor, sc, sh, act: str) -> None:
+        z = cached.to(self.dev).float()
+        if sc is not None:
+            z = z * sc.view(1, -1, 1, 1)
+        if sh is not None:
+            z = z + sh.view(1, -1, 1, 1)
+        if act == "swish":
+            z = z * torch.sigmoid(z)
+        v.copy_(z)
+
+    def slot(self, g) -> "IdxSlot":
+        """The fixed-capacity index buffer of Gather `g`'s tile list (one per distinct list)."""
+        key = id(g.active_indices)
+        if key not in self.slots:
+            self.slots[key] = IdxSlot(getattr(g, "real", g), self.dev)       # (a ScatterGather's geometry stub points at the real Gather)
+        return self.slots[key]
 
     # ------------------------------------------------------------------ emission of one fused launch
     def emit_conv(self, name: str, segs: Sequence[Tuple[Buf, int]], pre: Optional[Pre], hw: Tuple[int, int], idx: torch.Tensor, block: int,
@@ -670,6 +729,7 @@ class Lowering:
         s.k, s.stride, s.off, s.block = int(weight.shape[2]), stride, off, block
         s.B, s.H, s.W = B, hw[0], hw[1]
         s.idx, s.N, s.tile_img = idx, n, tile_img
+        s.slot = next((sl for sl in self.slots.values() if sl.buf is idx), None)
         s.pdl, s.tc5, s.ksplit = self.pdl, self.tc5, self.ksplit
         if stack_src is not None:
             s.src_is_stack = True
@@ -795,8 +855,9 @@ class Lowering:
     def _per_sample(pre: Pre) -> bool:
         return (pre.scale is not None and pre.scale.dim() == 2) or (pre.shift is not None and pre.shift.dim() == 2)
 
-    def tile_conv_args(self, co: ConvOut):
-        """(segs, pre, hw, idx, block, off, stack_src, tile_img) of a conv on tiles."""
+    def tile_conv_args(self, co: ConvOut, exact: bool = False):
+        """(segs, pre, hw, idx, block, off, stack_src, tile_img) of a conv on tiles.  `exact`: the launch's output stays a tile
+        stack that recorded torch calls consume — its row count must be the real tile count, not a padded capacity."""
         st = co.src
         if isinstance(st, RealStack):
             t = st.tensor
@@ -806,7 +867,11 @@ class Lowering:
         if st.scale is not None or st.shift is not None or g.activation_name != "identity":
             pre = Pre(self._chan_vec(st.scale, st.src), self._chan_vec(st.shift, st.src), None if g.activation_name == "identity" else g.activation_name)
         timg = getattr(g, "tile_images", None)
-        return (st.src.segs, pre, st.src.HW, g.active_indices.to(self.dev), int(g.block_size[0]), int(g.offset[0]), None,
+        if timg is None and int(g.active_indices.shape[0]) > 0 and not exact:
+            idx = self.slot(g).buf            # fixed capacity, padded with SIGE_TILE_NONE (see IdxSlot)
+        else:
+            idx = g.active_indices.to(self.dev)
+        return (st.src.segs, pre, st.src.HW, idx, int(g.block_size[0]), int(g.offset[0]), None,
                 None if timg is None else timg.to(self.dev))
 
     def _chan_vec(self, t: Optional[torch.Tensor], f: Full) -> Optional[torch.Tensor]:
@@ -922,7 +987,7 @@ class Lowering:
 
     def force_stack(self, lt: LazyTensor, co: ConvOut) -> torch.Tensor:
         """Emit a conv on tiles whose result stays a stack (a foreign op consumes it)."""
-        segs, pre, hw, idx, block, off, stack_src, timg = self.tile_conv_args(co)
+        segs, pre, hw, idx, block, off, stack_src, timg = self.tile_conv_args(co, exact=True)
         if timg is not None:
             raise TraceUnsupported("foreign ops on the tile stack of a batch of independent edits")
         n = int(idx.shape[0]) if idx is not None else int(stack_src.shape[0])
@@ -1219,6 +1284,7 @@ class Lowering:
 
         g2 = _G()
         g2.active_indices, g2.block_size, g2.offset, g2.tile_images = g.active_indices, g.block_size, g.offset, g.tile_images
+        g2.real = g
         g2.activation_name, g2.activation_first = m.activation_name, m.activation_first
         self.env[id(node.outs[0])] = Stack(Full([(dst, 0)]), g2, scale, shift)
         return True
@@ -1259,6 +1325,12 @@ class Lowering:
         name = self._module_name(node)
         if fuse:
             flags = torch.isin(main_key, sc_key).to(torch.uint8).contiguous()
+            if mg.tile_images is None:          # fixed-capacity form (IdxSlot): padded entries carry flag 0
+                ms, ss = self.slot(mg), self.slot(sg)
+                fbuf = torch.zeros((ms.cap,), dtype=torch.uint8, device=self.dev)
+                fbuf[:ms.n] = flags
+                self.flag_recipes.append((fbuf, ms, off, ss, soff))
+                flags = fbuf
             shortcut = ([b for b, _ in sc_full.segs], sc.weight, sc.bias, flags)
             self._tile_emit(node, co, dst, residual=skip, shortcut=shortcut, name=name)
         else:
@@ -1736,6 +1808,32 @@ class FusedStep:
             self.graph.replay()
             return self.outputs
         return self.run_eager()
+
+    def rebind(self) -> bool:
+        """Install the model's CURRENT tile lists (after a new ``set_masks``) into this compiled step without re-tracing or
+        re-capturing: possible when every list fits the capacity it was built with and nothing outside the fused launches
+        holds a tile list (no eager operator-module fallbacks, no batch of edits).  Index buffers and shortcut flags are
+        rewritten in place and every cached buffer goes back to the original activations; the CUDA graph stays valid."""
+        low = self.low
+        if any(n.startswith(("sige.", "gather(")) for n in self.eager_nodes) or not low.slots:
+            return False
+        if not all(sl.fits() for sl in low.slots.values()):
+            return False
+        with torch.no_grad():
+            for sl in low.slots.values():
+                sl.reload()
+            width = 1 << 16
+            for (fbuf, ms, off, ss, soff) in low.flag_recipes:
+                mi, si = ms.buf[:ms.n].long(), ss.buf[:ss.n].long()
+                main_key = (mi[:, 0] + off) * width + (mi[:, 1] + off)
+                sc_key = (si[:, 0] + soff) * width + (si[:, 1] + soff)
+                if not bool(torch.isin(sc_key, main_key).all()):
+                    return False            # the shortcut's tiles left the main conv's grid: a different program
+                fbuf.zero_()
+                fbuf[:ms.n] = torch.isin(main_key, sc_key).to(torch.uint8)
+            for b in low.cached_bufs:
+                b.restore()
+        return True
 
     def __call__(self, *args, **kwargs):
         args = tuple(args) + tuple(kwargs[k] for k in self._kw_names)

@@ -213,6 +213,13 @@ class SIGEModel(nn.Module):
         key = (d.get("timestamp", 0), _cache_generation[0], d.get("_sige_cache_id", 0), sig)
         steps = d.setdefault("_fused_steps", {})
         if key not in steps:
+            # same caches, same arguments, NEW masks: try to install the new tile lists into the compiled step in place
+            for k in [k for k in steps if k[1:] == key[1:] and k[0] != key[0]]:
+                st = steps.pop(k)
+                if st is not None and st.rebind():
+                    steps[key] = st
+                    break
+        if key not in steps:
             for k in [k for k in steps if k[0] != key[0] or k[1] != key[1]]:
                 del steps[k]           # older masks / older caches: their buffers are garbage now
             from ..fused import FusedStep

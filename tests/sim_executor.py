@@ -70,6 +70,10 @@ class SimExecutor:
                 else:
                     for bi in range(B):
                         for (iy, ix) in idx:
+                            if iy <= -20000:          # SIGE_TILE_NONE padding of a fixed-capacity list: reads zeros, writes nothing
+                                tiles.append(torch.zeros_like(padded[0, :, :R, :R]))
+                                coords.append(None)
+                                continue
                             tiles.append(padded[bi, :, iy + P:iy + P + R, ix + P:ix + P + R])
                             coords.append((bi, iy, ix))
                 X = torch.stack(tiles)
@@ -82,7 +86,10 @@ class SimExecutor:
                 raw = torch.cat([t.float() for t in sc_tensors], 1)
                 flags = [1] * s.N if sc_flags is None else sc_flags.tolist()
                 assert k == 3 and R == 6 and st == 1
-                for m, (bi, iy, ix) in enumerate(coords):
+                for m, co_ in enumerate(coords):
+                    if co_ is None:
+                        continue
+                    bi, iy, ix = co_
                     if flags[m % s.N]:
                         fresh[m] = True
                         Pp = 8
@@ -97,6 +104,8 @@ class SimExecutor:
             Bd, Cd, Hd, Wd = dst.shape
             res = None if s.residual is None else s.residual.float()
             for m in range(M):
+                if coords is not None and coords[m] is None:
+                    continue
                 bi, iy, ix = coords[m] if coords is not None else (0, 0, 0)
                 assert (s.off + iy) >= 0 and (s.off + ix) >= 0
                 oy, ox = (s.off + iy) // st, (s.off + ix) // st
@@ -132,6 +141,8 @@ class SimExecutor:
             else:
                 imgs = [None] * rec.tiles.shape[0] if rec.tile_img is None else rec.tile_img.tolist()
                 for bi, (iy, ix) in zip(imgs, rec.tiles.tolist()):
+                    if iy <= -20000:
+                        continue
                     sel[slice(None) if bi is None else bi, max(iy, 0):max(iy + rec.tile_size, 0), max(ix, 0):max(ix + rec.tile_size, 0)] = True
             sel4 = sel[:, None].expand_as(y)
             if rec.out.has_raw:

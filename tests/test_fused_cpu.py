@@ -206,3 +206,40 @@ def test_batch_of_independent_edits_equals_one_edit_at_a_time():
     with pytest.raises((NotImplementedError, RuntimeError)):
         with torch.no_grad():
             model(xb, t)
+
+
+def test_new_masks_are_installed_without_recompiling():
+    """A later edit with its own mask re-uses the compiled step: `set_masks` + the next call rewrite the fixed-capacity index
+    buffers (padded with SIGE_TILE_NONE), the shortcut flags and restore the cached buffers — same result as a fresh build."""
+    from sige.utils import downsample_mask
+    from sige_b200.fused import FusedStep
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
+    from sim_executor import SimExecutor
+
+    cfg = DDPMConfig.small()
+    model, x_a, t = _prepared("reference", cfg, 0.05)
+    x0, _, _, _ = synthetic_inputs(cfg, 0.05, seed=0)
+    with torch.no_grad():
+        step = FusedStep(model, x_a, t, executor=SimExecutor())
+        out_a = step.output.clone()
+        n_before = {k: sl.n for k, sl in step.low.slots.items()}
+        # edit B: a smaller mask elsewhere in the image (every tile list fits the capacities of edit A)
+        _, x_b, mask_b, _ = synthetic_inputs(cfg, 0.03, seed=0, edit_seed=5)
+        mask_b = torch.roll(mask_b, (9, -11), (0, 1))
+        x_b = x0 + torch.roll(x_b - x0, (9, -11), (2, 3))
+        model.set_masks(downsample_mask(mask_b, min_res=8))
+        assert step.rebind(), "the new tile lists fit: no recompilation"
+        assert {k: sl.n for k, sl in step.low.slots.items()} != n_before
+        out_b = step(x_b, t).clone()
+        fresh = FusedStep(model, x_b, t, executor=SimExecutor()).output
+        assert torch.allclose(out_b, fresh, atol=2e-5), float((out_b - fresh).abs().max())
+        assert float((out_b - out_a).abs().max()) > 1e-2
+        # back to edit A: identical to the first result (buffers fully restored)
+        _, _, mask_a, _ = synthetic_inputs(cfg, 0.05, seed=0)
+        model.set_masks(downsample_mask(mask_a, min_res=8))
+        assert step.rebind()
+        assert torch.allclose(step(x_a, t), out_a, atol=1e-6)
+        # a larger mask does not fit: the caller recompiles
+        _, _, mask_c, _ = synthetic_inputs(cfg, 0.20, seed=0)
+        model.set_masks(downsample_mask(mask_c, min_res=8))
+        assert not step.rebind()

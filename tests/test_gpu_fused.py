@@ -331,3 +331,35 @@ def test_resblock_entry_point_equals_its_two_launches():
     # a conv2 that does not read conv1's output is refused
     other = by_name["down.1.block.0.scatter"]
     assert _cabi.lib().sige_resblock(ctypes.byref(c1.desc), ctypes.byref(other.desc), stream) != 0
+
+
+def test_next_edit_reuses_the_compiled_step():
+    """Interactive editing: a NEW mask whose tile lists fit the capacities of the compiled step is installed in place
+    (index buffers padded with SIGE_TILE_NONE, shortcut flags, cached buffers restored) — no re-trace, no re-capture."""
+    import time
+
+    from sige.utils import downsample_mask
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
+
+    cfg = DDPMConfig()
+    model, x_a, t = _prepared("reference", cfg, 0.012, torch.float32)
+    x0, _, _, _ = synthetic_inputs(cfg, 0.012, seed=0)
+    with torch.no_grad():
+        out_a = model(x_a, t)
+        step = model.fused_step
+        _, x_b, mask_b, _ = synthetic_inputs(cfg, 0.010, seed=0, edit_seed=3)
+        mask_b = torch.roll(mask_b, (-60, 44), (0, 1))
+        x_b = (x0 + torch.roll(x_b - x0, (-60, 44), (2, 3))).to(DEV)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.set_masks(downsample_mask(mask_b.to(DEV), min_res=8))
+        out_b = model(x_b, t)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert model.fused_step is step, "the second edit must re-use the compiled step"
+        model.set_fused(False)
+        want_b = model(x_b, t)
+        model.set_fused(True, dtype=torch.float16)
+    e = float((out_b - want_b).abs().max() / want_b.abs().max())
+    print("second edit: set_masks + first step %.1f ms (no recompilation), fused-vs-eager %.3g" % (1e3 * dt, e))
+    assert e <= TOL_MAX and float((out_b - out_a).abs().max()) > 1e-2
