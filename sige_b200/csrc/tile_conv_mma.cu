@@ -139,6 +139,8 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
     const int warp_m = warp / WARPS_N, warp_n = warp % WARPS_N;
     const int tile0 = blockIdx.x * p.tpc;          // first tile of this CTA
     const int n0 = blockIdx.y * BN;                // first output channel of this CTA
+    // fixed-capacity tile lists: a CTA whose first tile is SIGE_TILE_NONE padding has nothing to do (see tile_conv_tc5.cu)
+    if (p.NT == p.N && p.idx != nullptr && !p.src_is_stack && !p.dst_is_stack && __ldg(p.idx + 2 * tile0) <= SIGE_TILE_NONE) return;
     const int ntile = min(p.tpc, p.NT - tile0);    // tiles actually present
     const int NC = p.Cin / KC;                     // K chunks
     const int J = NC * p.taps;                     // (chunk, tap) steps of the whole K loop

@@ -313,6 +313,9 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile0 = blockIdx.x * TILES;
+    // fixed-capacity tile lists (one image): real tiles are packed at the front, the rest are SIGE_TILE_NONE.  A CTA (and with it
+    // its whole split-K cluster: same tile0) whose first tile is padding has nothing to read or write.
+    if (p.NT == p.N && p.idx != nullptr && !p.src_is_stack && !p.dst_is_stack && __ldg(p.idx + 2 * tile0) <= SIGE_TILE_NONE) return;
     const int n0 = blockIdx.y * BN;
     const int ntile = min(TILES, p.NT - tile0);
     const int NC = p.Cin / KC;

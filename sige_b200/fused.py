@@ -197,13 +197,13 @@ class IdxSlot:
     count are SIGE_TILE_NONE origins (such a tile reads zeros and writes nothing, include/sige_b200.h).  A new mask whose lists
     fit is installed by rewriting the buffers in place (`FusedStep.rebind`): no re-trace, no re-capture."""
 
-    def __init__(self, gather, dev):
+    def __init__(self, gather, dev, headroom: float = 0.0):
         from ._cabi import TILE_NONE
 
         self.gather = gather
         idx = gather.active_indices.to(dev)
         self.n = int(idx.shape[0])
-        self.cap = max(8, (self.n + 7) // 8 * 8)
+        self.cap = max(8, (int(math.ceil(self.n * (1.0 + headroom))) + 7) // 8 * 8)
         self.buf = torch.full((self.cap, 2), TILE_NONE, dtype=torch.int32, device=dev)
         self.buf[:self.n] = idx
         self.none = TILE_NONE
@@ -573,8 +573,12 @@ def _pair(v) -> Tuple[int, int]:
 class Lowering:
     def __init__(self, tape: lazy.Tape, outputs, static_inputs: Sequence[torch.Tensor], executor, dtype: torch.dtype, device,
                  pdl: bool = True, tc5: bool = True, producer_preop: bool = True, fuse_shortcut: bool = True,
-                 fused_attention: bool = True, sparse_stem: bool = True, ksplit: int = 0, module_names: Optional[Dict[int, str]] = None):
+                 fused_attention: bool = True, sparse_stem: bool = True, ksplit: int = 0, module_names: Optional[Dict[int, str]] = None,
+                 headroom: float = 0.0):
+        """headroom: extra capacity of the tile-list buffers (0.25 = a later mask may have 25 % more tiles per list and still be
+        installed in place by `FusedStep.rebind`; CTAs made only of padding exit at once)."""
         self.tape, self.ex, self.dtype, self.dev = tape, executor, dtype, device
+        self.headroom = float(headroom)
         self.module_names = module_names or {}
         self.pdl, self.tc5, self.producer_preop, self.fuse_shortcut = pdl, tc5, producer_preop, fuse_shortcut
         self.fused_attention, self.sparse_stem, self.ksplit = fused_attention, sparse_stem, ksplit
@@ -695,7 +699,7 @@ class Lowering:
         """The fixed-capacity index buffer of Gather `g`'s tile list (one per distinct list)."""
         key = id(g.active_indices)
         if key not in self.slots:
-            self.slots[key] = IdxSlot(getattr(g, "real", g), self.dev)       # (a ScatterGather's geometry stub points at the real Gather)
+            self.slots[key] = IdxSlot(getattr(g, "real", g), self.dev, self.headroom)       # (a ScatterGather's geometry stub points at the real Gather)
         return self.slots[key]
 
     # ------------------------------------------------------------------ emission of one fused launch
