@@ -232,6 +232,10 @@ typedef struct {
 /* Use the tcgen05 / TMEM / TMA kernel when the geometry allows (3x3 s1 on 6x6 tiles, 1x1 on 4x4 tiles,
  * Cout % 64 == 0); otherwise the mma.sync kernel runs. */
 #define SIGE_CONV_TC5 2
+/* `idx` is a fixed-capacity list (B == 1): real tiles packed at the front, SIGE_TILE_NONE entries behind them, possibly whole
+ * CTAs' worth — CTAs made only of padding exit at once.  (Without the flag padding entries are still harmless: they read zeros
+ * and write nothing; the flag only buys the early exit, at the price of one index load on every CTA's prologue.) */
+#define SIGE_CONV_PADDED 4
 /* Origin of a padding entry of a per-image tile list (both coordinates). */
 #define SIGE_TILE_NONE (-30000)
 

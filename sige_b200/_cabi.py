@@ -22,6 +22,7 @@ NCHW, NHWC = 0, 1
 ACT_IDENTITY, ACT_SWISH = 0, 1
 CONV_PDL = 1
 CONV_TC5 = 2
+CONV_PADDED = 4
 TILE_NONE = -30000
 
 

@@ -53,6 +53,7 @@ struct ConvParams {
     int src_is_stack;
     const int32_t *idx;
     int N, NT;              // tiles per batch element, total tiles (B*N)
+    int padded;             // SIGE_CONV_PADDED (B == 1): whole CTAs of padding may follow the real tiles
     int idx_per_image;      // 1: idx holds B*N entries (row b*N + i = tile i of image b), else N shared by all images
     int R, S, RS;
     const float *scale, *shift;
@@ -140,7 +141,7 @@ tile_conv_mma_kernel(const __grid_constant__ ConvParams p) {
     const int tile0 = blockIdx.x * p.tpc;          // first tile of this CTA
     const int n0 = blockIdx.y * BN;                // first output channel of this CTA
     // fixed-capacity tile lists: a CTA whose first tile is SIGE_TILE_NONE padding has nothing to do (see tile_conv_tc5.cu)
-    if (p.NT == p.N && p.idx != nullptr && !p.src_is_stack && !p.dst_is_stack && __ldg(p.idx + 2 * tile0) <= SIGE_TILE_NONE) return;
+    if (p.padded && __ldg(p.idx + 2 * tile0) <= SIGE_TILE_NONE) return;
     const int ntile = min(p.tpc, p.NT - tile0);    // tiles actually present
     const int NC = p.Cin / KC;                     // K chunks
     const int J = NC * p.taps;                     // (chunk, tap) steps of the whole K loop
@@ -583,6 +584,7 @@ extern "C" int sige_tile_conv(const sige_tile_conv_t *a, sige_stream_t stream) {
     p.N = a->N;
     p.NT = a->B * a->N;
     p.idx_per_image = a->idx_per_image ? 1 : 0;
+    p.padded = ((a->flags & SIGE_CONV_PADDED) && a->B == 1 && a->idx && !a->src_is_stack && !a->dst_is_stack) ? 1 : 0;
     p.R = a->R; p.S = a->S; p.RS = a->R * a->S;
     p.scale = a->scale; p.shift = a->shift; p.affine_bstride = a->affine_bstride; p.act = a->act;
     p.w = a->w_packed; p.bias = a->bias;

@@ -81,6 +81,7 @@ struct Params {
     int C0_2, Cin2;
     const float *bias2;
     const unsigned char *sc_flags;
+    int padded;                // SIGE_CONV_PADDED: whole CTAs of SIGE_TILE_NONE padding may follow the real tiles (B == 1)
     int idx_per_image;         // 1: idx / sc_flags hold B*N entries (row b*N + i = tile i of image b), else N shared by all images
     int ksplit;
     int pdl;
@@ -315,7 +316,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     const int tile0 = blockIdx.x * TILES;
     // fixed-capacity tile lists (one image): real tiles are packed at the front, the rest are SIGE_TILE_NONE.  A CTA (and with it
     // its whole split-K cluster: same tile0) whose first tile is padding has nothing to read or write.
-    if (p.NT == p.N && p.idx != nullptr && !p.src_is_stack && !p.dst_is_stack && __ldg(p.idx + 2 * tile0) <= SIGE_TILE_NONE) return;
+    if (p.padded && __ldg(p.idx + 2 * tile0) <= SIGE_TILE_NONE) return;
     const int n0 = blockIdx.y * BN;
     const int ntile = min(TILES, p.NT - tile0);
     const int NC = p.Cin / KC;
@@ -1075,6 +1076,7 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.bias2 = a->n_src2 > 0 ? a->bias2 : nullptr;
     p.sc_flags = a->n_src2 > 0 ? a->sc_flags : nullptr;
     p.idx_per_image = a->idx_per_image ? 1 : 0;
+    p.padded = ((a->flags & SIGE_CONV_PADDED) && a->B == 1 && a->idx && !a->src_is_stack && !a->dst_is_stack) ? 1 : 0;
     p.ksplit = a->ksplit;
     static int trig_env = getenv("SIGE_TC5_LATE_TRIGGER") ? atoi(getenv("SIGE_TC5_LATE_TRIGGER")) : 1;     // A/B knob
     p.pdl = (a->flags & SIGE_CONV_PDL) ? (trig_env ? 2 : 1) : 0;

@@ -298,7 +298,7 @@ class CudaExecutor:
 
     def prepare_conv(self, fc: FusedConv) -> None:
         ops = self.ops
-        from ._cabi import CONV_PDL, CONV_TC5
+        from ._cabi import CONV_PADDED, CONV_PDL, CONV_TC5
 
         s = fc.spec
         w, b = s.weight, s.bias
@@ -350,6 +350,8 @@ class CudaExecutor:
             d.residual, d.rC, d.res_c0 = None, 0, 0
         d.ksplit = s.ksplit
         d.flags = (CONV_PDL if s.pdl else 0) | (CONV_TC5 if s.tc5 else 0)
+        if s.slot is not None and s.tile_img is None and s.B == 1 and s.slot.cap - s.slot.n >= 8:
+            d.flags |= CONV_PADDED          # whole CTAs of padding exist (capacity headroom): let them exit at once
         d.n_aux = len(s.aux)
         keep = [wp, b32]
         for i, (view, sc, sh, act) in enumerate(s.aux):

@@ -363,3 +363,26 @@ def test_next_edit_reuses_the_compiled_step():
     e = float((out_b - want_b).abs().max() / want_b.abs().max())
     print("second edit: set_masks + first step %.1f ms (no recompilation), fused-vs-eager %.3g" % (1e3 * dt, e))
     assert e <= TOL_MAX and float((out_b - out_a).abs().max()) > 1e-2
+
+
+def test_capacity_headroom_lets_a_larger_mask_in():
+    """set_fused(headroom=0.5): tile-list buffers 50 % larger than needed — a later, LARGER edit still re-uses the compiled step;
+    CTAs made only of SIGE_TILE_NONE padding exit at once (SIGE_CONV_PADDED)."""
+    from sige.utils import downsample_mask
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
+
+    cfg = DDPMConfig.small()
+    model, x_a, t = _prepared("intree", cfg, 0.04, torch.float16)
+    model.set_fused(True, headroom=0.6)
+    x0, _, _, _ = synthetic_inputs(cfg, 0.04, seed=0)
+    with torch.no_grad():
+        model(x_a, t)
+        step = model.fused_step
+        assert any(sl.cap - sl.n >= 8 for sl in step.low.slots.values())
+        _, x_b, mask_b, _ = synthetic_inputs(cfg, 0.055, seed=0, edit_seed=2)       # more tiles than edit A
+        model.set_masks(downsample_mask(mask_b.to(DEV), min_res=8))
+        out_b = model(x_b.to(DEV).half(), t)
+        assert model.fused_step is step
+        model.set_fused(False)
+        want = model(x_b.to(DEV).half(), t)
+    assert float((out_b - want).abs().max() / want.abs().max()) <= TOL_MAX
