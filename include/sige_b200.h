@@ -304,6 +304,29 @@ int sige_attention_tokens_supported(int N, int C, int dtype);
 int sige_attention_tokens(const void *qkv, void *out, int B, int N, int C, int dtype, int flags,
                           sige_stream_t stream);
 
+/* Multi-head attention core for SPARSE queries (Stable Diffusion's transformer blocks in sparse mode): the reference's
+ * torch.bmm(q, k^T) * scale -> softmax(-1) -> torch.bmm(., v) of stable-diffusion/ldm/modules/attention.py:81-93 (attn1: queries =
+ * tokens of the active tiles, keys / values = all tokens of the scattered tensor, sige_attention.py:79,153-160) and
+ * sige_attention.py:44-58 (attn2: the same queries against the text keys / values cached by the dense pass), as one launch;
+ * the [Nq x Nk] logits never reach HBM.
+ *   out[b, h, i, :] = softmax_j(scale * q[b, h, i, :] . k[b, h, j, :]) v[b, h, j, :]
+ * Element strides {batch, head, token} per operand, the head dim D contiguous — so both the reference's "(b h) n d" copies
+ * (heads = 1, B = b*h) and the "b n (h d)" layout the Linear layers produce are addressable without a rearrange.
+ * D in {32, 40, 64, 80, 128, 160}, f16 / bf16 (sige_sparse_attention_supported() tells); strides multiples of 8 elements, buffers
+ * 16-byte aligned; scale > 0; Nq == 0 is a no-op. */
+typedef struct {
+    const void *q;               /* Nq query tokens per (batch, head) */
+    const void *k, *v;           /* Nk key / value tokens per (batch, head) */
+    void *out;                   /* same shape as q */
+    int B, heads, Nq, Nk, D;
+    long long q_stride[3], k_stride[3], v_stride[3], out_stride[3];
+    float scale;
+    int dtype;
+    int flags;                   /* reserved, 0 */
+} sige_sparse_attention_t;
+int sige_sparse_attention_supported(int D, int dtype);
+int sige_sparse_attention(const sige_sparse_attention_t *p, sige_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* diagnostics                                                                */
 /* ------------------------------------------------------------------------- */

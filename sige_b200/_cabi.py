@@ -51,6 +51,13 @@ class TileConvPlan(ctypes.Structure):
                 ("grid_x", ctypes.c_int), ("grid_y", ctypes.c_int), ("grid_z", ctypes.c_int)]
 
 
+class SparseAttention(Structure):
+    _fields_ = [("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("out", c_void_p),
+                ("B", c_int), ("heads", c_int), ("Nq", c_int), ("Nk", c_int), ("D", c_int),
+                ("q_stride", c_int64 * 3), ("k_stride", c_int64 * 3), ("v_stride", c_int64 * 3), ("out_stride", c_int64 * 3),
+                ("scale", ctypes.c_float), ("dtype", c_int), ("flags", c_int)]
+
+
 class TileConv(Structure):
     _fields_ = [
         ("dtype", c_int),
@@ -109,6 +116,8 @@ PROTOTYPES = {
     "sige_conv_out_nhwc": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "sige_attention_tokens_supported": (_I, [_I, _I, _I]),
     "sige_attention_tokens": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "sige_sparse_attention_supported": (_I, [_I, _I]),
+    "sige_sparse_attention": (_I, [POINTER(SparseAttention), _P]),
     "sige_debug_set_trace": (_I, [_P]),
 }
 

@@ -38,6 +38,8 @@ inject a CPU simulator of the launch descriptors to check the lowering without a
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -431,6 +433,18 @@ class CudaExecutor:
 
         return run
 
+    def sparse_attention_supported(self, head_dim: int) -> bool:
+        return self.ops.sparse_attention_supported(head_dim, self.dtype)
+
+    def prepare_sparse_attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, out: torch.Tensor):
+        """softmax(scale * q k^T) v of [(b h), n, d] operands as ONE launch of this repo's kernel (sige_sparse_attention)."""
+        ops = self.ops
+
+        def run(_stream):
+            ops.sparse_attention(q, k, v, scale, out=out)
+
+        return run
+
     def gather(self, x, block, idx, scale, shift, act, act_first, up=0):
         return self.ops.gather(x, block[0], block[1], idx, scale, shift, act, act_first, up=up)
 
@@ -584,6 +598,9 @@ class Lowering:
         self.module_names = module_names or {}
         self.pdl, self.tc5, self.producer_preop, self.fuse_shortcut = pdl, tc5, producer_preop, fuse_shortcut
         self.fused_attention, self.sparse_stem, self.ksplit = fused_attention, sparse_stem, ksplit
+        # SD transformer cores on this repo's kernel (SIGE_SPARSE_ATTENTION=0: the cuDNN flash kernel through torch's SDPA, for A/B)
+        self.sparse_attention = os.environ.get("SIGE_SPARSE_ATTENTION", "1") != "0"
+        self.sparse_attention_calls = 0
         self.steps: List[Tuple[str, Callable[[int], None]]] = []
         self.fused: List[FusedConv] = []
         self.conv_ins: List[ConvInRec] = []
@@ -1651,6 +1668,16 @@ class Lowering:
             return False
         out = torch.empty(tuple(o.shape), dtype=q.dtype, device=self.dev)
         scale = float(g.scale)
+        D = int(q.shape[2])
+        ok = (self.sparse_attention and scale > 0 and q.stride(2) == k.stride(2) == vv.stride(2) == 1 and k.shape == vv.shape
+              and k.shape[0] == q.shape[0] and k.shape[2] == D and all(int(t.stride(i)) % 8 == 0 for t in (q, k, vv) for i in (0, 1))
+              and self.ex.sparse_attention_supported(D))
+        if ok:
+            # this repo's flash-style kernel: sparse queries against all keys / the cached text keys, one launch
+            self.steps.append(("sparse_attention", self.ex.prepare_sparse_attention(q, k, vv, scale, out)))
+            self.sparse_attention_calls += 1
+            self.env[id(o)] = RealT(out)
+            return True
 
         q4, k4, v4 = q.unsqueeze(0), k.unsqueeze(0), vv.unsqueeze(0)      # 4-D: with 3-D operands torch falls to its fp32 math path (40x slower)
 

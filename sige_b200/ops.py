@@ -526,3 +526,51 @@ def attention_tokens(qkv: torch.Tensor, out: Optional[torch.Tensor] = None, flag
                     "sige_attention_tokens")
     _bump()
     return out
+
+
+def sparse_attention_supported(head_dim: int, dtype: torch.dtype) -> bool:
+    code = {torch.float16: _cabi.F16, torch.bfloat16: _cabi.BF16}.get(dtype)
+    return code is not None and bool(_cabi.lib().sige_sparse_attention_supported(int(head_dim), code))
+
+
+def sparse_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(scale * q k^T) v for sparse queries against all keys (reference stable-diffusion/ldm/modules/attention.py:81-93,
+    sige_attention.py:44-58).  Operands are [BH, N, D] (the reference's "(b h) n d") or [B, heads, N, D]; any strides whose
+    last dim is contiguous and which are multiples of 8 elements — a permuted view of the Linear output "b n (h d)" works
+    without a copy.  Returns a tensor shaped like q."""
+    _require_cuda(q, k, v, out)
+    if q.dim() == 3:
+        q4, k4, v4 = q.unsqueeze(1), k.unsqueeze(1), v.unsqueeze(1)
+    else:
+        q4, k4, v4 = q, k, v
+    if not (q4.dim() == k4.dim() == v4.dim() == 4):
+        raise ValueError("sparse_attention: q, k, v must all be [BH, N, D] or all [B, heads, N, D]")
+    B, Hh, Nq, D = q4.shape
+    Nk = k4.shape[2]
+    if tuple(k4.shape) != (B, Hh, Nk, D) or tuple(v4.shape) != (B, Hh, Nk, D):
+        raise ValueError("sparse_attention: shapes q %s, k %s, v %s do not match" % (tuple(q.shape), tuple(k.shape), tuple(v.shape)))
+    if not (q.dtype == k.dtype == v.dtype):
+        raise TypeError("sparse_attention: dtypes differ (%s, %s, %s)" % (q.dtype, k.dtype, v.dtype))
+    if not scale > 0:
+        raise ValueError("sparse_attention: scale must be positive")
+    if out is None:
+        out = torch.empty(tuple(q.shape), dtype=q.dtype, device=q.device)
+    if tuple(out.shape) != tuple(q.shape) or out.dtype != q.dtype:
+        raise ValueError("sparse_attention: out must have q's shape and dtype")
+    o4 = out.unsqueeze(1) if out.dim() == 3 else out
+    d = _cabi.SparseAttention()
+    d.q, d.k, d.v, d.out = q4.data_ptr(), k4.data_ptr(), v4.data_ptr(), o4.data_ptr()
+    d.B, d.heads, d.Nq, d.Nk, d.D = int(B), int(Hh), int(Nq), int(Nk), int(D)
+    for name, t in (("q_stride", q4), ("k_stride", k4), ("v_stride", v4), ("out_stride", o4)):
+        if t.numel() and t.stride(3) != 1:
+            raise ValueError("sparse_attention: the head dim must be contiguous")
+        st = getattr(d, name)
+        for i in range(3):
+            st[i] = int(t.stride(i)) if t.shape[i] > 1 else 0
+    d.scale = float(scale)
+    d.dtype = _dt(q)
+    d.flags = 0
+    with torch.cuda.device(q.device):
+        _cabi.check(_cabi.lib().sige_sparse_attention(byref(d), _stream(q)), "sige_sparse_attention")
+    _bump()
+    return out

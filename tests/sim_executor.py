@@ -181,6 +181,17 @@ class SimExecutor:
 
         return run
 
+    def sparse_attention_supported(self, head_dim):
+        return True
+
+    def prepare_sparse_attention(self, q, k, v, scale, out):
+        def run(_stream):
+            self.launches += 1
+            att = torch.softmax(torch.bmm(q.float(), k.float().transpose(1, 2)) * scale, dim=-1)
+            out.copy_(torch.bmm(att, v.float()))
+
+        return run
+
     def gather(self, x, block, idx, scale, shift, act, act_first, up=0):
         if up:
             x = F.interpolate(x.float(), scale_factor=2.0, mode="nearest")

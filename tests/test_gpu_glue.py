@@ -106,3 +106,54 @@ def test_conv_in_tiles_matches_dense_inside_the_tiles(dtype):
         inside[max(y0, 0):max(min(y0 + 6, H), 0), max(x0, 0):max(min(x0 + 6, W), 0)] = True
     assert torch.equal(out[:, :, inside], dense[:, :, inside]) and torch.equal(aux[:, :, inside], dense_aux[:, :, inside])
     assert bool((out[:, :, ~inside] == 7.0).all()) and bool((aux[:, :, ~inside] == 7.0).all())
+
+
+# Stable Diffusion v1 shapes at a 15 % edit (8 heads x batch 2; head dims 40 / 80 / 160; self-attention against all 4096 / 1024 /
+# 256 / 64 tokens, cross-attention against the 77 text tokens) plus ragged ones (one query, one key, tails that are not a
+# multiple of the 64-row blocks).
+_SATTN_SHAPES = [(16, 1000, 4096, 40), (16, 250, 1024, 80), (16, 70, 256, 160), (16, 16, 64, 160), (16, 1000, 77, 40), (16, 250, 77, 80),
+                 (3, 1, 1, 64), (2, 65, 130, 128), (1, 129, 63, 40), (2, 64, 64, 64), (4, 200, 6, 32)]
+
+
+@pytest.mark.parametrize("BH,Nq,Nk,D", _SATTN_SHAPES)
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-3), (torch.bfloat16, 8e-3)])
+def test_sparse_attention_matches_fp32_softmax(BH, Nq, Nk, D, dtype, tol):
+    """sige_sparse_attention (the reference's bmm -> * scale -> softmax -> bmm for sparse queries, stable-diffusion/ldm/modules/
+    attention.py:81-93, sige_attention.py:44-58) vs plain fp32 torch on the same 16-bit operands.  Logits ~ N(0, 4): a peaked
+    softmax, so the online rescaling across key blocks is exercised."""
+    from sige_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(BH * 131 + Nq * 7 + Nk + D)
+    q = (torch.randn(BH, Nq, D, generator=g) * 2.0).to(DEV).to(dtype)
+    k = torch.randn(BH, Nk, D, generator=g).to(DEV).to(dtype)
+    v = torch.randn(BH, Nk, D, generator=g).to(DEV).to(dtype)
+    scale = D ** -0.5
+    want = torch.bmm(torch.softmax(torch.bmm(q.float(), k.float().transpose(1, 2)) * scale, dim=-1), v.float())
+    got = ops.sparse_attention(q, k, v, scale)
+    assert got.shape == q.shape and got.dtype == dtype
+    err = float((got.float() - want).abs().max() / want.abs().max())
+    assert err <= tol, err
+    again = ops.sparse_attention(q, k, v, scale)
+    assert torch.equal(got, again), "deterministic"
+
+
+def test_sparse_attention_strided_heads_and_empty():
+    """Operands addressed in place in the 'b n (h d)' layout the Linear layers produce (no rearrange copy), and the no-tile case."""
+    from sige_b200 import ops
+
+    torch.manual_seed(5)
+    b, h, nq, nk, d = 2, 8, 150, 300, 40
+    q = torch.randn(b, nq, h * d, device=DEV).half()
+    k = torch.randn(b, nk, h * d, device=DEV).half()
+    v = torch.randn(b, nk, h * d, device=DEV).half()
+    out = torch.zeros(b, nq, h * d, device=DEV).half()
+    view = lambda t: t.view(t.shape[0], t.shape[1], h, d).permute(0, 2, 1, 3)          # [b, h, n, d], strided
+    ops.sparse_attention(view(q), view(k), view(v), d ** -0.5, out=view(out))
+    q3, k3, v3 = (view(t).reshape(b * h, -1, d).float() for t in (q, k, v))
+    want = torch.bmm(torch.softmax(torch.bmm(q3, k3.transpose(1, 2)) * d ** -0.5, dim=-1), v3)
+    got = view(out).reshape(b * h, nq, d).float()
+    assert float((got - want).abs().max() / want.abs().max()) <= 1e-3
+    empty = ops.sparse_attention(q3[:, :0].half().contiguous(), k3.half(), v3.half(), d ** -0.5)
+    assert empty.shape == (b * h, 0, d)
+    with pytest.raises(Exception):
+        ops.sparse_attention(q3.half(), k3.half()[:, :, :32].contiguous(), v3.half(), d ** -0.5)      # head dims differ
