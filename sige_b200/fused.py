@@ -568,6 +568,19 @@ class GScores:
         self.q, self.k, self.scale, self.probs = q, k, scale, probs
 
 
+class HeadsOut:
+    """Result of the sparse-attention kernel, written straight into the "b n (h d)" tensor `full` that the next Linear reads.
+    `stage` follows einops' rearrange "(b h) n d -> b n (h d)" (attention.py:93): 0 = the [(b h), n, d] value, 1 = after
+    reshape to [b, h, n, d], 2 = after permute to [b, n, h, d]; the closing reshape to [b, n, h*d] IS `full` — no copy."""
+
+    def __init__(self, full: torch.Tensor, b: int, h: int, n: int, d: int, stage: int = 0):
+        self.full, self.b, self.h, self.n, self.d, self.stage = full, b, h, n, d, stage
+
+    @property
+    def bhnd(self) -> torch.Tensor:
+        return self.full.view(self.b, self.n, self.h, self.d).permute(0, 2, 1, 3)
+
+
 _MATERIAL = (Full, Stack, RealStack, ConvOut, RealT)
 _VIEW_OPS = {"reshape", "view", "permute", "transpose", "chunk", "split", "__getitem__", "unsqueeze", "squeeze", "flatten", "unflatten",
              "expand", "narrow", "select", "unbind", "t", "movedim", "swapaxes", "view_as", "reshape_as", "T.__get__", "mT.__get__"}
@@ -932,6 +945,18 @@ class Lowering:
             return buf.raw
         if isinstance(v, Stack):
             return self.materialize_stack(lt, v)
+        if isinstance(v, HeadsOut):           # a consumer other than einops' closing rearrange
+            if v.stage == 2:
+                t = v.full.view(v.b, v.n, v.h, v.d)
+            elif v.stage == 1:
+                t = v.bhnd
+            else:
+                t = torch.empty((v.b * v.h, v.n, v.d), dtype=v.full.dtype, device=v.full.device)
+                src, dst = v.bhnd, t.view(v.b, v.h, v.n, v.d)
+                self.steps.append(("eager", lambda _s, src=src, dst=dst: dst.copy_(src)))
+                self.eager_nodes.append("heads_copy")
+            self.env[id(lt)] = RealT(t)
+            return t
         # speculative symbolic kinds (or nothing yet): evaluate the producing node eagerly
         if v is None and id(lt) in self._alias_of:
             return self.runtime_tensor(self._alias_of[id(lt)])
@@ -1599,6 +1624,14 @@ class Lowering:
         shape = tuple(int(s) for s in shape)
         v = self.sym(x)
         out = node.outs[0]
+        if isinstance(v, HeadsOut):
+            if v.stage == 0 and shape == (v.b, v.h, v.n, v.d):
+                self.env[id(out)] = HeadsOut(v.full, v.b, v.h, v.n, v.d, 1)
+                return True
+            if v.stage == 2 and shape == (v.b, v.n, v.h * v.d):
+                self.env[id(out)] = RealT(v.full)
+                return True
+            return False
         if isinstance(v, ChanSlice):
             B, _, H, W = v.buf.shape
             if tuple(out.shape) == (B, v.c1 - v.c0, H * W):
@@ -1619,6 +1652,11 @@ class Lowering:
         x = node.args[0]
         dims = node.args[1:] if not isinstance(node.args[1], (tuple, list)) else tuple(node.args[1])
         v = self.sym(x)
+        if isinstance(v, HeadsOut):
+            if v.stage == 1 and tuple(int(d) for d in dims) == (0, 2, 1, 3):
+                self.env[id(node.outs[0])] = HeadsOut(v.full, v.b, v.h, v.n, v.d, 2)
+                return True
+            return False
         if tuple(dims) != (0, 2, 1):
             return False
         if isinstance(v, Tok):
@@ -1662,22 +1700,50 @@ class Lowering:
             self._keepalive.append(c)
             return c
 
-        q, k, vv = rt(g.q), rt(g.k), rt(v)
         o = node.outs[0]
-        if not (q.dtype == k.dtype == vv.dtype and q.dim() == 3):
+        scale = float(g.scale)
+        D = int(o.shape[2])
+        ours = self.sparse_attention and scale > 0 and self.ex.sparse_attention_supported(D)
+
+        def operand(t):
+            """The [(b h), n, d] operand — or, when it is einops' copy of a "b n (h d)" tensor (reshape -> permute -> reshape,
+            attention.py:81) that nothing else reads, the strided [b, h, n, d] VIEW of that tensor: the kernel takes explicit
+            (batch, head, token) strides, so the three rearrange copies per attention call disappear."""
+            if (ours and isinstance(t, LazyTensor) and t.node is not None and t.node.name in ("reshape", "view") and self.sym(t) is None
+                    and self.n_uses(t) == 1):
+                src = t.node.args[0]
+                if isinstance(src, LazyTensor) and src.dim() == 4 and tuple(t.shape) == (src.shape[0] * src.shape[1], src.shape[2], src.shape[3]):
+                    r = self.runtime_tensor(src)
+                    if r.dtype == self.dtype and r.stride(3) == 1 and all(int(r.stride(i)) % 8 == 0 for i in range(3)) and r.data_ptr() % 16 == 0:
+                        return r
+            return rt(t)
+
+        q, k, vv = operand(g.q), operand(g.k), operand(v)
+        if not (q.dtype == k.dtype == vv.dtype):
             return False
         out = torch.empty(tuple(o.shape), dtype=q.dtype, device=self.dev)
-        scale = float(g.scale)
-        D = int(q.shape[2])
-        ok = (self.sparse_attention and scale > 0 and q.stride(2) == k.stride(2) == vv.stride(2) == 1 and k.shape == vv.shape
-              and k.shape[0] == q.shape[0] and k.shape[2] == D and all(int(t.stride(i)) % 8 == 0 for t in (q, k, vv) for i in (0, 1))
-              and self.ex.sparse_attention_supported(D))
-        if ok:
-            # this repo's flash-style kernel: sparse queries against all keys / the cached text keys, one launch
-            self.steps.append(("sparse_attention", self.ex.prepare_sparse_attention(q, k, vv, scale, out)))
-            self.sparse_attention_calls += 1
-            self.env[id(o)] = RealT(out)
-            return True
+        if ours:
+            heads = {int(t.shape[1]) for t in (q, k, vv) if t.dim() == 4}
+            ho = None
+            if len(heads) == 1:       # mixed 3-D / 4-D operands: present every one as [b, h, n, d]
+                hh = heads.pop()
+                q, k, vv = (t if t.dim() == 4 else t.view(t.shape[0] // hh, hh, t.shape[1], t.shape[2]) for t in (q, k, vv))
+                # ... and write the result in the "b n (h d)" layout its consumer (to_out's Linear) reads: see HeadsOut
+                ho = HeadsOut(torch.empty((out.shape[0] // hh, out.shape[1], hh * D), dtype=out.dtype, device=self.dev), out.shape[0] // hh, hh,
+                              int(out.shape[1]), D)
+                out_arg = ho.bhnd
+            else:
+                out_arg = out
+            ok = (len(heads) == 0 and q.dim() == k.dim() == vv.dim() and k.shape == vv.shape and k.shape[:-2] == q.shape[:-2] and k.shape[-1] == D
+                  and all(t.stride(-1) == 1 and all(int(st) % 8 == 0 for st in t.stride()[:-1]) for t in (q, k, vv)))
+            if ok:
+                # this repo's flash-style kernel: sparse queries against all keys / the cached text keys, one launch
+                self.steps.append(("sparse_attention", self.ex.prepare_sparse_attention(q, k, vv, scale, out_arg)))
+                self.sparse_attention_calls += 1
+                self.env[id(o)] = ho if ho is not None else RealT(out)
+                return True
+        if not (q.dim() == k.dim() == vv.dim() == 3):
+            return False            # (strided operands the kernel refused: the recorded bmm / softmax / bmm run as they are)
 
         q4, k4, v4 = q.unsqueeze(0), k.unsqueeze(0), vv.unsqueeze(0)      # 4-D: with 3-D operands torch falls to its fp32 math path (40x slower)
 

@@ -187,8 +187,8 @@ class SimExecutor:
     def prepare_sparse_attention(self, q, k, v, scale, out):
         def run(_stream):
             self.launches += 1
-            att = torch.softmax(torch.bmm(q.float(), k.float().transpose(1, 2)) * scale, dim=-1)
-            out.copy_(torch.bmm(att, v.float()))
+            att = torch.softmax(torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale, dim=-1)       # [bh, n, d] or strided [b, h, n, d]
+            out.copy_(torch.matmul(att, v.float()))
 
         return run
 
