@@ -221,6 +221,19 @@ class IdxSlot:
         self.buf[:self.n] = idx
         self.buf[self.n:] = self.none
 
+    def install_device(self, out: torch.Tensor, count: torch.Tensor, status: torch.Tensor) -> None:
+        """Install the result of `sige_reduce_mask` (`out` [candidates, 2] of which the first `count` rows are real, `count` a
+        DEVICE int32) without the host ever learning the count: the first min(count, cap) origins, SIGE_TILE_NONE behind them;
+        `status` (device int32) gets bit 0 set if the list did not fit."""
+        cap = self.cap
+        src = out[:cap]
+        if src.shape[0] < cap:
+            src = torch.cat([src, torch.full((cap - src.shape[0], 2), self.none, dtype=torch.int32, device=src.device)], 0)
+        rows = torch.arange(cap, device=src.device, dtype=torch.int32).view(cap, 1)
+        self.buf.copy_(torch.where(rows < count.view(1, 1), src, torch.full_like(src, self.none)))
+        status.bitwise_or_((count > cap).to(torch.int32))
+        self.n = cap           # the real count is only known on the device: host-side code treats every entry as potentially real
+
 
 class ConvInRec:
     """conv_in launch record (<=4-channel stem) with up to two transformed extra outputs."""
@@ -1933,6 +1946,55 @@ class FusedStep:
             for b in low.cached_bufs:
                 b.restore()
         return True
+
+    def rebind_device(self, masks) -> bool:
+        """`rebind` without a host synchronisation: the mask reductions (`sige_reduce_mask`) run on the device
+        and their results go straight into the fixed-capacity tile lists the captured launches read — count and all stay in HBM,
+        nothing is copied back, so the call only ENQUEUES work (a handful of small kernels) and the next replay sees the new edit.
+        Whether every list fit its capacity is recorded in `self.async_status` (device int32: bit 0 = a list overflowed and was
+        truncated, bit 1 = a fused shortcut's tiles left the main conv's grid); `async_ok()` reads it (that one does synchronise).
+        Returns False — nothing changed — when this step cannot be re-bound in place at all."""
+        from . import ops
+
+        low = self.low
+        if any(n.startswith(("sige.", "gather(")) for n in self.eager_nodes) or not low.slots:
+            return False
+        for sl in low.slots.values():
+            g = sl.gather
+            m = masks.get(tuple(g.input_res)) if g.input_res is not None else None
+            if getattr(g, "tile_images", None) is not None or m is None or not m.is_cuda or m.dim() != 2:
+                return False
+        with torch.no_grad():
+            if getattr(self, "async_status", None) is None:
+                self.async_status = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+            self.async_status.zero_()
+            memo: Dict = {}
+            for sl in low.slots.values():
+                g = sl.gather
+                res = tuple(g.input_res)
+                key = (res, tuple(g.block_size), tuple(g.block_stride), tuple(g.offset))
+                if key not in memo:
+                    m = masks[res]
+                    m = (m > 0.5) if m.is_floating_point() else (m != 0)          # same binarisation as masks.reduce_mask
+                    memo[key] = ops.reduce_mask_cuda_launch(m, g.block_size, g.block_stride, g.offset)
+                sl.install_device(*memo[key], self.async_status)
+            width = 1 << 16
+            for (fbuf, ms, off, ss, soff) in low.flag_recipes:
+                mi, si = ms.buf.long(), ss.buf.long()
+                real_m, real_s = mi[:, 0] > ms.none, si[:, 0] > ss.none
+                main_key = torch.where(real_m, (mi[:, 0] + off) * width + (mi[:, 1] + off), torch.full_like(mi[:, 0], -1))
+                sc_key = torch.where(real_s, (si[:, 0] + soff) * width + (si[:, 1] + soff), torch.full_like(si[:, 0], -2))
+                fbuf.copy_((torch.isin(main_key, sc_key) & real_m).to(torch.uint8))
+                stray = (~torch.isin(sc_key, main_key) & real_s).any().to(torch.int32) * 2
+                self.async_status.bitwise_or_(stray.view(1))
+            for b in low.cached_bufs:
+                b.restore()
+        return True
+
+    def async_ok(self) -> bool:
+        """True if the lists installed by the last `rebind_device` all fit (synchronises)."""
+        st = getattr(self, "async_status", None)
+        return st is None or int(st.item()) == 0
 
     def __call__(self, *args, **kwargs):
         args = tuple(args) + tuple(kwargs[k] for k in self._kw_names)

@@ -150,6 +150,7 @@ class SIGEModel(nn.Module):
         ``torch.nonzero`` sync per geometry)."""
         sig = tuple(sorted((tuple(res), t.data_ptr(), t._version, tuple(t.shape), str(t.dtype), str(t.device)) for res, t in masks.items()))
         d = self.__dict__
+        d.pop("_async_masks", None)          # a synchronous call supersedes lists installed by set_masks_async
         if d.get("_mask_sig") == sig and d.get("_mask_modules") == sum(1 for _ in self._sige_modules()):
             return
         self.timestamp += 1
@@ -161,6 +162,41 @@ class SIGEModel(nn.Module):
         for m in mods:
             m.set_mask(masks, shared, self.timestamp)
         d["_mask_sig"], d["_mask_keep"], d["_mask_modules"] = sig, list(masks.values()), len(mods)     # (the tensors are kept alive: their addresses are part of the key)
+
+    def set_masks_async(self, masks: Dict[Tuple[int, int], torch.Tensor]) -> bool:
+        """`set_masks` for the NEXT edit without a host synchronisation (an extension): when a compiled fused
+        step exists whose tile lists are fixed-capacity device buffers (`set_fused(headroom=...)` sizes them), the new pyramid is
+        reduced on the device straight into those buffers (`FusedStep.rebind_device`) — the host never learns the tile counts, no
+        re-trace, no re-capture, only enqueued work.  Returns True when that happened; `masks_async_ok()` tells (with a sync,
+        whenever the caller can afford one) whether every list fit.  Otherwise — no compiled step yet, a batch of edits, eager
+        operator-module fallbacks in the step, CPU masks — falls back to the synchronous `set_masks` and returns False.
+        The operator modules' own `active_indices` are brought up to date lazily (by a synchronous `set_masks`) if a later call
+        cannot use the compiled step."""
+        d = self.__dict__
+        steps = d.get("_fused_steps", {})
+        live = [(k, st) for k, st in steps.items() if st is not None and k[1] == _cache_generation[0] and k[2] == d.get("_sige_cache_id", 0)]
+        if d.get("_fused_enabled", False) and d.get("mode") == "sparse" and len(live) == 1 and live[0][1].rebind_device(masks):
+            key, st = live[0]
+            steps.clear()
+            self.timestamp += 1
+            steps[(self.timestamp, *key[1:])] = st
+            d["_async_masks"] = dict(masks)
+            d["_mask_sig"] = None
+            return True
+        self.set_masks(masks)
+        return False
+
+    def masks_async_ok(self) -> bool:
+        """Did every tile list of the last `set_masks_async` fit its capacity?  (Synchronises.)"""
+        st = self.__dict__.get("fused_step")
+        return st is None or st.async_ok()
+
+    def _sync_async_masks(self) -> None:
+        """The operator modules' tile lists are stale after `set_masks_async`; bring them up to date (one host sync)."""
+        pending = self.__dict__.pop("_async_masks", None)
+        if pending is not None:
+            self.__dict__.get("_fused_steps", {}).clear()
+            self.set_masks(pending)
 
     def set_mode(self, mode: str):
         self.mode = mode
@@ -212,6 +248,9 @@ class SIGEModel(nn.Module):
             return None
         key = (d.get("timestamp", 0), _cache_generation[0], d.get("_sige_cache_id", 0), sig)
         steps = d.setdefault("_fused_steps", {})
+        if key not in steps and d.get("_async_masks") is not None:
+            self._sync_async_masks()          # lists installed on the device only: a different call signature needs the modules' lists
+            key = (d.get("timestamp", 0), _cache_generation[0], d.get("_sige_cache_id", 0), sig)
         if key not in steps:
             # same caches, same arguments, NEW masks: try to install the new tile lists into the compiled step in place
             for k in [k for k in steps if k[1:] == key[1:] and k[0] != key[0]]:
@@ -241,6 +280,7 @@ class SIGEModel(nn.Module):
     def __call__(self, *args, **kwargs):
         step = self._fused_lookup(args, kwargs)
         if step is None:
+            self._sync_async_masks()
             return super().__call__(*args, **kwargs)
         self.__dict__["fused_step"] = step
         out = step(*args, **kwargs)

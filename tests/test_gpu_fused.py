@@ -386,3 +386,50 @@ def test_capacity_headroom_lets_a_larger_mask_in():
         model.set_fused(False)
         want = model(x_b.to(DEV).half(), t)
     assert float((out_b - want).abs().max() / want.abs().max()) <= TOL_MAX
+
+
+def test_next_edit_without_a_host_sync():
+    """`set_masks_async` reduces the new mask pyramid ON THE DEVICE straight into the fixed-capacity tile lists of
+    the compiled step (counts never reach the host), so installing the next edit only enqueues work.  Same result as the
+    synchronous path; a mask that does NOT fit is reported by `masks_async_ok()` (device status word), and a following
+    synchronous `set_masks` recovers."""
+    from sige.utils import downsample_mask
+    from sige_b200.workloads.ddpm import DDPMConfig, synthetic_inputs
+
+    cfg = DDPMConfig.small()
+    model, x_a, t = _prepared("intree", cfg, 0.04, torch.float16)
+    model.set_fused(True, headroom=0.6)
+    with torch.no_grad():
+        model(x_a, t)
+        step = model.fused_step
+        _, x_b, mask_b, _ = synthetic_inputs(cfg, 0.055, seed=0, edit_seed=2)       # more tiles than edit A, within the headroom
+        pyr_b = downsample_mask(mask_b.to(DEV), min_res=8)
+        x_b = x_b.to(DEV).half()
+        torch.cuda.synchronize()
+        # the proof of "no host sync": with sync debugging on, any .item() / .cpu() / nonzero in the call would raise
+        torch.cuda.set_sync_debug_mode("error")
+        try:
+            assert model.set_masks_async(pyr_b) is True
+            out_b = model(x_b, t)
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+        assert model.fused_step is step and model.masks_async_ok()
+        # reference: the synchronous path on a fresh build
+        model.set_masks(pyr_b)
+        want_fused = model(x_b, t)
+        model.set_fused(False)
+        want = model(x_b, t)
+        model.set_fused(True, headroom=0.6)
+        assert torch.equal(out_b, want_fused), "device-installed lists == host-installed lists"
+        assert float((out_b - want).abs().max() / want.abs().max()) <= TOL_MAX
+        # a much larger edit does not fit: flagged on the device, and the synchronous call rebuilds
+        model(x_a, t)
+        _, x_c, mask_c, _ = synthetic_inputs(cfg, 0.30, seed=0, edit_seed=4)
+        pyr_c = downsample_mask(mask_c.to(DEV), min_res=8)
+        if model.set_masks_async(pyr_c):
+            assert not model.masks_async_ok()
+        model.set_masks(pyr_c)
+        out_c = model(x_c.to(DEV).half(), t)
+        model.set_fused(False)
+        want_c = model(x_c.to(DEV).half(), t)
+    assert float((out_c - want_c).abs().max() / want_c.abs().max()) <= 6e-2
