@@ -42,6 +42,15 @@ constexpr int NPROD = 32 * NPROD_WARPS;
 constexpr int A_COPY_BYTES = 6 * TILES * 4 * 128;        // one kx-copy: [6][8][4] rows x 128 B = 24576
 constexpr int A_BUF_BYTES = 3 * A_COPY_BYTES;            // 73728 per 64-channel chunk
 constexpr int EPI_PAD = 4;
+// Stride-2 geometry (3x3 stride 2 on 5x5 halo tiles -> 2x2 outputs, the DDPM Downsample: reference
+// diffusion/models/ddpm_arch/sige_fused_unet.py:212-221): 32 tiles x 4 outputs = 128 GEMM rows, row m = oy*64 + tile*2 + ox.
+// Output (oy, ox) of tap (ky, kx) reads halo pixel (2*oy + ky, 2*ox + kx), so the halo rows are kept as five 64-row PLANES
+// ordered y = 0, 2, 4, 1, 3 and copy kx holds pixel (y, 2*ox + kx) in row plane(y)*64 + tile*2 + ox: tap (ky, kx) is then
+// copy kx starting at plane {0, 3, 1}[ky] — again ONE descriptor per tap, a start offset that is a multiple of 8192 bytes.
+// A gathered pixel is stored 1.2 times (x = 2 feeds kx = 0 and kx = 2).
+constexpr int S2_TILES = 32;
+constexpr int S2_COPY_BYTES = 5 * 64 * 128;              // 40960
+constexpr int S2_BUF_BYTES = 3 * S2_COPY_BYTES;          // 122880 per 64-channel chunk
 
 struct Seg {
     const void *ptr;
@@ -91,33 +100,39 @@ struct Params {
     long long *trace;          // development aid: per-CTA clock stamps (16 slots), or nullptr
 };
 
-template <int BN, int TAPS, bool DEEP = false> struct Cfg {
+template <int BN, int TAPS, bool DEEP = false, bool S2 = false> struct Cfg {
+    static_assert(!S2 || (BN == 64 && TAPS == 9 && !DEEP), "stride-2 geometry: narrow 3x3 only");
+    static constexpr int CT = S2 ? S2_TILES : TILES;           // tiles per CTA
+    static constexpr int A_COPY = S2 ? S2_COPY_BYTES : A_COPY_BYTES;
+    static constexpr int A_BUF = S2 ? S2_BUF_BYTES : A_BUF_BYTES;
     // DEEP (split-K launches of the narrow 3x3 configuration: small, latency-bound problems whose K slices rarely span
     // more than one or two chunks): ONE halo buffer, and the other 72 KB go to the weight ring — 5 stages = 120 KB in
     // flight, so a slice's weights are on their way before the previous layer has finished, instead of one L2/HBM
     // round trip per two ring steps.
     static_assert(!DEEP || (BN == 64 && TAPS == 9), "deep ring: narrow 3x3 only");
-    static constexpr int NAB = DEEP ? 1 : 2;
+    static constexpr int NAB = (DEEP || S2) ? 1 : 2;
     // one weight-ring stage = TPS taps (a whole kernel row for the narrow 3x3 configuration): fewer barrier round
     // trips for the single MMA-issuing thread
     static constexpr int TPS = (TAPS == 9 && BN == 64) ? 3 : 1;
     static constexpr int SPC = TAPS / TPS;                     // ring steps per 64-channel chunk
     static constexpr int B_TILE_BYTES = BN * 128;              // one (tap, chunk) weight tile
     static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES;
-    static constexpr int NSTB = DEEP ? 5 : ((BN == 128) ? 4 : (TPS == 3 ? 2 : 4));   // weight ring depth (120 / 48 / 32 / 64 KB in flight per CTA)
+    static constexpr int NSTB = S2 ? 3 : DEEP ? 5 : ((BN == 128) ? 4 : (TPS == 3 ? 2 : 4));   // weight ring depth (72 / 120 / 48 / 32 / 64 KB in flight per CTA)
     static constexpr int EPI_PITCH = BN + EPI_PAD;             // floats
     static constexpr int OFF_A = 0;
-    static constexpr int OFF_B = NAB * A_BUF_BYTES;
+    static constexpr int OFF_B = NAB * A_BUF;
     // split-K (BN = 64 only): partial-tile rows pushed by the other ranks of the cluster land here — a region that no
     // mainloop touches, so a fast rank may push while this CTA is still multiplying.  <= 7 remote ranks x 16 rows.
     static constexpr int OFF_SLOT = OFF_B + NSTB * B_STAGE_BYTES;
     static constexpr int SLOT_BYTES = (BN == 64) ? 112 * EPI_PITCH * 4 : 0;
     static constexpr bool kSplitOk = (BN == 64);
     static constexpr int OFF_BAR = OFF_SLOT + SLOT_BYTES;
-    static constexpr int OFF_CONST = OFF_BAR + 256;            // idx[8][2] ints + 8 shortcut flags, then bias | aux0 scale,shift | aux1 scale,shift | bias2
-    static constexpr int SMEM_BYTES = OFF_CONST + 80 + 6 * BN * 4 + 1024;    // + slack for the 1024-byte alignment
+    static constexpr int OFF_CONST = OFF_BAR + 256;            // idx[CT][2] ints + CT shortcut flags, then bias | aux0 scale,shift | aux1 scale,shift | bias2
+    static constexpr int OFF_FLAGS = OFF_CONST + CT * 8;
+    static constexpr int OFF_VEC = OFF_FLAGS + (CT + 15) / 16 * 16;          // (80 bytes after OFF_CONST for the 8-tile geometries)
+    static constexpr int SMEM_BYTES = OFF_VEC + 6 * BN * 4 + 1024;    // + slack for the 1024-byte alignment
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
-    static_assert(128 * EPI_PITCH * 4 <= NAB * A_BUF_BYTES, "epilogue staging must fit in the halo buffers");
+    static_assert(128 * EPI_PITCH * 4 <= NAB * A_BUF, "epilogue staging must fit in the halo buffers");
 };
 
 // ------------------------------------------------------------------------------------------
@@ -287,13 +302,16 @@ __device__ __forceinline__ long long gtime() {
     } while (0)
 
 // ASYNC: the gather is a pure copy (no pre-op: the producer of the source already applied it) and is done with cp.async.
-template <typename T, int BN, int TAPS, bool DEEP, bool ASYNC>
+template <typename T, int BN, int TAPS, bool DEEP, bool ASYNC, bool S2 = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap wmap,
                      const __grid_constant__ CUtensorMap wmap2) {
-    using C = Cfg<BN, TAPS, DEEP>;
+    using C = Cfg<BN, TAPS, DEEP, S2>;
+    static_assert(!S2 || ASYNC, "stride-2 geometry: pure-copy (cp.async) gather only");
     constexpr int NSTB = C::NSTB, TPS = C::TPS, SPC = C::SPC, NAB = C::NAB;
-    constexpr int R = (TAPS == 9) ? 6 : 4;            // halo tile extent
+    constexpr int TILES = C::CT;                      // (shadows the namespace constant: 32 for the stride-2 geometry)
+    constexpr int A_COPY_BYTES = C::A_COPY, A_BUF_BYTES = C::A_BUF;
+    constexpr int R = (TAPS == 9) ? (S2 ? 5 : 6) : 4; // halo tile extent
     constexpr int RS = R * R;
     constexpr int UNITS = TILES * RS * 8;             // 16-byte units gathered per chunk
     constexpr int LOADS = (UNITS + NPROD - 1) / NPROD;
@@ -321,7 +339,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     const int ntile = min(TILES, p.NT - tile0);
     const int NC = p.Cin / KC;
     const int J_main = NC * SPC;                   // ring steps of the main conv (a step = TPS taps of one 64-channel chunk)
-    const int NC2 = (TAPS == 9) ? p.Cin2 / KC : 0;  // fused 1x1 shortcut: one step (the centre tap) per chunk of ITS input
+    const int NC2 = (TAPS == 9 && !S2) ? p.Cin2 / KC : 0;  // fused 1x1 shortcut: one step (the centre tap) per chunk of ITS input
     const int J = J_main + NC2;
     const int kr = blockIdx.z;
     const int j_begin = (int)(((long long)J * kr) / p.ksplit), j_end = (int)(((long long)J * (kr + 1)) / p.ksplit);
@@ -329,8 +347,8 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     auto chunk_of = [&](int j) { return j < J_main ? j / SPC : NC + (j - J_main); };
     const int c_first = chunk_of(j_begin), c_last = chunk_of(j_end - 1);
     int32_t *s_idx = reinterpret_cast<int32_t *>(smem + C::OFF_CONST);          // [TILES][2] tile origins of this CTA
-    unsigned char *s_flags = smem + C::OFF_CONST + 64;                          // [TILES] 1 = evaluate the fused shortcut on this tile
-    float *s_const = reinterpret_cast<float *>(smem + C::OFF_CONST + 80);       // bias | aux0 scale | aux0 shift | aux1 scale | aux1 shift | bias2
+    unsigned char *s_flags = smem + C::OFF_FLAGS;                               // [TILES] 1 = evaluate the fused shortcut on this tile
+    float *s_const = reinterpret_cast<float *>(smem + C::OFF_VEC);              // bias | aux0 scale | aux0 shift | aux1 scale | aux1 shift | bias2
 
     if (tid == 0) SIGE_TRACE(0);
     // ---------------- one-time setup ----------------
@@ -347,7 +365,13 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         tmem_alloc(s32(tmem_slot), BN);     // BN fp32 accumulator columns (power of two >= 32)
     } else if (warp == 2) {
         // this CTA's tile origins (constant since set_masks): one global round trip here instead of one per gather thread
-        if (lane < 2 * TILES) {
+        if (S2) {
+            for (int e = lane; e < 2 * TILES; e += 32) {
+                const int t = tile0 + (e >> 1);
+                s_idx[e] = (t < p.NT && p.idx) ? __ldg(p.idx + 2 * (p.idx_per_image ? t : t % p.N) + (e & 1)) : 0;
+            }
+            s_flags[lane] = 0;                        // (no fused shortcut in this geometry)
+        } else if (lane < 2 * TILES) {
             const int t = tile0 + (lane >> 1);
             int v = 0;
             if (t < p.NT && p.idx) v = __ldg(p.idx + 2 * (p.idx_per_image ? t : t % p.N) + (lane & 1));
@@ -376,19 +400,25 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     if (tid == 0) SIGE_TRACE(1);
     if (p.pdl == 1) asm volatile("griddepcontrol.launch_dependents;\n" ::);   // the next layer may start prefetching ITS weights
 
-    auto tl_of = [&](int m) { return TAPS == 9 ? (m >> 2) & 7 : m >> 4; };
+    auto tl_of = [&](int m) { return S2 ? (m >> 1) & 31 : (TAPS == 9 ? (m >> 2) & 7 : m >> 4); };
     // GEMM row m -> destination pixel index, or -1 (row of a tile that does not exist / outside the image)
     auto pixel_of = [&](int m) -> long long {
         int tl, oy, ox;
-        if (TAPS == 9) { oy = m >> 5; tl = (m >> 2) & 7; ox = m & 3; } else { tl = m >> 4; oy = (m >> 2) & 3; ox = m & 3; }
+        if (S2) { oy = m >> 6; tl = (m >> 1) & 31; ox = m & 1; }
+        else if (TAPS == 9) { oy = m >> 5; tl = (m >> 2) & 7; ox = m & 3; } else { tl = m >> 4; oy = (m >> 2) & 3; ox = m & 3; }
         if (tl >= ntile) return -1;
         const int t = tile0 + tl;
         int hh = oy, ww = ox, img = t;
         if (!p.dst_is_stack) {
             img = 0;
             if (p.NT != p.N) img = t / p.N;
-            hh += p.offH + s_idx[2 * tl];
-            ww += p.offW + s_idx[2 * tl + 1];
+            if (S2) {       // output origin = (offset + tile origin) / stride, C division (reference sige/cuda/scatter_kernel.cu:24-25)
+                hh += (p.offH + s_idx[2 * tl]) / 2;
+                ww += (p.offW + s_idx[2 * tl + 1]) / 2;
+            } else {
+                hh += p.offH + s_idx[2 * tl];
+                ww += p.offW + s_idx[2 * tl + 1];
+            }
         }
         if (hh < 0 || hh >= p.dH || ww < 0 || ww >= p.dW) return -1;
         return ((long long)img * p.dH + hh) * p.dW + ww;
@@ -456,7 +486,9 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 tc_fence_after();
                 const uint32_t b_step = b_lo0 + s * (C::B_STAGE_BYTES >> 4);
                 uint32_t a_step = a_lo0 + ab * (A_BUF_BYTES >> 4);
-                if (TAPS == 9) {
+                if (S2) {
+                    a_step += (st == 0 ? 0 : (st == 1 ? 3 : 1)) * ((64 * 128) >> 4);               // ky = st: planes {0,2,4 | 1,3} start at {0, 3, 1}
+                } else if (TAPS == 9) {
                     if (is_sc) a_step += (A_COPY_BYTES + 32 * 128) >> 4;                           // tap (1,1)
                     else if (TPS == 3) a_step += st * ((32 * 128) >> 4);                           // ky = st, kx = t
                     else { const int ky = st / 3; a_step += ky * ((32 * 128) >> 4) + (st - 3 * ky) * (A_COPY_BYTES >> 4); }
@@ -487,6 +519,82 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     } else {
         // ================= A-operand producers: gather + pre-op + swizzled stores =================
         const int ptid = tid - 64;
+        if constexpr (S2) {
+            // ---- stride-2 geometry: 32 tiles x 5x5 halo pixels x 8 units = 6400 sixteen-byte copies per chunk (25 per thread),
+            //      pure copy with cp.async straight into the plane layout described at S2_TILES.  Only the source offsets are
+            //      resolved ahead (in the prologue, overlapping the previous layer); destinations are recomputed per chunk.
+            int g_off[LOADS];
+            int g_sg = -1;
+            auto decode = [&](int q, int &x, int &y, int &tl) {
+                const int pix = q >> 3;
+                tl = pix / RS;
+                const int rem = pix - tl * RS;
+                y = rem / R;
+                x = rem - y * R;
+            };
+            auto resolve = [&](int sg) {
+                const Seg &seg = p.seg[sg];
+                const int Hs = p.H >> seg.up, Ws = p.W >> seg.up;
+#pragma unroll
+                for (int k = 0; k < LOADS; ++k) {
+                    const int q = ptid + k * NPROD;
+                    g_off[k] = -2;
+                    if (q < UNITS) {
+                        g_off[k] = -1;
+                        int x, y, tl;
+                        decode(q, x, y, tl);
+                        const int t = tile0 + tl;
+                        if (t < p.NT) {
+                            int hh = y, ww = x, img = t;
+                            if (!p.src_is_stack) {
+                                hh += s_idx[2 * tl];
+                                ww += s_idx[2 * tl + 1];
+                                img = (p.NT != p.N) ? t / p.N : 0;
+                            }
+                            if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+                                g_off[k] = ((img * Hs + (hh >> seg.up)) * Ws + (ww >> seg.up)) * seg.C + (q & 7) * 8;
+                        }
+                    }
+                }
+                g_sg = sg;
+            };
+            resolve(c_first * KC >= p.C0 ? 1 : 0);
+            if (ptid == 0) SIGE_TRACE(2);
+            if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");   // activations of the previous layer are complete
+            int ause = 0;
+            for (int c = c_first; c <= c_last; ++c) {
+                mbar_wait(A_EMPTY(0), (ause & 1) ^ 1);                    // the MMAs that read the (single) halo buffer have retired
+                if (ptid == 0 && c == c_first) SIGE_TRACE(3);
+                const int cbase = c * KC;
+                const int sg = cbase >= p.C0 ? 1 : 0;
+                const Seg &seg = p.seg[sg];
+                const int cl = cbase - (sg ? p.C0 : 0);
+                if (sg != g_sg) resolve(sg);
+                const uint32_t abase = sbase + C::OFF_A;
+#pragma unroll
+                for (int k = 0; k < LOADS; ++k) {
+                    if (g_off[k] == -2) continue;
+                    const bool ok = g_off[k] >= 0;
+                    const T *src = reinterpret_cast<const T *>(seg.ptr) + (ok ? g_off[k] + cl : 0);
+                    const uint32_t nb = ok ? 16u : 0u;
+                    const int q = ptid + k * NPROD, u = q & 7;
+                    int x, y, tl;
+                    decode(q, x, y, tl);
+                    const int plane = (y & 1) ? 3 + (y >> 1) : (y >> 1);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int xp = x - kx;
+                        if (xp == 0 || xp == 2) {
+                            const int row = plane * 64 + tl * 2 + (xp >> 1);
+                            cp_async16(abase + kx * A_COPY_BYTES + row * 128 + ((u ^ (row & 7)) << 4), src, nb);
+                        }
+                    }
+                }
+                cp_async_arrive(A_FULL(0));
+                if (ptid == 0 && c == c_first) SIGE_TRACE(4);
+                ++ause;
+            }
+        } else {
         // per-thread gather list (fixed for the whole kernel)
         int g_xyt[LOADS];     // x | y << 4 | tile << 8 of the halo pixel this load feeds
         int g_off[LOADS];     // element offset of its 16-byte unit in the CURRENT source segment (channel-chunk offset
@@ -724,6 +832,7 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             ab = ause % NAB;
         }
         }
+        }   // !S2
     }
 
     // ---------------- epilogue ----------------
@@ -903,14 +1012,14 @@ struct Plan {
     int bn, ksplit, deep;
 };
 
-static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int ksplit_req) {
+static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int ksplit_req, bool s2 = false) {
     Plan pl;
-    const long long m_blocks = ceil_div(NT, TILES);
+    const long long m_blocks = ceil_div(NT, s2 ? S2_TILES : TILES);
     // BN = 128 when that still fills the machine — or when the narrow tiling would need more waves of 148 one-per-SM CTAs
     // than the wide one (a batch of edits: 64 row blocks x Cout 256 is 256 narrow CTAs = 2 waves, 128 wide CTAs = 1 wave,
     // and a CTA's gather — the long pole — is the same either way); small problems want more, narrower CTAs
     const long long narrow_ctas = m_blocks * (Cout / 64), wide_ctas = m_blocks * (Cout / 128);
-    const bool wide = (Cout % 128 == 0) && (wide_ctas >= 148 || (narrow_ctas > 148 && ceil_div(wide_ctas, 148) < ceil_div(narrow_ctas, 148)));
+    const bool wide = !s2 && (Cout % 128 == 0) && (wide_ctas >= 148 || (narrow_ctas > 148 && ceil_div(wide_ctas, 148) < ceil_div(narrow_ctas, 148)));
     pl.bn = wide ? 128 : 64;
     const bool split_ok = pl.bn == 64;                       // Cfg::kSplitOk
     const int tps = (taps == 9 && pl.bn == 64) ? 3 : 1;     // Cfg::TPS
@@ -937,13 +1046,13 @@ static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int kspl
     static int deep_env = getenv("SIGE_TC5_DEEP") ? atoi(getenv("SIGE_TC5_DEEP")) : 1;   // A/B knob
     // (2 = also for un-split launches: with the cp.async gather a single halo buffer costs 0.65 us of exposed gather per chunk,
     //  while two weight stages — 48 KB in flight — cap the weight ring at ~1.5 us per chunk; an A/B knob)
-    pl.deep = (pl.bn == 64 && taps == 9 && deep_env && (ks > 1 || deep_env >= 2)) ? 1 : 0;
+    pl.deep = (!s2 && pl.bn == 64 && taps == 9 && deep_env && (ks > 1 || deep_env >= 2)) ? 1 : 0;
     return pl;
 }
 
-template <typename T, int BN, int TAPS, bool DEEP, bool ASYNC>
+template <typename T, int BN, int TAPS, bool DEEP, bool ASYNC, bool S2 = false>
 static int launch_v(Params &p, const void *w_packed, const void *w2_packed, cudaStream_t st) {
-    using C = Cfg<BN, TAPS, DEEP>;
+    using C = Cfg<BN, TAPS, DEEP, S2>;
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("sige_tile_conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
@@ -972,7 +1081,7 @@ static int launch_v(Params &p, const void *w_packed, const void *w2_packed, cuda
             return 2;
         }
     }
-    auto kern = tile_conv_tc5_kernel<T, BN, TAPS, DEEP, ASYNC>;
+    auto kern = tile_conv_tc5_kernel<T, BN, TAPS, DEEP, ASYNC, S2>;
     static int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -985,7 +1094,7 @@ static int launch_v(Params &p, const void *w_packed, const void *w2_packed, cuda
         attr_dev = dev;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ceil_div(p.NT, TILES), p.Cout / BN, p.ksplit);
+    cfg.gridDim = dim3(ceil_div(p.NT, C::CT), p.Cout / BN, p.ksplit);
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
@@ -1032,9 +1141,16 @@ extern "C" int sige_debug_set_trace(void *buf) {
     return 0;
 }
 
-// Can the tcgen05 kernel take this layer?  (3x3 stride 1 on 6x6 tiles, or 1x1 on 4x4 tiles; Cout % 64 == 0)
+// stride-2 geometry: 3x3 stride 2 on 5x5 tiles -> 2x2 outputs, pure-copy gather (no pre-op in the gather stage), no fused shortcut
+static bool tc5_is_s2(const sige_tile_conv_t *a) {
+    static int s2_env = getenv("SIGE_TC5_S2") ? atoi(getenv("SIGE_TC5_S2")) : 1;      // A/B knob (0: these layers stay on the mma.sync kernel)
+    return s2_env && a->kH == 3 && a->kW == 3 && a->stride == 2 && a->R == 5 && a->S == 5 && a->n_src2 == 0 && a->scale == nullptr &&
+           a->shift == nullptr && a->act == SIGE_ACT_IDENTITY;
+}
+
+// Can the tcgen05 kernel take this layer?  (3x3 stride 1 on 6x6 tiles, 1x1 on 4x4 tiles, or 3x3 stride 2 on 5x5 tiles; Cout % 64 == 0)
 bool tc5_supported(const sige_tile_conv_t *a) {
-    const bool g3 = a->kH == 3 && a->kW == 3 && a->stride == 1 && a->R == 6 && a->S == 6;
+    const bool g3 = (a->kH == 3 && a->kW == 3 && a->stride == 1 && a->R == 6 && a->S == 6) || tc5_is_s2(a);
     const bool g1 = a->kH == 1 && a->kW == 1 && a->stride == 1 && a->R == 4 && a->S == 4;
     if (a->n_src2 > 0 && !g3) return false;
     // the kernel keeps 32-bit element offsets into its sources
@@ -1043,6 +1159,7 @@ bool tc5_supported(const sige_tile_conv_t *a) {
     for (int i = 0; i < a->n_src; ++i) cmax = a->src[i].C > cmax ? a->src[i].C : cmax;
     if (px * cmax >= (1ll << 31)) return false;
     if ((a->dst_is_stack ? (long long)a->B * a->N * 16 : (long long)a->B * a->dH * a->dW) >= (1ll << 31)) return false;
+    if (tc5_is_s2(a) && a->dst_is_stack) return false;          // (stack outputs of this geometry: mma.sync kernel)
     return (g3 || g1) && a->Cout % 64 == 0 && a->Cin % 64 == 0 && (a->ksplit == 0 || a->ksplit == 1 || a->ksplit == 2 || a->ksplit == 4 || a->ksplit == 8);
 }
 
@@ -1086,8 +1203,13 @@ int tc5_launch(const sige_tile_conv_t *a, cudaStream_t st) {
     p.push_async = push_env;
     p.dealloc_late = late_env;
     p.trace = g_trace;
-    const tc5::Plan pl = tc5::decide(p.NT, p.Cin, p.Cout, p.taps, p.Cin2, a->ksplit);
+    const bool s2 = tc5_is_s2(a);
+    const tc5::Plan pl = tc5::decide(p.NT, p.Cin, p.Cout, p.taps, p.Cin2, a->ksplit, s2);
     p.ksplit = pl.ksplit;
+    if (s2) {
+        if (a->dtype == SIGE_F16) return tc5::launch_v<__half, 64, 9, false, true, true>(p, a->w_packed, a->w2_packed, st);
+        return tc5::launch_v<__nv_bfloat16, 64, 9, false, true, true>(p, a->w_packed, a->w2_packed, st);
+    }
     const bool wide = pl.bn == 128, three = p.taps == 9;
 #define SIGE_TC5(T)                                                                              \
     (wide ? (three ? tc5::launch<T, 128, 9>(p, a->w_packed, a->w2_packed, st) : tc5::launch<T, 128, 1>(p, a->w_packed, a->w2_packed, st)) \
@@ -1107,12 +1229,13 @@ extern "C" int sige_tile_conv_plan(const sige_tile_conv_t *a, sige_tile_conv_pla
     out->path = 0; out->bn = 0; out->ksplit = 0; out->deep_ring = 0; out->grid_x = out->grid_y = out->grid_z = 0;
     if (!((a->flags & SIGE_CONV_TC5) && tc5_supported(a))) return 0;      // mma.sync / CUDA-core paths
     const long long NT = (long long)a->B * a->N;
-    const tc5::Plan pl = tc5::decide(NT, a->Cin, a->Cout, a->kH * a->kW, a->n_src2 > 0 ? a->Cin2 : 0, a->ksplit);
+    const bool s2 = tc5_is_s2(a);
+    const tc5::Plan pl = tc5::decide(NT, a->Cin, a->Cout, a->kH * a->kW, a->n_src2 > 0 ? a->Cin2 : 0, a->ksplit, s2);
     out->path = 1;
     out->bn = pl.bn;
     out->ksplit = pl.ksplit;
     out->deep_ring = pl.deep;
-    out->grid_x = ceil_div(NT, tc5::TILES);
+    out->grid_x = ceil_div(NT, s2 ? tc5::S2_TILES : tc5::TILES);
     out->grid_y = a->Cout / pl.bn;
     out->grid_z = pl.ksplit;
     return 0;

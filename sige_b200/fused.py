@@ -1984,8 +1984,9 @@ class FusedStep:
                 real_m, real_s = mi[:, 0] > ms.none, si[:, 0] > ss.none
                 main_key = torch.where(real_m, (mi[:, 0] + off) * width + (mi[:, 1] + off), torch.full_like(mi[:, 0], -1))
                 sc_key = torch.where(real_s, (si[:, 0] + soff) * width + (si[:, 1] + soff), torch.full_like(si[:, 0], -2))
-                fbuf.copy_((torch.isin(main_key, sc_key) & real_m).to(torch.uint8))
-                stray = (~torch.isin(sc_key, main_key) & real_s).any().to(torch.int32) * 2
+                eq = main_key.view(-1, 1) == sc_key.view(1, -1)       # (torch.isin synchronises; the lists are a few hundred entries)
+                fbuf.copy_((eq.any(1) & real_m).to(torch.uint8))
+                stray = (~eq.any(0) & real_s).any().to(torch.int32) * 2
                 self.async_status.bitwise_or_(stray.view(1))
             for b in low.cached_bufs:
                 b.restore()

@@ -122,7 +122,12 @@ def test_tile_conv_launch_plan_heuristics(cabi_lib):
     assert (p.bn, p.ksplit, p.deep_ring, p.grid_x) == (128, 1, 0, 162)
     p = plan(_conv_desc(16, 512, 1536, 1))                  # qkv of the 16x16 attention block
     assert p.path == 1 and p.bn == 64 and p.ksplit in (1, 2) and p.deep_ring == 0
-    assert plan(_conv_desc(16, 256, 256, 3, stride=2)).path == 0      # stride-2 downsample: mma.sync kernel
+    p = plan(_conv_desc(16, 512, 512, 3, stride=2))                    # stride-2 downsample (5x5 -> 2x2 tiles): tcgen05, 32 tiles per CTA
+    assert (p.path, p.bn, p.deep_ring, p.grid_x, p.grid_y) == (1, 64, 0, 1, 8) and p.ksplit == 8
+    assert plan(_conv_desc(64, 256, 256, 3, stride=2)).grid_x == 2
+    d2 = _conv_desc(16, 256, 256, 3, stride=2)
+    d2.act = 1                                                         # ... a pre-op in the gather stage of that geometry: mma.sync kernel
+    assert plan(d2).path == 0
     assert plan(_conv_desc(16, 96, 128, 3)).path == 0                  # Cin not a multiple of 64
     assert plan(_conv_desc(4, 512, 512, 3, ksplit=2)).ksplit == 2      # an explicit request is honoured
     # sweep

@@ -403,3 +403,49 @@ def test_few_channel_stacks_take_the_tensor_cores(oracle, dtype, cl):
         e = rel_err(got, want)
         assert e <= TOL[dtype], "case %s: rel err %g" % ((M, Ci, Co, R, k), e)
         assert ops.launch_count - before <= 2, "one weight pack + one tensor-core launch"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_tc5_stride2_downsample_vs_oracle(oracle, dtype):
+    """The DDPM Downsample (3x3 stride 2 on 5x5 tiles -> 2x2 outputs, reference sige_fused_unet.py:212-221) on the tcgen05 kernel:
+    32 tiles per CTA, halo rows as even / odd planes.  Pure-copy gather (this geometry has no pre-op in the model), ragged image
+    edges (odd extents: tiles overhang), more and fewer tiles than one CTA holds, batch 2, a channel-concatenated source, residual,
+    every split-K factor; and the plan really is the tcgen05 path."""
+    from ctypes import byref
+
+    from sige_b200 import _cabi, ops
+
+    rng = np.random.default_rng(21)
+    for (B, C, Co, H, W, p, two) in [(1, 128, 128, 64, 64, 0.03, False), (1, 256, 256, 32, 32, 1.0, False), (2, 64, 192, 33, 41, 0.1, False),
+                                     (1, 512, 512, 16, 16, 1.0, False), (1, 128, 64, 40, 24, 0.3, True), (1, 64, 64, 8, 8, 0.02, False)]:
+        bs, ts, k, s, off = 5, 4, 3, 2, 0
+        mask = rng.random((H, W)) < p
+        mask[0, 0] = mask[H - 1, W - 1] = True
+        idx = oracle.reduce_mask(mask, bs, ts, off)
+        x = _round(rng.standard_normal((B, C, H, W)).astype(np.float32), dtype)
+        w = _round(rng.standard_normal((Co, C, k, k)).astype(np.float32) / np.sqrt(C * k * k), dtype)
+        b = rng.standard_normal((Co,)).astype(np.float32)
+        Ho, Wo = (H + 1 - k) // 2 + 1, (W + 1 - k) // 2 + 1
+        y = _round(rng.standard_normal((B, Co, Ho, Wo)).astype(np.float32), dtype)
+        res = _round(rng.standard_normal((B, Co, Ho, Wo)).astype(np.float32), dtype)
+        g = oracle.gather(x, bs, bs, idx, None, None, "identity", False)
+        want = oracle.scatter(oracle.conv2d_tiles(g, w, b, (s, s)), y, off, off, s, s, idx, res)
+        out = T(y, dtype, cl=True).clone(memory_format=torch.channels_last)
+        tx = T(x, dtype, cl=True)
+        if two:        # torch.cat([a, b], 1) as two sources
+            xa, xb = tx[:, :C // 2].contiguous(memory_format=torch.channels_last), tx[:, C // 2:].contiguous(memory_format=torch.channels_last)
+            d = _fused_desc(ops, xa, ops.pack_conv_weight(T(w, dtype), dtype), T(b), T(idx), out, R=bs, k=k, stride=s, off=off,
+                            residual=T(res, dtype, cl=True), x2=xb)
+        else:
+            d = _fused_desc(ops, tx, ops.pack_conv_weight(T(w, dtype), dtype), T(b), T(idx), out, R=bs, k=k, stride=s, off=off,
+                            residual=T(res, dtype, cl=True))
+        d.flags, d.ksplit = TC5, 0
+        plan = _cabi.TileConvPlan()
+        assert _cabi.lib().sige_tile_conv_plan(byref(d), byref(plan)) == 0 and plan.path == 1 and plan.grid_x == -(-B * idx.shape[0] // 32)
+        for ks, flags in ((0, TC5), (1, TC5), (2, TC5), (4, TC5), (8, TC5), (0, TC5 | 1), (0, 0)):
+            out.copy_(T(y, dtype, cl=True))
+            d.ksplit, d.flags = ks, flags
+            ops.launch_tile_conv(d, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            e = rel_err(out, want)
+            assert e <= 2 * TOL[dtype], "stride-2 case %s ksplit %d flags %d: rel err %g" % ((B, C, Co, H, W), ks, flags, e)
