@@ -520,45 +520,25 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         // ================= A-operand producers: gather + pre-op + swizzled stores =================
         const int ptid = tid - 64;
         if constexpr (S2) {
-            // ---- stride-2 geometry: 32 tiles x 5x5 halo pixels x 8 units = 6400 sixteen-byte copies per chunk (25 per thread),
-            //      pure copy with cp.async straight into the plane layout described at S2_TILES.  Only the source offsets are
-            //      resolved ahead (in the prologue, overlapping the previous layer); destinations are recomputed per chunk.
-            int g_off[LOADS];
-            int g_sg = -1;
-            auto decode = [&](int q, int &x, int &y, int &tl) {
-                const int pix = q >> 3;
-                tl = pix / RS;
-                const int rem = pix - tl * RS;
-                y = rem / R;
-                x = rem - y * R;
-            };
-            auto resolve = [&](int sg) {
-                const Seg &seg = p.seg[sg];
-                const int Hs = p.H >> seg.up, Ws = p.W >> seg.up;
-#pragma unroll
-                for (int k = 0; k < LOADS; ++k) {
-                    const int q = ptid + k * NPROD;
-                    g_off[k] = -2;
-                    if (q < UNITS) {
-                        g_off[k] = -1;
-                        int x, y, tl;
-                        decode(q, x, y, tl);
-                        const int t = tile0 + tl;
-                        if (t < p.NT) {
-                            int hh = y, ww = x, img = t;
-                            if (!p.src_is_stack) {
-                                hh += s_idx[2 * tl];
-                                ww += s_idx[2 * tl + 1];
-                                img = (p.NT != p.N) ? t / p.N : 0;
-                            }
-                            if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
-                                g_off[k] = ((img * Hs + (hh >> seg.up)) * Ws + (ww >> seg.up)) * seg.C + (q & 7) * 8;
-                        }
-                    }
-                }
-                g_sg = sg;
-            };
-            resolve(c_first * KC >= p.C0 ? 1 : 0);
+            // ---- stride-2 geometry: 32 tiles x 5x5 halo pixels x 8 units = 6400 sixteen-byte copies per chunk, pure copy with
+            //      cp.async straight into the plane layout described at S2_TILES.  Thread -> (tile = ptid / 8, unit = ptid % 8), and
+            //      it walks the 25 pixels of ITS tile: pixel coordinates, planes and destination rows are compile-time constants of
+            //      the unrolled loop, per-thread state is the tile origin and two swizzled row offsets.  (A first version kept 25
+            //      resolved source offsets per thread: 92 bytes spilled, re-read through a ~20 KB L1 that the gather itself
+            //      thrashes — 12-15 us per chunk, profiles/r02b_graph_timeline_s2_spill.txt.)
+            static_assert(NPROD == S2_TILES * 8 && UNITS == NPROD * RS, "one (tile, unit) per producer thread");
+            const int tl = ptid >> 3, u = ptid & 7;
+            const int t = tile0 + tl;
+            const bool live = t < p.NT;
+            int hh0 = 0, ww0 = 0, img = t;
+            if (!p.src_is_stack) {
+                hh0 = s_idx[2 * tl];
+                ww0 = s_idx[2 * tl + 1];
+                img = (p.NT != p.N) ? t / p.N : 0;
+            }
+            // destination of (plane 0, ox): row = tile*2 + ox, 16-byte chunk u XOR-swizzled by the row
+            const uint32_t d_ox0 = sbase + C::OFF_A + (tl * 2) * 128 + ((u ^ ((tl * 2) & 7)) << 4);
+            const uint32_t d_ox1 = sbase + C::OFF_A + (tl * 2 + 1) * 128 + ((u ^ ((tl * 2 + 1) & 7)) << 4);
             if (ptid == 0) SIGE_TRACE(2);
             if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");   // activations of the previous layer are complete
             int ause = 0;
@@ -568,25 +548,24 @@ tile_conv_tc5_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 const int cbase = c * KC;
                 const int sg = cbase >= p.C0 ? 1 : 0;
                 const Seg &seg = p.seg[sg];
-                const int cl = cbase - (sg ? p.C0 : 0);
-                if (sg != g_sg) resolve(sg);
-                const uint32_t abase = sbase + C::OFF_A;
+                const int Hs = p.H >> seg.up, Ws = p.W >> seg.up;
+                const T *sbase_p = reinterpret_cast<const T *>(seg.ptr) + (cbase - (sg ? p.C0 : 0)) + u * 8;
 #pragma unroll
-                for (int k = 0; k < LOADS; ++k) {
-                    if (g_off[k] == -2) continue;
-                    const bool ok = g_off[k] >= 0;
-                    const T *src = reinterpret_cast<const T *>(seg.ptr) + (ok ? g_off[k] + cl : 0);
-                    const uint32_t nb = ok ? 16u : 0u;
-                    const int q = ptid + k * NPROD, u = q & 7;
-                    int x, y, tl;
-                    decode(q, x, y, tl);
+                for (int y = 0; y < R; ++y) {
+                    const int hh = hh0 + y;
+                    const bool row_ok = live && hh >= 0 && hh < p.H;
+                    const long long rbase = ((long long)img * Hs + (hh >> seg.up)) * Ws;
                     const int plane = (y & 1) ? 3 + (y >> 1) : (y >> 1);
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int xp = x - kx;
-                        if (xp == 0 || xp == 2) {
-                            const int row = plane * 64 + tl * 2 + (xp >> 1);
-                            cp_async16(abase + kx * A_COPY_BYTES + row * 128 + ((u ^ (row & 7)) << 4), src, nb);
+                    for (int x = 0; x < R; ++x) {
+                        const int ww = ww0 + x;
+                        const bool ok = row_ok && ww >= 0 && ww < p.W;
+                        const T *src = ok ? sbase_p + (rbase + (ww >> seg.up)) * seg.C : reinterpret_cast<const T *>(seg.ptr);
+                        const uint32_t nb = ok ? 16u : 0u;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int xp = x - kx;
+                            if (xp == 0 || xp == 2) cp_async16((xp == 0 ? d_ox0 : d_ox1) + kx * A_COPY_BYTES + plane * (64 * 128), src, nb);
                         }
                     }
                 }
