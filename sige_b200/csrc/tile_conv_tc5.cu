@@ -117,15 +117,19 @@ template <int BN, int TAPS, bool DEEP = false, bool S2 = false> struct Cfg {
     static constexpr int SPC = TAPS / TPS;                     // ring steps per 64-channel chunk
     static constexpr int B_TILE_BYTES = BN * 128;              // one (tap, chunk) weight tile
     static constexpr int B_STAGE_BYTES = TPS * B_TILE_BYTES;
-    static constexpr int NSTB = S2 ? 3 : DEEP ? 5 : ((BN == 128) ? 4 : (TPS == 3 ? 2 : 4));   // weight ring depth (72 / 120 / 48 / 32 / 64 KB in flight per CTA)
+    // The narrow 3x3 configuration WITHOUT the deep ring is only launched un-split (decide(): every split launch takes the deep
+    // ring), so its split-K exchange slots are never used: their 30 KB hold a third weight stage instead (un-split launches are
+    // the ones with long K loops per CTA, i.e. weight-ring bound: 72 KB in flight instead of 48).
+    static constexpr bool kUnsplit39 = (BN == 64 && TAPS == 9 && !DEEP && !S2);
+    static constexpr int NSTB = S2 ? 3 : DEEP ? 5 : ((BN == 128) ? 4 : (TPS == 3 ? 3 : 4));   // weight ring depth (72 / 120 / 64 / 72 / 32 KB in flight per CTA)
     static constexpr int EPI_PITCH = BN + EPI_PAD;             // floats
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = NAB * A_BUF;
     // split-K (BN = 64 only): partial-tile rows pushed by the other ranks of the cluster land here — a region that no
     // mainloop touches, so a fast rank may push while this CTA is still multiplying.  <= 7 remote ranks x 16 rows.
     static constexpr int OFF_SLOT = OFF_B + NSTB * B_STAGE_BYTES;
-    static constexpr int SLOT_BYTES = (BN == 64) ? 112 * EPI_PITCH * 4 : 0;
-    static constexpr bool kSplitOk = (BN == 64);
+    static constexpr int SLOT_BYTES = (BN == 64 && !kUnsplit39) ? 112 * EPI_PITCH * 4 : 0;
+    static constexpr bool kSplitOk = (BN == 64 && !kUnsplit39);
     static constexpr int OFF_BAR = OFF_SLOT + SLOT_BYTES;
     static constexpr int OFF_CONST = OFF_BAR + 256;            // idx[CT][2] ints + CT shortcut flags, then bias | aux0 scale,shift | aux1 scale,shift | bias2
     static constexpr int OFF_FLAGS = OFF_CONST + CT * 8;
@@ -1025,7 +1029,7 @@ static Plan decide(long long NT, int Cin, int Cout, int taps, int Cin2, int kspl
     static int deep_env = getenv("SIGE_TC5_DEEP") ? atoi(getenv("SIGE_TC5_DEEP")) : 1;   // A/B knob
     // (2 = also for un-split launches: with the cp.async gather a single halo buffer costs 0.65 us of exposed gather per chunk,
     //  while two weight stages — 48 KB in flight — cap the weight ring at ~1.5 us per chunk; an A/B knob)
-    pl.deep = (!s2 && pl.bn == 64 && taps == 9 && deep_env && (ks > 1 || deep_env >= 2)) ? 1 : 0;
+    pl.deep = (!s2 && pl.bn == 64 && taps == 9 && (ks > 1 || deep_env >= 2)) ? 1 : 0;       // (split launches: always — Cfg::kUnsplit39)
     return pl;
 }
 
