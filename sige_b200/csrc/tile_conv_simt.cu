@@ -10,6 +10,8 @@
 // tile and the matching weight slab are staged in shared memory; a warp shares one output
 // pixel group, so activation reads are smem broadcasts and weight reads are conflict-free
 // (row pitch padded to an odd number of words).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sige {
@@ -99,6 +101,76 @@ tile_conv_simt_kernel(SimtParams p, const T *__restrict__ x, const T *__restrict
     }
 }
 
+// Depthwise form (groups == Cin == Cout: GauGAN's separable convolutions, reference gaugan/models/mobile_modules.py:83-91).  The
+// generic kernel above gives one CTA of 256 threads to each (tile, channel) and uses one of them; here a thread owns one
+// output pixel of one channel (NCHW) or of 8 / 4 adjacent channels (NHWC: 16-byte vectors, neighbouring threads = neighbouring
+// channel vectors, so every tap is a coalesced row read that L1 serves for the other taps).  Same arithmetic: fp32 fmaf in
+// (ky, kx) order.
+template <typename T>
+__global__ void __launch_bounds__(256) tile_conv_depthwise_kernel(SimtParams p, const T *__restrict__ x, const T *__restrict__ w,
+                                                                  const T *__restrict__ bias, T *__restrict__ out) {
+    constexpr int V = DT<T>::vec;
+    if (p.nhwc == 1) {
+        const int CV = p.Cin / V;
+        const long long total = (long long)p.M * p.P * CV;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int cv = (int)(i % CV);
+            const long long mp = i / CV;
+            const int pp = (int)(mp % p.P);
+            const long long m = mp / p.P;
+            const int oy = pp / p.So, ox = pp - oy * p.So;
+            const int c0 = cv * V;
+            float acc[V];
+#pragma unroll
+            for (int z = 0; z < V; ++z) acc[z] = bias ? DT<T>::to_f(bias[c0 + z]) : 0.f;
+            float part[V];
+#pragma unroll
+            for (int z = 0; z < V; ++z) part[z] = 0.f;
+            for (int ky = 0; ky < p.kH; ++ky)
+                for (int kx = 0; kx < p.kW; ++kx) {
+                    const int pix = (oy * p.strideH + ky * p.dilH) * p.S + ox * p.strideW + kx * p.dilW;
+                    const Vec16<T> xv = *reinterpret_cast<const Vec16<T> *>(x + (m * p.RS + pix) * p.Cin + c0);
+#pragma unroll
+                    for (int z = 0; z < V; ++z)
+                        part[z] = fmaf(DT<T>::to_f(xv.v[z]), DT<T>::to_f(w[(long long)(c0 + z) * p.taps + ky * p.kW + kx]), part[z]);
+                }
+            Vec16<T> o;
+#pragma unroll
+            for (int z = 0; z < V; ++z) o.v[z] = DT<T>::from_f(part[z] + acc[z]);
+            *reinterpret_cast<Vec16<T> *>(out + (m * p.P + pp) * p.Cout + c0) = o;
+        }
+        return;
+    }
+    const long long total = (long long)p.M * p.Cin * p.P;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int pp, c;
+        long long m;
+        if (p.nhwc) { c = (int)(i % p.Cin); pp = (int)((i / p.Cin) % p.P); m = i / ((long long)p.Cin * p.P); }
+        else { pp = (int)(i % p.P); c = (int)((i / p.P) % p.Cin); m = i / ((long long)p.P * p.Cin); }
+        const int oy = pp / p.So, ox = pp - oy * p.So;
+        float acc = 0.f;
+        for (int ky = 0; ky < p.kH; ++ky)
+            for (int kx = 0; kx < p.kW; ++kx) {
+                const int pix = (oy * p.strideH + ky * p.dilH) * p.S + ox * p.strideW + kx * p.dilW;
+                const long long src = p.nhwc ? ((m * p.RS + pix) * p.Cin + c) : ((m * p.Cin + c) * p.RS + pix);
+                acc = fmaf(DT<T>::to_f(x[src]), DT<T>::to_f(w[(long long)c * p.taps + ky * p.kW + kx]), acc);
+            }
+        const long long dst = p.nhwc ? ((m * p.P + pp) * p.Cout + c) : ((m * p.Cout + c) * p.P + pp);
+        out[dst] = DT<T>::from_f(acc + (bias ? DT<T>::to_f(bias[c]) : 0.f));
+    }
+}
+
+template <typename T>
+static int launch_depthwise(const SimtParams &p, const void *x, const void *w, const void *bias, void *out, cudaStream_t st) {
+    SimtParams q = p;
+    const bool vec = p.nhwc && p.Cin % DT<T>::vec == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    q.nhwc = p.nhwc ? (vec ? 1 : 2) : 0;          // 1 = NHWC with 16-byte channel vectors, 2 = NHWC scalar, 0 = NCHW scalar
+    const long long items = vec ? (long long)p.M * p.P * (p.Cin / DT<T>::vec) : (long long)p.M * p.Cin * p.P;
+    const int blocks = (int)std::min<long long>((items + 255) / 256, 148LL * 16);
+    tile_conv_depthwise_kernel<T><<<blocks, 256, 0, st>>>(q, (const T *)x, (const T *)w, (const T *)bias, (T *)out);
+    return check_launch("sige_tile_conv_generic(depthwise)");
+}
+
 template <typename T>
 static int launch_simt(const SimtParams &p, const void *x, const void *w, const void *bias, void *out, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)SIMT_CI * p.RS + (size_t)SIMT_CO * (SIMT_CI * p.taps + 1));
@@ -140,6 +212,14 @@ extern "C" int sige_tile_conv_generic(const void *x, const void *w, const void *
     p.nhwc = layout == SIGE_NHWC;
     SIGE_REQUIRE(groups <= 65535 && ceil_div(p.cog, SIMT_CO) <= 65535, "sige_tile_conv_generic: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
+    if (groups == Cin && Cout == Cin) {            // depthwise: one thread per output (vector), not one CTA per (tile, channel)
+        switch (dtype) {
+            case SIGE_F32: return launch_depthwise<float>(p, x, w, bias, out, st);
+            case SIGE_F16: return launch_depthwise<__half>(p, x, w, bias, out, st);
+            case SIGE_BF16: return launch_depthwise<__nv_bfloat16>(p, x, w, bias, out, st);
+            default: set_error("sige_tile_conv_generic: unsupported dtype %d", dtype); return 1;
+        }
+    }
     switch (dtype) {
         case SIGE_F32: return launch_simt<float>(p, x, w, bias, out, st);
         case SIGE_F16: return launch_simt<__half>(p, x, w, bias, out, st);

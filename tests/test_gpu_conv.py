@@ -37,8 +37,11 @@ def test_generic_conv_fp32_exact(oracle, cl):
     from sige_b200 import ops
 
     rng = np.random.default_rng(1)
+    # (groups == Cin == Cout: the depthwise kernel — GauGAN's separable convs, gaugan/models/mobile_modules.py:83-91 — in its
+    #  16-byte-vector NHWC form (Cin % 4 == 0 for fp32), its scalar NHWC form (Cin = 6) and its NCHW form)
     for (M, Ci, Co, R, k, s, d, g) in [(5, 8, 12, 6, 3, 1, 1, 1), (3, 16, 16, 5, 3, 2, 1, 1), (4, 12, 12, 6, 3, 1, 1, 12), (7, 36, 70, 6, 3, 1, 1, 1),
-                                       (2, 36, 20, 4, 1, 1, 1, 1), (3, 8, 8, 7, 3, 1, 2, 2), (64, 64, 64, 6, 3, 1, 1, 1), (2, 3, 5, 10, 3, 1, 1, 1)]:
+                                       (2, 36, 20, 4, 1, 1, 1, 1), (3, 8, 8, 7, 3, 1, 2, 2), (64, 64, 64, 6, 3, 1, 1, 1), (2, 3, 5, 10, 3, 1, 1, 1),
+                                       (300, 128, 128, 6, 3, 1, 1, 128), (9, 6, 6, 5, 3, 2, 1, 6), (5, 64, 64, 8, 3, 1, 2, 64)]:
         x = rng.standard_normal((M, Ci, R, R)).astype(np.float32)
         w = rng.standard_normal((Co, Ci // g, k, k)).astype(np.float32) / np.sqrt(Ci // g * k * k)
         b = rng.standard_normal((Co,)).astype(np.float32)
@@ -59,6 +62,12 @@ def test_generic_conv_half(oracle, dtype):
     b = _round(rng.standard_normal((48,)).astype(np.float32), dtype)
     want = oracle.conv2d_tiles(x, w, b)
     assert rel_err(ops.tile_conv_generic(T(x, dtype), T(w, dtype), T(b, dtype), (1, 1), (1, 1), 1), want) <= TOL[dtype]
+    for cl in (False, True):            # depthwise
+        xd = _round(rng.standard_normal((40, 96, 6, 6)).astype(np.float32), dtype)
+        wd = _round(rng.standard_normal((96, 1, 3, 3)).astype(np.float32) / 3, dtype)
+        bd = _round(rng.standard_normal((96,)).astype(np.float32), dtype)
+        got = ops.tile_conv_generic(T(xd, dtype, cl=cl), T(wd, dtype), T(bd, dtype), (1, 1), (1, 1), 96)
+        assert rel_err(got, oracle.conv2d_tiles(xd, wd, bd, (1, 1), (1, 1), 96)) <= TOL[dtype]
 
 
 STACK_CASES = [  # M, Cin, Cout, R, k, stride  — DDPM shape classes + edge sizes
