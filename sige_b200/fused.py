@@ -599,6 +599,51 @@ _VIEW_OPS = {"reshape", "view", "permute", "transpose", "chunk", "split", "__get
              "expand", "narrow", "select", "unbind", "t", "movedim", "swapaxes", "view_as", "reshape_as", "T.__get__", "mT.__get__"}
 
 
+def _bits(t: torch.Tensor) -> torch.Tensor:
+    """Bit pattern of a tensor (NaN-safe equality)."""
+    if t.dtype in (torch.float16, torch.bfloat16):
+        return t.contiguous().view(torch.int16)
+    if t.dtype == torch.float32:
+        return t.contiguous().view(torch.int32)
+    return t
+
+
+def _out_variant(name: str, op):
+    """out= form of a recorded torch call: f(args, kwargs, dst) writes the call's result into dst, or None if there is none.
+    Only calls whose out= overload computes exactly what the recorded call computes under autocast on 16-bit operands."""
+    if name in ("add", "mul") and op in (torch.add, torch.mul, torch.Tensor.add, torch.Tensor.mul, torch.Tensor.__add__, torch.Tensor.__mul__,
+                                         torch.Tensor.__radd__, torch.Tensor.__rmul__):
+        fn = torch.add if name == "add" else torch.mul
+        return lambda args, kwargs, dst: fn(*args, **kwargs, out=dst)
+    if name == "linear" and op is F.linear:
+        def linear(args, kwargs, dst):
+            kw = dict(zip(("input", "weight", "bias"), args))
+            kw.update(kwargs)
+            x, w, b = kw["input"], kw["weight"], kw.get("bias")
+            if not (x.dtype == w.dtype == dst.dtype and x.dtype in (torch.float16, torch.bfloat16) and (b is None or b.dtype == x.dtype)
+                    and x.is_contiguous() and dst.is_contiguous()):
+                raise TypeError("linear: not the plain 16-bit case")
+            x2, d2 = x.view(-1, x.shape[-1]), dst.view(-1, dst.shape[-1])
+            if b is None:
+                torch.mm(x2, w.t(), out=d2)
+            else:
+                torch.addmm(b, x2, w.t(), out=d2)
+        return linear
+    if name == "gelu" and op is F.gelu:
+        return lambda args, kwargs, dst: torch._C._nn.gelu(*args, **kwargs, out=dst)
+    if name == "silu" and op is F.silu:
+        return lambda args, kwargs, dst: torch._C._nn.silu(args[0], out=dst) if not kwargs.get("inplace", False) and len(args) == 1 else (_ for _ in ()).throw(TypeError())
+    if name == "leaky_relu" and op is F.leaky_relu:
+        def leaky(args, kwargs, dst):
+            kw = dict(zip(("input", "negative_slope", "inplace"), args))
+            kw.update(kwargs)
+            if kw.get("inplace", False):
+                raise TypeError("in-place")
+            torch._C._nn.leaky_relu(kw["input"], kw.get("negative_slope", 0.01), out=dst)
+        return leaky
+    return None
+
+
 def _is_const(o) -> bool:
     return isinstance(o, torch.Tensor) and not isinstance(o, LazyTensor)
 
@@ -1118,9 +1163,19 @@ class Lowering:
         use_autocast = self.dev.type == "cuda" and self.dtype in (torch.float16, torch.bfloat16) and not is_module_call
         dev_type, ac_dtype = self.dev.type, self.dtype
 
+        # The result of a recorded call has to live at a stable address (fused launches hold raw pointers), so by default it is
+        # COPIED into its persistent tensor: one extra launch per recorded call (9 % of the full-size SD step).  The common calls
+        # have an out= form that writes there directly; it is adopted per node only after the first (warm-up) run has checked,
+        # on the real data, that it reproduces the recorded call bit for bit.
+        fast = None if (is_module_call or multi or len(outs) != 1) else _out_variant(node.name, op)
+        state = {"mode": 0 if fast is not None else 2}        # 0 undecided, 1 out= form, 2 call + copy
+
         def run(_stream):
             args = lazy._tree_map(sub, node.args)
             kwargs = lazy._tree_map(sub, node.kwargs)
+            if state["mode"] == 1:
+                fast(args, kwargs, outs[0])
+                return
             with torch.autocast(device_type=dev_type, dtype=ac_dtype, enabled=use_autocast):
                 if isinstance(op, str):
                     res = module(*args)
@@ -1129,6 +1184,16 @@ class Lowering:
             res = list(res) if multi else [res]
             for dst, r in zip(outs, [r for r in res if isinstance(r, torch.Tensor)]):
                 dst.copy_(r)
+            if state["mode"] == 0:
+                ok = False
+                if not (dev_type == "cuda" and torch.cuda.is_current_stream_capturing()):
+                    try:
+                        tmp = torch.empty_strided(tuple(outs[0].shape), tuple(outs[0].stride()), dtype=outs[0].dtype, device=outs[0].device)
+                        fast(args, kwargs, tmp)
+                        ok = tmp.dtype == outs[0].dtype and bool(torch.equal(_bits(tmp), _bits(outs[0])))
+                    except Exception:  # noqa: BLE001  (dtype promotion the out= form refuses, unsupported overload, ...)
+                        ok = False
+                state["mode"] = 1 if ok else 2
 
         self.steps.append(("eager", run))
         self.eager_nodes.append(node.name)
