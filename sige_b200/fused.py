@@ -594,6 +594,7 @@ class HeadsOut:
         return self.full.view(self.b, self.n, self.h, self.d).permute(0, 2, 1, 3)
 
 
+_POINTWISE = {"add", "mul", "sub", "div", "rsub", "neg", "leaky_relu", "relu", "silu", "gelu", "sigmoid", "tanh", "clamp", "clamp_min", "abs"}
 _MATERIAL = (Full, Stack, RealStack, ConvOut, RealT)
 _VIEW_OPS = {"reshape", "view", "permute", "transpose", "chunk", "split", "__getitem__", "unsqueeze", "squeeze", "flatten", "unflatten",
              "expand", "narrow", "select", "unbind", "t", "movedim", "swapaxes", "view_as", "reshape_as", "T.__get__", "mT.__get__"}
@@ -1127,12 +1128,24 @@ class Lowering:
         if not is_module_call and node.name in _VIEW_OPS and self._static_view(node, getters):
             return
         outs = []
+        # Pointwise math between fused layers (SPADE's x*(1+gamma)+beta, leaky_relu, ...: GauGAN) keeps the layout of its operands:
+        # when every 4-D operand is an NHWC buffer / stack the result is allocated channels-last too, so the fused launch that
+        # reads it needs no NCHW -> NHWC copy (53 such copies per full-size GauGAN step).  Ops that depend on the recorded strides
+        # (`view`, operator modules) still get their operands in the recorded layout (see `sub`).
+        big = [g for g in getters.values() if g.dim() == 4]
+        follow_nhwc = (not is_module_call and node.name in _POINTWISE and len(big) > 0
+                       and all(g.is_contiguous(memory_format=torch.channels_last) and not g.is_contiguous() or g.shape[1] == 1 or g.shape[2:] == (1, 1)
+                               for g in big)
+                       and any(g.is_contiguous(memory_format=torch.channels_last) and not g.is_contiguous() for g in big))
         for o in node.outs:
             with torch._C.DisableTorchFunctionSubclass():
                 st = tuple(o.stride())
             # the recorded memory layout: later `view`s of this value were validated against exactly these strides
             act_like = o.dtype.is_floating_point and o.dim() >= 3
-            outs.append(torch.empty_strided(tuple(o.shape), st, dtype=self.dtype if act_like else o.dtype, device=self.dev))
+            if follow_nhwc and o.dim() == 4:
+                outs.append(torch.empty(tuple(o.shape), dtype=self.dtype if act_like else o.dtype, device=self.dev, memory_format=torch.channels_last))
+            else:
+                outs.append(torch.empty_strided(tuple(o.shape), st, dtype=self.dtype if act_like else o.dtype, device=self.dev))
 
         # Precision of a recorded call (mixed-precision steps: fp32 model, fp16/bf16 step): it runs under autocast — GEMM-like
         # ops on the tensor cores in the step's dtype, softmax / norms / transcendental math in fp32 — on the tensors as they

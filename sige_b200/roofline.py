@@ -256,7 +256,8 @@ def measure_in_graph(model, args, options, flush, reps: int = 5):
     return {
         "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
         "traffic": traffic, "traffic_source": ("profiles/%s (ncu capture of `bench.py --ncu`, same kernel build; not measured in this run)" % TRAFFIC_CAPTURE) if traffic else None,
-        "kernel": "sige::tc5::tile_conv_tc5_kernel (%d of the %d fused gather-conv-scatter launches of one step; the rest run on mma.sync)" % (len(traced), len(ctas)),
+        "kernel": "sige::tc5::tile_conv_tc5_kernel (%d of the %d fused gather-conv-scatter launches of one step%s)" % (
+            len(traced), len(ctas), "" if len(traced) == len(ctas) else "; the rest run on mma.sync"),
         "launches": len(traced), "avg_launch_us": tot_us / max(1, len(traced)), "sum_in_graph_us": tot_us,
         "first_start_to_last_end_us": sorted(first_last)[len(first_last) // 2] if first_last else None,
         "algorithmic_bytes_per_launch": tot_bytes / max(1, len(traced)), "algorithmic_bytes_per_step": float(step.algorithmic_bytes()),
