@@ -20,7 +20,7 @@ from .nn import SIGEConv2d
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-TRAFFIC_CAPTURE = "r02_tileconv_dram_traffic_step.csv"      # ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of `bench.py --ncu`
+TRAFFIC_CAPTURE = "r02b_tileconv_dram_traffic_step.csv"      # ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of `bench.py --ncu`
 
 
 def peaks():
