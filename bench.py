@@ -105,6 +105,7 @@ def parse():
 class ClockSampler:
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.interval = float(os.environ.get("SIGE_BENCH_SAMPLE_S", "0.01"))       # NVML polling period
         self._stop = threading.Event()
         self._thr = None
         try:
@@ -138,7 +139,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(self.interval)
 
     def start(self):
         if self.nv is not None:

@@ -1133,10 +1133,12 @@ class Lowering:
         # reads it needs no NCHW -> NHWC copy (53 such copies per full-size GauGAN step).  Ops that depend on the recorded strides
         # (`view`, operator modules) still get their operands in the recorded layout (see `sub`).
         big = [g for g in getters.values() if g.dim() == 4]
-        follow_nhwc = (not is_module_call and node.name in _POINTWISE and len(big) > 0
-                       and all(g.is_contiguous(memory_format=torch.channels_last) and not g.is_contiguous() or g.shape[1] == 1 or g.shape[2:] == (1, 1)
-                               for g in big)
-                       and any(g.is_contiguous(memory_format=torch.channels_last) and not g.is_contiguous() for g in big))
+
+        def nhwc_like(g):      # channels innermost (an NHWC buffer / stack, or a channel slice of one: torch.split(gamma_beta, C, dim=1))
+            return g.shape[1] > 1 and g.shape[2] * g.shape[3] > 1 and g.stride(1) == 1
+
+        follow_nhwc = (not is_module_call and node.name in _POINTWISE and any(nhwc_like(g) for g in big)
+                       and all(nhwc_like(g) or g.shape[1] == 1 or tuple(g.shape[2:]) == (1, 1) for g in big))
         for o in node.outs:
             with torch._C.DisableTorchFunctionSubclass():
                 st = tuple(o.stride())
