@@ -1864,10 +1864,12 @@ class Lowering:
         buf = q.buf
         B, C3, H, W = buf.shape
         C = q.c1 - q.c0
-        if not (self.fused_attention and k.buf is buf and vv.buf is buf and (q.c0, k.c0, vv.c0) == (0, C, 2 * C) and C3 == 3 * C):
+        if not self.fused_attention:
             return False
-        if not self.ex.attention_supported(H * W, C) or len(buf.producers) != 1 or not isinstance(buf.producers[0], FusedConv):
-            return False
+        cluster_ok = (k.buf is buf and vv.buf is buf and (q.c0, k.c0, vv.c0) == (0, C, 2 * C) and C3 == 3 * C
+                      and self.ex.attention_supported(H * W, C) and len(buf.producers) == 1 and isinstance(buf.producers[0], FusedConv))
+        if not cluster_ok:
+            return self._emit_attention_generic(out, v)
         prod: FusedConv = buf.producers[0]
         if prod.spec.out_row_scale is not None or prod.spec.aux or any(r is None for r in buf.readers):
             return False
@@ -1879,6 +1881,30 @@ class Lowering:
         tok = buf.raw.permute(0, 2, 3, 1).reshape(B, H * W, 3 * C)
         o_tok = dst.raw.permute(0, 2, 3, 1).reshape(B, H * W, C)
         self.steps.append(("attention", self.ex.prepare_attention(tok, o_tok, self.pdl)))
+        self.env[id(out)] = Full([(dst, 0)])
+        return True
+
+    def _emit_attention_generic(self, out: LazyTensor, v: AttnOut) -> bool:
+        """Single-head attention core outside the cluster kernel's range (token count / channel count): the flash-style
+        `sige_sparse_attention` on the channel slices of the NHWC buffers, addressed in place — q, k, v = [B, 1, H*W, C] views with
+        the token stride of their buffer, the result written as NHWC tokens of a fresh buffer."""
+        q, k, vv = v.s.q, v.s.k, v.v
+        C = q.c1 - q.c0
+        B, _, H, W = q.buf.shape
+        if not (self.sparse_attention and k.c1 - k.c0 == C and vv.c1 - vv.c0 == C and k.buf.shape[0] == B and vv.buf.shape[0] == B
+                and tuple(k.buf.shape[2:]) == tuple(vv.buf.shape[2:]) and v.s.scale > 0 and self.ex.sparse_attention_supported(C)
+                and all(sl.c0 % 8 == 0 and sl.buf.shape[1] % 8 == 0 for sl in (q, k, vv))):
+            return False
+
+        def tokens(sl):
+            sl.buf.readers.append(None)
+            b, ct, h, w = sl.buf.shape
+            return sl.buf.raw.permute(0, 2, 3, 1).reshape(b, h * w, ct)[:, :, sl.c0:sl.c1].unsqueeze(1)        # [B, 1, N, C], strided view
+
+        dst = self.fresh(B, C, H, W)
+        o_tok = dst.raw.permute(0, 2, 3, 1).reshape(B, H * W, C).unsqueeze(1)
+        self.steps.append(("sparse_attention", self.ex.prepare_sparse_attention(tokens(q), tokens(k), tokens(vv), float(v.s.scale), o_tok)))
+        self.sparse_attention_calls += 1
         self.env[id(out)] = Full([(dst, 0)])
         return True
 
