@@ -76,6 +76,26 @@ def test_attention_shape_predicate_is_pure_host_logic(cabi_lib):
     assert f(100, 512, F16) == 0 and f(512, 512, F16) == 0 and f(256, 192, F16) == 0 and f(0, 512, F16) == 0
 
 
+def test_sparse_attention_predicate_and_argument_checks_need_no_device(cabi_lib):
+    """sige_sparse_attention_supported() is host logic; the entry point validates its descriptor before touching the device
+    (null descriptor, unsupported head dim, misaligned strides) and treats Nq == 0 as a no-op."""
+    from sige_b200 import _cabi
+
+    h = _cabi.lib()
+    F32, F16, BF16 = 0, 1, 2
+    for d in (32, 40, 64, 80, 128, 160):
+        assert h.sige_sparse_attention_supported(d, F16) == 1 and h.sige_sparse_attention_supported(d, BF16) == 1
+    assert h.sige_sparse_attention_supported(40, F32) == 0 and h.sige_sparse_attention_supported(48, F16) == 0 and h.sige_sparse_attention_supported(320, F16) == 0
+    a = _cabi.SparseAttention()
+    a.B, a.heads, a.Nq, a.Nk, a.D, a.dtype, a.scale = 1, 8, 0, 77, 40, F16, 0.158
+    assert h.sige_sparse_attention(ctypes.byref(a), None) == 0            # no query: no-op, pointers not looked at
+    a.D = 48
+    assert h.sige_sparse_attention(ctypes.byref(a), None) != 0 and b"head dim" in h.sige_last_error()
+    a.D, a.Nq = 40, 16
+    assert h.sige_sparse_attention(ctypes.byref(a), None) != 0 and b"null buffer" in h.sige_last_error()
+    assert h.sige_sparse_attention(None, None) != 0
+
+
 def _conv_desc(n_tiles, cin, cout, k, *, stride=1, cin2=0, ksplit=0, res=64):
     from sige_b200 import _cabi
 

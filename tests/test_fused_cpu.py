@@ -102,6 +102,28 @@ def test_eager_islands_keep_the_result_exact():
     assert np.abs(step.output.numpy() - ref).max() / np.abs(ref).max() < 1e-5
 
 
+def test_attention_outside_the_cluster_kernels_range_takes_the_flash_kernel():
+    """The miniature's 128-channel attention cores are below the cluster attention kernel's range (256 / 512 channels): they go out
+    as `sige_sparse_attention` launches on the channel slices of the NHWC qkv buffer — nothing eager (what `smoke()` asserts on
+    the GPU box)."""
+    from sige_b200.fused import FusedStep
+    from sige_b200.workloads.ddpm import DDPMConfig
+    from sim_executor import SimExecutor
+
+    class NoClusterAttention(SimExecutor):
+        def attention_supported(self, n_tokens, channels):
+            return False
+
+    G = golden("ddpm_small_golden.npz")
+    model, x1, t = _prepared("intree", DDPMConfig.small(), float(G["ratio"][0]))
+    with torch.no_grad():
+        step = FusedStep(model, x1, t, executor=NoClusterAttention())
+    kinds = [k for k, _ in step.steps]
+    assert step.eager_nodes == [] and kinds.count("sparse_attention") == 4 and kinds.count("attention") == 0 and len(step.fused) == 34
+    ref = G["sparse_out"]
+    assert np.abs(step.output.numpy() - ref).max() / np.abs(ref).max() < 1e-5
+
+
 def test_foreign_math_on_the_tile_stack_falls_back_per_op():
     """GauGAN-style: plain torch math on the gathered stack between Gather and the conv
     (reference gaugan/models/sige_normalization.py:84-86).  The gather is materialised, the torch ops run as recorded,
