@@ -1436,19 +1436,30 @@ class Lowering:
         co, sc = self.sym(x), self.sym(residual)
         if not (isinstance(co, ConvOut) and isinstance(sc, ConvOut) and co.on_tiles and sc.on_tiles and self.n_uses(x) == 1 and self.n_uses(residual) == 1):
             return False
-        if not (isinstance(co.src, Stack) and isinstance(sc.src, Stack)):
+        # sources: lazy gathers (DDPM) or materialised stacks (GauGAN: SPADE's torch math sits between the Gather and the conv —
+        # reference gaugan/models/spade_generators/sige_fused_spade_generator.py:160-198 — such a launch scatters through the
+        # module's own tile sets and always takes the un-fused form below)
+        main_real, sc_real = isinstance(co.src, RealStack), isinstance(sc.src, RealStack)
+        if not ((isinstance(co.src, Stack) or main_real) and (isinstance(sc.src, Stack) or sc_real)):
             return False
         mg, sg = m.main_gather.module, m.shortcut_gather.module
-        if not self._same_gather(co.src.gather, mg):
+
+        def real_ok(c, g):
+            return int(c.src.tensor.shape[2]) == int(g.block_size[0]) and g.block_size[0] == g.block_size[1] and g.tile_images is None
+
+        if (main_real and not real_ok(co, mg)) or (not main_real and not self._same_gather(co.src.gather, mg)):
             return False
-        if sc.src.gather is not sg or sc.k != 1 or sc.src.scale is not None or sc.src.shift is not None or sg.activation_name != "identity":
+        if sc_real:
+            if not real_ok(sc, sg):
+                return False
+        elif sc.src.gather is not sg or sc.k != 1 or sc.src.scale is not None or sc.src.shift is not None or sg.activation_name != "identity":
             return False
         cid = m.cache_id
         dst = self.cached(m.original_outputs[cid], mg.num_edits)
         skip = self.cached(m.original_residuals[cid], mg.num_edits)
         idx, off = mg.active_indices.to(self.dev), int(mg.offset[0])
         sidx, soff = sg.active_indices.to(self.dev), int(sg.offset[0])
-        sc_full: Full = sc.src.src
+        sc_full: Optional[Full] = None if sc_real else sc.src.src
         # the shortcut's active tiles must sit on the main conv's output-tile grid and be a subset of it: then evaluating the
         # shortcut on those main tiles (and adding the cached shortcut output elsewhere) IS the reference's
         # `out += fresh - cached` patch (sige/cuda/scatter_kernel.cu:46-74)
@@ -1460,7 +1471,7 @@ class Lowering:
             sc_key = sc_key + sg.tile_images.to(self.dev).long() * (width * width)
         subset = bool(torch.isin(sc_key, main_key).all()) and tuple(mg.block_stride) == tuple(sg.block_stride) == (4, 4) \
             and int(sg.block_size[0]) == 4 and int(mg.block_size[0]) == 6
-        fuse = (self.fuse_shortcut and self.tc5 and self.producer_preop and subset and co.k == 3 and co.stride == 1
+        fuse = (not main_real and not sc_real and self.fuse_shortcut and self.tc5 and self.producer_preop and subset and co.k == 3 and co.stride == 1
                 and all(up == 0 for _, up in sc_full.segs) and len(sc_full.segs) <= 2 and sc_full.plain
                 and int(sc.weight.shape[1]) % 64 == 0)
         name = self._module_name(node)
@@ -1478,8 +1489,8 @@ class Lowering:
             if not subset:
                 return False
             # un-fused: the shortcut's own launch refreshes its tiles of `skip`, then conv2 adds `skip` as the residual
-            self._tile_emit(node, sc, skip, name=name + ".shortcut")
-            self._tile_emit(node, co, dst, residual=skip, name=name)
+            self._tile_emit(node, sc, skip, name=name + ".shortcut", gather=sg if sc_real else None)
+            self._tile_emit(node, co, dst, residual=skip, name=name, gather=mg if main_real else None)
         self.env[id(node.outs[0])] = Full([(dst, 0)])
         return True
 
