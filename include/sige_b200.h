@@ -327,6 +327,16 @@ typedef struct {
 int sige_sparse_attention_supported(int D, int dtype);
 int sige_sparse_attention(const sige_sparse_attention_t *p, sige_stream_t stream);
 
+/* SPADE's modulation of a tile stack (or any channels-innermost tensor of `pixels` pixels), one launch:
+ *   out = act(x * (1 + gamma) + beta),  act = leaky_relu(negative_slope)  (negative_slope = 1: identity)
+ * — the four pointwise torch calls of reference gaugan/models/sige_normalization.py:84-86 plus the block's F.leaky_relu(., 0.2)
+ * (gaugan/models/spade_generators/sige_fused_spade_generator.py:200-201) on the gathered tiles.  Every operand has its own pixel
+ * stride in elements (gamma and beta are the channel halves of one [pixels, 2C] tensor); C and the strides multiples of one
+ * 16-byte vector, buffers 16-byte aligned; f32 / f16 / bf16; fp32 arithmetic. */
+int sige_spade_modulate(const void *x, long long x_pixel_stride, const void *gamma, long long gamma_pixel_stride,
+                        const void *beta, long long beta_pixel_stride, void *out, long long out_pixel_stride,
+                        long long pixels, int C, float negative_slope, int dtype, sige_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* diagnostics                                                                */
 /* ------------------------------------------------------------------------- */

@@ -118,6 +118,7 @@ PROTOTYPES = {
     "sige_attention_tokens": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "sige_sparse_attention_supported": (_I, [_I, _I]),
     "sige_sparse_attention": (_I, [POINTER(SparseAttention), _P]),
+    "sige_spade_modulate": (_I, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int64, _I, ctypes.c_float, _I, _P]),
     "sige_debug_set_trace": (_I, [_P]),
 }
 

@@ -446,6 +446,18 @@ class CudaExecutor:
 
         return run
 
+    def spade_supported(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> bool:
+        return self.ops.spade_modulate_supported(x, gamma, beta)
+
+    def prepare_spade(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, slope: float, out: torch.Tensor):
+        """out = leaky_relu(x * (1 + gamma) + beta, slope) as ONE launch (sige_spade_modulate); slope = 1: no activation."""
+        ops = self.ops
+
+        def run(_stream):
+            ops.spade_modulate(x, gamma, beta, slope, out=out)
+
+        return run
+
     def sparse_attention_supported(self, head_dim: int) -> bool:
         return self.ops.sparse_attention_supported(head_dim, self.dtype)
 
@@ -594,6 +606,16 @@ class HeadsOut:
         return self.full.view(self.b, self.n, self.h, self.d).permute(0, 2, 1, 3)
 
 
+class Spade:
+    """SPADE's modulation recognised on the tape (reference gaugan/models/sige_normalization.py:84-86 + the block's leaky_relu):
+    stage 1 = `1 + gamma`, 2 = `x * (1 + gamma)`, 3 = `x * (1 + gamma) + beta` (optionally followed by leaky_relu: `slope`).
+    Speculative: a consumer that wants an intermediate value simply gets the recorded call evaluated; only stage 3 materialises
+    as ONE `sige_spade_modulate` launch."""
+
+    def __init__(self, stage: int, gamma: LazyTensor, x: Optional[LazyTensor] = None, beta: Optional[LazyTensor] = None, slope: Optional[float] = None):
+        self.stage, self.gamma, self.x, self.beta, self.slope = stage, gamma, x, beta, slope
+
+
 _POINTWISE = {"add", "mul", "sub", "div", "rsub", "neg", "leaky_relu", "relu", "silu", "gelu", "sigmoid", "tanh", "clamp", "clamp_min", "abs"}
 _MATERIAL = (Full, Stack, RealStack, ConvOut, RealT)
 _VIEW_OPS = {"reshape", "view", "permute", "transpose", "chunk", "split", "__getitem__", "unsqueeze", "squeeze", "flatten", "unflatten",
@@ -673,6 +695,8 @@ class Lowering:
         # SD transformer cores on this repo's kernel (SIGE_SPARSE_ATTENTION=0: the cuDNN flash kernel through torch's SDPA, for A/B)
         self.sparse_attention = os.environ.get("SIGE_SPARSE_ATTENTION", "1") != "0"
         self.sparse_attention_calls = 0
+        self.spade = os.environ.get("SIGE_SPADE_FUSE", "1") != "0"       # SPADE modulation as one launch (0: recorded torch calls, for A/B)
+        self.spade_calls = 0
         self.steps: List[Tuple[str, Callable[[int], None]]] = []
         self.fused: List[FusedConv] = []
         self.conv_ins: List[ConvInRec] = []
@@ -1004,6 +1028,13 @@ class Lowering:
             return buf.raw
         if isinstance(v, Stack):
             return self.materialize_stack(lt, v)
+        if isinstance(v, Spade) and v.stage == 3:
+            t = self._materialize_spade(lt, v)
+            if t is not None:
+                return t
+            self.env.pop(id(lt), None)        # operands the kernel does not take: the recorded calls run as they are
+            self.eager(lt.node)
+            return self.runtime_tensor(lt)
         if isinstance(v, HeadsOut):           # a consumer other than einops' closing rearrange
             if v.stage == 2:
                 t = v.full.view(v.b, v.n, v.h, v.d)
@@ -1023,6 +1054,18 @@ class Lowering:
             raise TraceUnsupported("input without a binding")
         self.eager(lt.node)
         return self.runtime_tensor(lt)
+
+    def _materialize_spade(self, lt: LazyTensor, v: Spade) -> Optional[torch.Tensor]:
+        x, g, b = self.runtime_tensor(v.x), self.runtime_tensor(v.gamma), self.runtime_tensor(v.beta)
+        if not (x.dtype == g.dtype == b.dtype == self.dtype and tuple(x.shape) == tuple(g.shape) == tuple(b.shape) == tuple(lt.shape)
+                and self.ex.spade_supported(x, g, b)):
+            return None
+        out = torch.empty(tuple(lt.shape), dtype=self.dtype, device=self.dev, memory_format=torch.channels_last)
+        self.steps.append(("spade", self.ex.prepare_spade(x, g, b, 1.0 if v.slope is None else float(v.slope), out)))
+        self.spade_calls += 1
+        is_stack = isinstance(self.sym(v.x), RealStack)       # pointwise math on a tile stack yields a tile stack
+        self.env[id(lt)] = RealStack(out) if is_stack else RealT(out)
+        return out
 
     def materialize_full(self, lt: LazyTensor, f: Full) -> torch.Tensor:
         B, C = f.B, f.C
@@ -1543,6 +1586,11 @@ class Lowering:
                     self.env[id(out)] = GNVal(v.src, v.groups, v.weight, v.bias, v.eps, "swish")
                     return True
                 return False
+        for x_lt, s_ in ((a, sb), (b, sa)):       # x * (1 + gamma)
+            if (isinstance(s_, Spade) and s_.stage == 1 and isinstance(x_lt, LazyTensor) and x_lt.dim() == 4
+                    and tuple(x_lt.shape) == tuple(s_.gamma.shape) == tuple(out.shape)):
+                self.env[id(out)] = Spade(2, s_.gamma, x=x_lt)
+                return True
         for x, c in ((sa, b), (sb, a)):
             if isinstance(x, Scores) and isinstance(c, (int, float)):
                 self.env[id(out)] = Scores(x.q, x.k, x.scale * float(c))
@@ -1563,6 +1611,18 @@ class Lowering:
         if node.kwargs.get("alpha", 1) != 1 or len(node.args) > 2:
             return False
         out = node.outs[0]
+        if self.spade:
+            for t_, c_ in ((a, b), (b, a)):        # 1 + gamma on a value that has no symbolic form (a slice of a tile stack)
+                if (isinstance(t_, LazyTensor) and isinstance(c_, (int, float)) and float(c_) == 1.0 and t_.dim() == 4 and self.sym(t_) is None
+                        and tuple(t_.shape) == tuple(out.shape) and t_.dtype.is_floating_point):
+                    self.env[id(out)] = Spade(1, t_)
+                    return True
+            if isinstance(a, LazyTensor) and isinstance(b, LazyTensor):
+                for m_lt, b_lt in ((a, b), (b, a)):       # x * (1 + gamma) + beta
+                    sm = self.sym(m_lt)
+                    if isinstance(sm, Spade) and sm.stage == 2 and b_lt.dim() == 4 and tuple(b_lt.shape) == tuple(out.shape) == tuple(m_lt.shape):
+                        self.env[id(out)] = Spade(3, sm.gamma, x=sm.x, beta=b_lt)
+                        return True
         if isinstance(a, LazyTensor) and isinstance(b, LazyTensor):
             for x, r in ((a, b), (b, a)):
                 co = self.sym(x)
@@ -1595,6 +1655,14 @@ class Lowering:
         return True
 
     _h_radd = _h_add
+
+    def _h_leaky_relu(self, node: Node):
+        a = self._bind(node, ("input", "negative_slope", "inplace"), {"negative_slope": 0.01, "inplace": False})
+        v = self.sym(a["input"]) if isinstance(a["input"], LazyTensor) else None
+        if isinstance(v, Spade) and v.stage == 3 and v.slope is None and not a["inplace"] and self.n_uses(a["input"]) == 1:
+            self.env[id(node.outs[0])] = Spade(3, v.gamma, x=v.x, beta=v.beta, slope=float(a["negative_slope"]))
+            return True
+        return False
 
     def _h_sigmoid(self, node: Node):
         x = node.args[0]

@@ -574,3 +574,46 @@ def sparse_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: f
         _cabi.check(_cabi.lib().sige_sparse_attention(byref(d), _stream(q)), "sige_sparse_attention")
     _bump()
     return out
+
+
+def _pixel_rows(t: torch.Tensor):
+    """(pixels, C, pixel stride) of a channels-innermost 4-D tensor whose pixels are uniformly strided (an NHWC buffer / stack or a
+    channel slice of one); None otherwise."""
+    if t.dim() != 4 or t.numel() == 0 or t.stride(1) != 1:
+        return None
+    n, c, h, w = t.shape
+    ps = t.stride(3) if w > 1 else (t.stride(2) if h > 1 else t.stride(0))
+    if (w > 1 and h > 1 and t.stride(2) != ps * w) or ((h > 1 or w > 1) and n > 1 and t.stride(0) != ps * h * w):
+        return None
+    return n * h * w, c, int(ps)
+
+
+def spade_modulate_supported(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> bool:
+    if not (x.is_cuda and x.dtype == gamma.dtype == beta.dtype and x.dtype in (torch.float32, torch.float16, torch.bfloat16)
+            and tuple(x.shape) == tuple(gamma.shape) == tuple(beta.shape)):
+        return False
+    vec = 4 if x.dtype == torch.float32 else 8
+    for t in (x, gamma, beta):
+        r = _pixel_rows(t)
+        if r is None or r[1] % vec or r[2] % vec or t.data_ptr() % 16:
+            return False
+    return True
+
+
+def spade_modulate(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, negative_slope: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(x * (1 + gamma) + beta) on channels-innermost tensors (reference gaugan/models/sige_normalization.py:84-86 + the
+    block's leaky_relu); negative_slope = 1 is the identity.  Returns a channels-last tensor shaped like x."""
+    _require_cuda(x, gamma, beta, out)
+    if not spade_modulate_supported(x, gamma, beta):
+        raise ValueError("spade_modulate: operands must be same-shape, same-dtype, channels-innermost 4-D tensors with 16-byte channel vectors")
+    if out is None:
+        out = torch.empty(tuple(x.shape), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    ro = _pixel_rows(out)
+    if ro is None or tuple(out.shape) != tuple(x.shape) or out.dtype != x.dtype:
+        raise ValueError("spade_modulate: out must be a channels-innermost tensor with x's shape and dtype")
+    (px, c, xs), (_, _, gs), (_, _, bs) = _pixel_rows(x), _pixel_rows(gamma), _pixel_rows(beta)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().sige_spade_modulate(x.data_ptr(), xs, gamma.data_ptr(), gs, beta.data_ptr(), bs, out.data_ptr(), ro[2], px, c,
+                                                   float(negative_slope), _dt(x), _stream(x)), "sige_spade_modulate")
+    _bump()
+    return out

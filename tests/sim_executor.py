@@ -181,6 +181,17 @@ class SimExecutor:
 
         return run
 
+    def spade_supported(self, x, gamma, beta):
+        return True
+
+    def prepare_spade(self, x, gamma, beta, slope, out):
+        def run(_stream):
+            self.launches += 1
+            z = x.float() * (1 + gamma.float()) + beta.float()
+            out.copy_(torch.where(z > 0, z, z * slope))
+
+        return run
+
     def sparse_attention_supported(self, head_dim):
         return True
 

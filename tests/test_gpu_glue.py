@@ -157,3 +157,31 @@ def test_sparse_attention_strided_heads_and_empty():
     assert empty.shape == (b * h, 0, d)
     with pytest.raises(Exception):
         ops.sparse_attention(q3.half(), k3.half()[:, :, :32].contiguous(), v3.half(), d ** -0.5)      # head dims differ
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.float16, 1e-3), (torch.bfloat16, 8e-3)])
+def test_spade_modulate_matches_torch(dtype, tol):
+    """sige_spade_modulate = act(x * (1 + gamma) + beta) (reference gaugan/models/sige_normalization.py:84-86 + the block's
+    leaky_relu) vs plain fp32 torch on the same operands: NHWC tile stacks, gamma / beta as the channel halves of one stack
+    (torch.split views, pixel stride 2C), with and without the activation, an NHWC full tensor, and the refusal of NCHW operands."""
+    from sige_b200 import ops
+
+    torch.manual_seed(3)
+    for (N, C, R) in [(300, 128, 6), (7, 64, 4), (1, 256, 6), (33, 32, 5)]:
+        x = torch.randn(N, C, R, R, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+        gb = (0.5 * torch.randn(N, 2 * C, R, R, device=DEV)).to(dtype).contiguous(memory_format=torch.channels_last)
+        gamma, beta = torch.split(gb, C, dim=1)
+        for slope in (1.0, 0.2):
+            want = x.float() * (1 + gamma.float()) + beta.float()
+            want = torch.where(want > 0, want, want * slope)
+            got = ops.spade_modulate(x, gamma, beta, slope)
+            assert got.shape == x.shape and got.dtype == dtype and got.is_contiguous(memory_format=torch.channels_last)
+            assert float((got.float() - want).abs().max() / want.abs().max()) <= tol
+    full = torch.randn(2, 64, 16, 24, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    got = ops.spade_modulate(full, full, full, 1.0)
+    want = full.float() * (1 + full.float()) + full.float()
+    assert float((got.float() - want).abs().max() / want.abs().max()) <= tol
+    nchw = torch.randn(4, 64, 6, 6, device=DEV).to(dtype)
+    assert not ops.spade_modulate_supported(nchw, nchw, nchw)
+    with pytest.raises(ValueError):
+        ops.spade_modulate(nchw, nchw, nchw)
