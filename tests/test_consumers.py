@@ -59,6 +59,34 @@ def test_consumer_forward_traces_and_lowers_exactly(which):
 
 
 @needs_ref
+def test_spade_modulation_lowers_to_one_launch_and_falls_back_to_the_recorded_calls():
+    """GauGAN: `normalized * (1 + gamma) + beta -> leaky_relu` on the tile stacks (reference gaugan/models/sige_normalization.py:84-86)
+    is recognised on the tape and goes out as `sige_spade_modulate` launches; when the kernel refuses the operands (NCHW stacks out
+    of an operator-module fallback on the GPU) the recorded torch calls run instead — same result either way."""
+    from oracle.cpu_runtime import reference_cpu_runtime
+    from sige_b200.fused import FusedStep
+    from sim_executor import SimExecutor
+
+    class NoSpade(SimExecutor):
+        def spade_supported(self, x, gamma, beta):
+            return False
+
+    net, G, run = _build("gaugan")
+    with reference_cpu_runtime():
+        run("cpu", lambda n: n.set_fused(False))
+        args = (consumers.gaugan_inputs()[1],)
+        with torch.no_grad():
+            fused = FusedStep(net, *args, executor=SimExecutor())
+            plain = FusedStep(net, *args, executor=NoSpade())
+    kinds = [k for k, _ in fused.steps]
+    assert kinds.count("spade") >= 8 and fused.eager_nodes.count("leaky_relu") < plain.eager_nodes.count("leaky_relu")
+    assert [k for k, _ in plain.steps].count("spade") == 0
+    scale = np.abs(G["sparse1"]).max()
+    assert np.abs(fused.output.numpy() - G["sparse1"]).max() <= 2e-5 * scale
+    assert np.abs(plain.output.numpy() - G["sparse1"]).max() <= 2e-5 * scale
+
+
+@needs_ref
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["sd", "gaugan"])
 def test_consumer_on_gpu_modules_fp32_and_fused_fp16(which):
