@@ -634,7 +634,8 @@ def run_consumer(args):
         "metric": "%s sparse steps/sec" % args.workload, "value": 1e3 / ms_fused, "unit": "steps/s", "n_gpus": 1, "ms_per_step": ms_fused,
         "higher_is_better": True, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic (random-init weights)",
         "config": {"workload": name, "model_file": "the reference's unmodified model file (baseline/_ref) on this repo's sige.nn",
-                   "path": "model(...) as a fused step: %d fused conv launches + %d recorded torch calls in one CUDA graph" % (len(step.fused), len(step.eager_nodes)) if step else "eager"},
+                   "path": ("model(...) as a fused step: %d fused conv launches + %d sige_sparse_attention + %d sige_spade_modulate launches + %d recorded torch calls in one CUDA graph"
+                            % (len(step.fused), step.low.sparse_attention_calls, step.low.spade_calls, len(step.eager_nodes))) if step else "eager"},
         "eager_fp32_modules_ms_per_step": ms_mod,
         "reference_cuda_ms_per_step": None if ref is None else ref[0]["ms_per_step"],
         "speedup_vs_reference_cuda": None if ref is None else ref[0]["ms_per_step"] / ms_fused,
