@@ -391,9 +391,13 @@ def run_ours(args):
         if distributed:
             from sige_b200.parallel import broadcast_caches
 
+            torch.cuda.synchronize()
+            t_b = time.perf_counter()
             nbytes = broadcast_caches(model, src=0)
+            torch.cuda.synchronize()
+            bcast_ms = 1e3 * (time.perf_counter() - t_b)     # one-off, outside the per-step path: reported, not part of `value`
         else:
-            nbytes = 0
+            nbytes, bcast_ms = 0, 0.0
         if n_edits == 1:
             model.set_masks(downsample_mask(edit_masks[0].to(dev), min_res=8))
         else:
@@ -546,7 +550,7 @@ def run_ours(args):
                 "workload": workload_name(args.ratio), "model_file": model_label,
                 "path": path + (" (model(x, t) -> SIGEModel fused step: traced, lowered, CUDA graph; fp32 model + fp32 I/O, %s arithmetic)" % args.dtype if path == "fused" else ""),
                 "edits_per_gpu": n_edits, "total_edits": n_edits * world,
-                "parallelism": "edits sharded %d/GPU (batched in one fused step), caches broadcast once (%d bytes), no per-step collective" % (n_edits, nbytes),
+                "parallelism": "edits sharded %d/GPU (batched in one fused step), caches broadcast once (%d bytes, %.1f ms over NCCL, outside the timed region), no per-step collective" % (n_edits, nbytes, bcast_ms),
                 "l2": "flushed (256 MiB write) between timed steps" if flush is not None else "not flushed",
                 "timing": "per-step CUDA events on the launching stream, max over ranks",
             },
