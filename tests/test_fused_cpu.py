@@ -265,3 +265,35 @@ def test_new_masks_are_installed_without_recompiling():
         _, _, mask_c, _ = synthetic_inputs(cfg, 0.20, seed=0)
         model.set_masks(downsample_mask(mask_c, min_res=8))
         assert not step.rebind()
+
+
+def test_device_side_install_of_a_tile_list_pads_truncates_and_flags_overflow():
+    """`IdxSlot.install_device` (the sync-free `set_masks_async` path) is plain tensor arithmetic: the first min(count, capacity)
+    origins of the reduction, SIGE_TILE_NONE behind them, bit 0 of the status word when the list did not fit — checked here
+    on CPU tensors against the host-side `reload`."""
+    from types import SimpleNamespace
+
+    from sige_b200._cabi import TILE_NONE
+    from sige_b200.fused import IdxSlot
+
+    first = torch.tensor([[0, 0], [0, 4], [4, 8], [8, 8], [12, 0]], dtype=torch.int32)
+    g = SimpleNamespace(active_indices=first, tile_images=None)
+    sl = IdxSlot(g, torch.device("cpu"), headroom=0.6)
+    assert sl.cap == 8 and sl.n == 5 and bool((sl.buf[5:] == TILE_NONE).all())
+    cand = torch.arange(40, dtype=torch.int32).view(20, 2)             # what sige_reduce_mask leaves: `count` real rows, garbage behind
+    status = torch.zeros(1, dtype=torch.int32)
+    sl.install_device(cand, torch.tensor([3], dtype=torch.int32), status)
+    assert torch.equal(sl.buf[:3], cand[:3]) and bool((sl.buf[3:] == TILE_NONE).all()) and int(status) == 0
+    sl.install_device(cand, torch.tensor([8], dtype=torch.int32), status)       # exactly full
+    assert torch.equal(sl.buf, cand[:8]) and int(status) == 0
+    sl.install_device(cand, torch.tensor([0], dtype=torch.int32), status)       # no active tile: every entry is padding
+    assert bool((sl.buf == TILE_NONE).all()) and int(status) == 0
+    sl.install_device(cand, torch.tensor([13], dtype=torch.int32), status)      # does not fit: truncated AND reported
+    assert torch.equal(sl.buf, cand[:8]) and int(status) & 1
+    short = cand[:5]                                                             # fewer candidate rows than the capacity
+    status.zero_()
+    sl.install_device(short, torch.tensor([5], dtype=torch.int32), status)
+    assert torch.equal(sl.buf[:5], short) and bool((sl.buf[5:] == TILE_NONE).all()) and int(status) == 0
+    g.active_indices = first[:2]
+    sl.reload()                                                                  # the synchronous path resets the host-side count
+    assert sl.n == 2 and torch.equal(sl.buf[:2], first[:2]) and bool((sl.buf[2:] == TILE_NONE).all())
